@@ -1,0 +1,199 @@
+/* rr_b200.h -- C ABI of the B200-native hybrid-retrieval hot path.
+ *
+ * The reference (Ntropy86/review-recommender) is pure Python and has no FFI of its own; the
+ * seam this library replaces is the set of Python functions listed below.  Each entry point
+ * names the reference interface it stands behind (paths relative to the reference root).
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is either a HOST pointer (prefix h_) or a DEVICE
+ *     pointer (prefix d_) and is documented as such;
+ *   - every call returns 0 on success or a negative RR_E* code and never throws, aborts or
+ *     falls back to a CPU implementation; rr_last_error() gives the thread-local message;
+ *   - the index handle BORROWS the device buffers named in rr_index_desc (the caller -- torch
+ *     tensors in the shipped host code -- owns them and must keep them alive); the handle owns
+ *     only its internal scratch;
+ *   - calls on one handle are serialised by an internal mutex (Streamlit runs sessions on
+ *     several threads against one cached index, app/app_product_search.py:53,71,119);
+ *   - work is enqueued on the caller's stream; *_host entry points synchronise that stream
+ *     before returning, device-pointer entry points do not.
+ */
+#ifndef RR_B200_H
+#define RR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RR_OK              0
+#define RR_EINVAL         -1   /* bad argument */
+#define RR_ECUDA          -2   /* CUDA runtime error (message has the CUDA string) */
+#define RR_ENOMEM         -3
+#define RR_EUNSUPPORTED   -4   /* e.g. tensor path asked for but no bf16 copy / not sm_100 */
+#define RR_EOVERFLOW      -5
+
+typedef struct rr_index rr_index;
+typedef struct rr_postings rr_postings;
+typedef void* rr_stream;       /* cudaStream_t */
+
+const char* rr_last_error(void);
+int rr_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-side BM25 index construction.
+ * Replaces rank_bm25.BM25Okapi.__init__ as called at app/test.py:156 and
+ * app/app_product_search.py:142 (corpus = blob["corpus"] of product_bm25.pkl,
+ * nlp/12_product_prep.py:85-88), k1=1.5 b=0.75 epsilon=0.25.
+ * The corpus is passed flat: h_doc_offsets int64[n_docs+1], h_token_ids int32[total], term ids
+ * in [0, vocab_size).  Three steps so that a row-sharded build can all-reduce the statistics:
+ * ---------------------------------------------------------------------------------------- */
+
+/* df[t] += number of local docs containing t; first_pos[t] = min(global flat position of the
+ * first occurrence of t) -- the dict insertion order rank_bm25 sums idf in.  The caller
+ * initialises h_df to 0 and h_first_pos to INT64_MAX.  token_pos0 = global flat index of this
+ * shard's first token. */
+int rr_bm25_local_stats(const int64_t* h_doc_offsets, const int32_t* h_token_ids, int64_t n_docs,
+                        int32_t vocab_size, int64_t token_pos0,
+                        int64_t* h_df, int64_t* h_first_pos, int64_t* h_total_tokens);
+
+/* idf[t] = ln(N-df+.5) - ln(df+.5); negatives floored to epsilon*mean(idf) (mean over all
+ * present terms, summed in first_pos order); absent terms get 0. */
+int rr_bm25_idf(const int64_t* h_df, const int64_t* h_first_pos, int32_t vocab_size,
+                int64_t corpus_size, double epsilon, double* h_idf, double* h_average_idf);
+
+/* Tile-blocked CSR postings of the local docs with per-posting fp32 impact
+ *   impact = (float)( idf[t] * ( tf*(k1+1) / (tf + k1*(1 - b + b*len/avgdl)) ) )   (float64 math)
+ * Layout: docs are cut into tiles of tile_docs; inside a tile postings are
+ * grouped by term, doc-ascending.  posting = {uint32 local doc, float impact}. */
+int rr_bm25_build_postings(const int64_t* h_doc_offsets, const int32_t* h_token_ids, int64_t n_docs,
+                           int32_t vocab_size, const double* h_idf, double avgdl, double k1, double b,
+                           int32_t tile_docs, int32_t n_threads, rr_postings** out);
+int64_t         rr_postings_nnz(const rr_postings*);        /* entries incl. alignment padding */
+int32_t         rr_postings_n_tiles(const rr_postings*);
+const uint64_t* rr_postings_data(const rr_postings*);       /* host, nnz x {u32 doc, f32 impact} */
+const uint64_t* rr_postings_tile_base(const rr_postings*);  /* host, n_tiles+1 */
+const uint32_t* rr_postings_blk_off(const rr_postings*);    /* host, n_tiles*(vocab_size+1) */
+void            rr_postings_free(rr_postings*);
+
+/* ------------------------------------------------------------------------------------------
+ * Device index
+ * ---------------------------------------------------------------------------------------- */
+typedef struct rr_index_desc {
+    int64_t n_docs;              /* rows of this shard */
+    int64_t row_offset;          /* global row of local row 0 (row-sharded corpus) */
+    int32_t dim;                 /* D */
+    int32_t dim_pad;             /* row length of d_emb_bf16 (multiple of 64) or 0 */
+    const float*    d_emb_f32;   /* [n_docs, dim] row-major; the reference's Vn (app/app_product_search.py:110) */
+    const uint16_t* d_emb_bf16;  /* [n_docs, dim_pad] round-to-nearest bf16 copy, or NULL (exact path only) */
+    float   max_row_norm;        /* max ||row||_2, used for the bf16 error bound */
+    int32_t vocab_size;          /* 0 = no BM25 index ("BM25 absent": zeros, app/app_product_search.py:202) */
+    int32_t tile_docs;
+    int32_t n_tiles;
+    const uint64_t* d_postings;  /* as rr_postings_data */
+    const uint64_t* d_tile_base;
+    const uint32_t* d_blk_off;
+    const double*   d_n_reviews; /* [n_docs] n_reviews with NaN already mapped to 0 (:264), or NULL */
+    const double*   d_avg_stars; /* [n_docs] avg_stars, NaN allowed (:265), or NULL */
+} rr_index_desc;
+
+int  rr_index_create(rr_index** out, const rr_index_desc* desc, int device);
+void rr_index_destroy(rr_index*);
+
+/* ------------------------------------------------------------------------------------------
+ * Hot path, device pointers.  B = queries in the batch.
+ * ---------------------------------------------------------------------------------------- */
+
+/* rank_bm25.BM25Okapi.get_scores (app/test.py:170, app/app_product_search.py:206), batched:
+ * d_out[b, doc] = sum over the query's term list (duplicates counted) of impact(term, doc).
+ * d_term_ids int32[B, l_max] (ids <0 or >=V are "unknown": contribute 0), d_n_terms int32[B].
+ * d_out float[B, ld_out], ld_out >= n_docs and a multiple of 4. */
+int rr_bm25_get_scores(rr_index*, const int32_t* d_term_ids, const int32_t* d_n_terms, int32_t B,
+                       int32_t l_max, float* d_out, int64_t ld_out, rr_stream);
+
+/* The gather half of bm25_scores (app/test.py:168-173) / _bm25_for_candidates
+ * (app/app_product_search.py:201-208) without materialising N scores: BM25 of the given
+ * candidate rows only, bit-identical to rr_bm25_get_scores at those rows.
+ * d_cand int64[B, pool] local rows (<0 = no candidate -> 0). */
+int rr_bm25_candidates(rr_index*, const int32_t* d_term_ids, const int32_t* d_n_terms, int32_t B,
+                       int32_t l_max, const int64_t* d_cand, int32_t pool, float* d_out, rr_stream);
+
+/* cosine_similarity_search utils.py:111-124 (= cosine_search app/test.py:125-132, _cosine_pool
+ * app/app_product_search.py:192-195), batched: for each query the `pool` rows of largest
+ * fp32 dot product, ordered (similarity desc, row asc).  d_q float[B, dim].
+ * mode: RR_DENSE_AUTO | RR_DENSE_EXACT (fp32 everywhere) | RR_DENSE_TENSOR (bf16 tcgen05
+ * shortlist + exact fp32 rescoring + certification; uncertified queries are redone exactly).
+ * d_idx int64[B, pool] local rows (-1 past the end when pool > n_docs), d_sims float[B, pool],
+ * d_count int32[B] = min(pool, n_docs). */
+#define RR_DENSE_AUTO   0
+#define RR_DENSE_EXACT  1
+#define RR_DENSE_TENSOR 2
+int rr_dense_topk(rr_index*, const float* d_q, int32_t B, int32_t pool, int32_t mode,
+                  int64_t* d_idx, float* d_sims, int32_t* d_count, rr_stream);
+
+/* Candidate tuples for fusion: BM25 at the candidates plus their metadata and global rows.
+ * Output arrays are [B, pool]. */
+int rr_candidate_tuples(rr_index*, const int32_t* d_term_ids, const int32_t* d_n_terms, int32_t B,
+                        int32_t l_max, const int64_t* d_cand, int32_t pool,
+                        float* d_bm25, double* d_n_reviews, double* d_avg_stars, int64_t* d_global_row,
+                        rr_stream);
+
+/* Fusion + selection: app/app_product_search.py:256-312 (use_trust=1) and app/test.py:252-309
+ * (use_trust=0) on candidate tuples.  Inputs are [B, n_in]; per query the first d_count[b]
+ * entries are valid.  They are first ordered by (dense desc, global row asc) and cut to `pool`
+ * (this is the cross-shard merge when n_in = n_shards*pool), then normalised, blended and
+ * sorted by (final desc, pool position asc).
+ * Optional per-candidate inputs (NULL = absent): d_rerank (already min-max normalised, in pool
+ * order -- only meaningful when n_in == pool), d_best, d_gate.
+ * Outputs: d_top_row int64[B, k] global rows (-1 padding), d_top_final float[B, k],
+ * d_top_pos int32[B, k] pool positions; d_components float[B, pool, 8] or NULL:
+ * {dense_mm, bm25_mm, prior, trust, final, dense_raw, bm25_raw, (float)global_row_low}. */
+typedef struct rr_fusion_params {
+    double w_dense, w_bm25, w_rerank, w_prior, w_best;
+    double prior_C;
+    int32_t min_reviews;
+    int32_t saturation;      /* 80 in run_search (:303) */
+    int32_t use_trust;       /* 1 = Streamlit driver, 0 = CLI driver */
+    int32_t rerank_is_f32;   /* 1 when rerank_k > 0 (column is float32), 0 = the float64 `0.0` column */
+    int32_t bm25_is_f64_zero;/* 1 = CLI without BM25 (`cand["_bm25"] = 0.0`, app/test.py:252) */
+    int32_t k;
+    int32_t pool;
+} rr_fusion_params;
+
+int rr_fuse_topk(const rr_fusion_params*, int32_t B, int32_t n_in, const int32_t* d_count,
+                 const float* d_dense, const float* d_bm25, const double* d_n_reviews,
+                 const double* d_avg_stars, const int64_t* d_global_row,
+                 const float* d_rerank, const float* d_best, const float* d_gate,
+                 int64_t* d_top_row, float* d_top_final, int32_t* d_top_pos, float* d_components,
+                 int device, rr_stream);
+
+/* One-shot single-shard search (rerank/best/gate absent): dense top-pool -> tuples -> fuse. */
+int rr_hybrid_search(rr_index*, const float* d_q, const int32_t* d_term_ids, const int32_t* d_n_terms,
+                     int32_t B, int32_t l_max, const rr_fusion_params*, int32_t dense_mode,
+                     int64_t* d_top_row, float* d_top_final, rr_stream);
+
+/* Same, HOST buffers in and out (pinned or pageable); copies are issued on the stream inside
+ * the call and the stream is synchronised before returning.  This is the call the reference's
+ * search functions make through the Python binding. */
+int rr_hybrid_search_host(rr_index*, const float* h_q, const int32_t* h_term_ids, const int32_t* h_n_terms,
+                          int32_t B, int32_t l_max, const rr_fusion_params*, int32_t dense_mode,
+                          int64_t* h_top_row, float* h_top_final, rr_stream);
+
+/* Counters for bench.py: number of kernels this library launched since the last reset, and
+ * diagnostics of the last rr_dense_topk on this handle. */
+int64_t rr_launch_count(int reset);
+typedef struct rr_dense_stats {
+    int32_t path;            /* 1 exact, 2 tensor */
+    int32_t n_uncertified;   /* queries redone on the exact path */
+    int32_t n_overflow;      /* queries whose candidate buffer overflowed */
+    int32_t shortlist;       /* k' */
+    int32_t n_segments;
+    float   eps;             /* bf16 score error bound used for certification */
+} rr_dense_stats;
+int rr_dense_last_stats(rr_index*, rr_dense_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RR_B200_H */

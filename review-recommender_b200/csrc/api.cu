@@ -1,0 +1,325 @@
+// C ABI of librr_b200.so: handle management, scratch, and the call sequences of the hot path.
+// See include/rr_b200.h for the contract of every entry point.
+#include "rr_internal.h"
+#include "rr_kernels.h"
+#include "dense_tc.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+// ---------------------------------------------------------------------------------------------
+// errors / counters
+// ---------------------------------------------------------------------------------------------
+static thread_local char t_err[512] = "";
+std::atomic<int64_t> g_rr_launches{0};
+
+int rr_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char* rr_last_error(void) { return t_err; }
+extern "C" int rr_abi_version(void) { return 1; }
+extern "C" int64_t rr_launch_count(int reset) {
+    return reset ? g_rr_launches.exchange(0) : g_rr_launches.load();
+}
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct DeviceBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return RR_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        const size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return rr_fail(RR_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
+        cap = want;
+        return RR_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct rr_index {
+    rr_index_desc d;
+    int device = 0;
+    int sm_count = 148;
+    int cc_major = 0, cc_minor = 0;
+    std::mutex mu;
+    DeviceBuf scores;     // exact path: [Bchunk, ld] fp32
+    DeviceBuf select;     // radix-select state
+    DeviceBuf tuples;     // hybrid: candidate tuples
+    DeviceBuf staging;    // *_host entry points
+    rr_tc_state* tc = nullptr;
+    rr_dense_stats stats{};
+};
+
+namespace {
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Carver {
+    char* p;
+    template <class T> T* take(size_t n) {
+        T* r = reinterpret_cast<T*>(p);
+        p += align_up(sizeof(T) * n, 256);
+        return r;
+    }
+};
+}  // namespace
+
+extern "C" int rr_index_create(rr_index** out, const rr_index_desc* desc, int device) {
+    if (!out || !desc) return rr_fail(RR_EINVAL, "rr_index_create: null argument");
+    if (desc->n_docs <= 0 || desc->dim <= 0 || !desc->d_emb_f32)
+        return rr_fail(RR_EINVAL, "rr_index_create: n_docs, dim and d_emb_f32 are required");
+    if (desc->n_docs > 0xFFFFFFF0ll) return rr_fail(RR_EINVAL, "rr_index_create: more than 2^32 rows per shard");
+    if (desc->d_emb_bf16 && (desc->dim_pad < desc->dim || desc->dim_pad % 64))
+        return rr_fail(RR_EINVAL, "rr_index_create: dim_pad must be a multiple of 64 and >= dim");
+    if (desc->vocab_size > 0) {
+        if (!desc->d_postings || !desc->d_tile_base || !desc->d_blk_off || desc->tile_docs <= 0 || (desc->tile_docs & 3) ||
+            desc->n_tiles != (int32_t)((desc->n_docs + desc->tile_docs - 1) / desc->tile_docs))
+            return rr_fail(RR_EINVAL, "rr_index_create: inconsistent BM25 postings description");
+        if ((size_t)desc->tile_docs * 4 > 200 * 1024)
+            return rr_fail(RR_EINVAL, "rr_index_create: tile_docs too large for shared-memory accumulators");
+    }
+    RR_CUDA(cudaSetDevice(device));
+    rr_index* ix = new (std::nothrow) rr_index();
+    if (!ix) return rr_fail(RR_ENOMEM, "rr_index_create: out of host memory");
+    ix->d = *desc;
+    ix->device = device;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete ix; return rr_fail(RR_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    ix->sm_count = prop.multiProcessorCount;
+    ix->cc_major = prop.major;
+    ix->cc_minor = prop.minor;
+    *out = ix;
+    return RR_OK;
+}
+
+extern "C" void rr_index_destroy(rr_index* ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    ix->scores.release();
+    ix->select.release();
+    ix->tuples.release();
+    ix->staging.release();
+    rr_tc_destroy(ix->tc);
+    delete ix;
+}
+
+extern "C" int rr_dense_last_stats(rr_index* ix, rr_dense_stats* out) {
+    if (!ix || !out) return rr_fail(RR_EINVAL, "rr_dense_last_stats: null argument");
+    *out = ix->stats;
+    return RR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BM25
+// ---------------------------------------------------------------------------------------------
+extern "C" int rr_bm25_get_scores(rr_index* ix, const int32_t* d_term_ids, const int32_t* d_n_terms, int32_t B,
+                                  int32_t l_max, float* d_out, int64_t ld_out, rr_stream stream) {
+    if (!ix || !d_out || B < 0 || l_max < 0) return rr_fail(RR_EINVAL, "rr_bm25_get_scores: bad argument");
+    if (ld_out < ix->d.n_docs || (ld_out & 3) || (reinterpret_cast<uintptr_t>(d_out) & 15))
+        return rr_fail(RR_EINVAL, "rr_bm25_get_scores: ld_out must be >= n_docs and a multiple of 4, d_out 16-byte aligned");
+    if (B == 0) return RR_OK;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    RR_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (ix->d.vocab_size <= 0 || l_max == 0 || !d_term_ids || !d_n_terms) {
+        // "BM25 absent" / no tokens -> zeros (app/app_product_search.py:202-204)
+        RR_CUDA(cudaMemset2DAsync(d_out, sizeof(float) * (size_t)ld_out, 0, sizeof(float) * (size_t)ix->d.n_docs, (size_t)B, s));
+        return RR_OK;
+    }
+    return rr_launch_bm25_tile_scores(ix->d.d_postings, ix->d.d_tile_base, ix->d.d_blk_off, ix->d.vocab_size,
+                                      ix->d.tile_docs, ix->d.n_tiles, ix->d.n_docs, d_term_ids, d_n_terms, B, l_max,
+                                      d_out, ld_out, s);
+}
+
+static int candidates_locked(rr_index* ix, const int32_t* d_term_ids, const int32_t* d_n_terms, int32_t B,
+                             int32_t l_max, const int64_t* d_cand, int32_t pool, float* d_bm25, double* d_n,
+                             double* d_avg, int64_t* d_grow, cudaStream_t s) {
+    const bool have = ix->d.vocab_size > 0 && l_max > 0 && d_term_ids && d_n_terms;
+    return rr_launch_bm25_candidates(ix->d.d_postings, ix->d.d_tile_base, ix->d.d_blk_off,
+                                     have ? ix->d.vocab_size : 0, std::max(ix->d.tile_docs, 1), ix->d.n_docs,
+                                     have ? d_term_ids : nullptr, d_n_terms, B, l_max, d_cand, pool, ix->d.d_n_reviews,
+                                     ix->d.d_avg_stars, ix->d.row_offset, d_bm25, d_n, d_avg, d_grow, s);
+}
+
+extern "C" int rr_bm25_candidates(rr_index* ix, const int32_t* d_term_ids, const int32_t* d_n_terms, int32_t B,
+                                  int32_t l_max, const int64_t* d_cand, int32_t pool, float* d_out, rr_stream stream) {
+    if (!ix || !d_cand || !d_out || B < 0 || pool <= 0) return rr_fail(RR_EINVAL, "rr_bm25_candidates: bad argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    RR_CUDA(cudaSetDevice(ix->device));
+    return candidates_locked(ix, d_term_ids, d_n_terms, B, l_max, d_cand, pool, d_out, nullptr, nullptr, nullptr,
+                             static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rr_candidate_tuples(rr_index* ix, const int32_t* d_term_ids, const int32_t* d_n_terms, int32_t B,
+                                   int32_t l_max, const int64_t* d_cand, int32_t pool, float* d_bm25,
+                                   double* d_n_reviews, double* d_avg_stars, int64_t* d_global_row, rr_stream stream) {
+    if (!ix || !d_cand || B < 0 || pool <= 0) return rr_fail(RR_EINVAL, "rr_candidate_tuples: bad argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    RR_CUDA(cudaSetDevice(ix->device));
+    return candidates_locked(ix, d_term_ids, d_n_terms, B, l_max, d_cand, pool, d_bm25, d_n_reviews, d_avg_stars,
+                             d_global_row, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense
+// ---------------------------------------------------------------------------------------------
+static int dense_exact_locked(rr_index* ix, const float* d_q, int32_t B, int32_t pool, int64_t* d_idx,
+                              float* d_sims, int32_t* d_count, cudaStream_t s) {
+    const int64_t n = ix->d.n_docs;
+    const int64_t ld = (int64_t)align_up((size_t)n, 4);
+    const size_t budget = (size_t)1 << 30;
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>(64, budget / (sizeof(float) * (size_t)ld)));
+    chunk = std::min(chunk, B);
+    if (chunk > 8) chunk = chunk / 8 * 8;
+    RR_TRY(ix->scores.ensure(sizeof(float) * (size_t)ld * chunk));
+    RR_TRY(ix->select.ensure(rr_exact_scratch_bytes(chunk, std::min<int64_t>(pool, n))));
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = std::min(chunk, B - b0);
+        RR_TRY(rr_launch_dense_scores_f32(ix->d.d_emb_f32, n, ix->d.dim, d_q + (int64_t)b0 * ix->d.dim, nb,
+                                          static_cast<float*>(ix->scores.p), ld, ix->sm_count, s));
+        RR_TRY(rr_launch_topk_rows(static_cast<const float*>(ix->scores.p), ld, n, nb, pool, ix->select.p,
+                                   d_idx + (int64_t)b0 * pool, d_sims + (int64_t)b0 * pool,
+                                   d_count ? d_count + b0 : nullptr, pool, ix->sm_count, s));
+    }
+    return RR_OK;
+}
+
+static int dense_topk_locked(rr_index* ix, const float* d_q, int32_t B, int32_t pool, int32_t mode,
+                             int64_t* d_idx, float* d_sims, int32_t* d_count, cudaStream_t s) {
+    if (mode == RR_DENSE_AUTO) {
+        const bool tc_ok = rr_tc_supported(ix->cc_major, ix->cc_minor) && ix->d.d_emb_bf16 != nullptr;
+        mode = (tc_ok && B >= 32 && ix->d.n_docs >= 65536 && pool <= 1024) ? RR_DENSE_TENSOR : RR_DENSE_EXACT;
+    }
+    if (mode == RR_DENSE_TENSOR) {
+        if (!ix->d.d_emb_bf16) return rr_fail(RR_EUNSUPPORTED, "tensor path needs the bf16 corpus copy (d_emb_bf16)");
+        if (!rr_tc_supported(ix->cc_major, ix->cc_minor))
+            return rr_fail(RR_EUNSUPPORTED, "tensor path needs an sm_100 device (found sm_%d%d)", ix->cc_major, ix->cc_minor);
+        return rr_tc_dense_topk(&ix->tc, &ix->d, ix->sm_count, d_q, B, pool, d_idx, d_sims, d_count, &ix->stats,
+                                [](void* ctx, const float* q, int32_t b, int32_t p, int64_t* idx, float* sims, int32_t* cnt,
+                                   cudaStream_t st) {
+                                    return dense_exact_locked(static_cast<rr_index*>(ctx), q, b, p, idx, sims, cnt, st);
+                                },
+                                ix, s);
+    }
+    if (mode != RR_DENSE_EXACT) return rr_fail(RR_EINVAL, "rr_dense_topk: unknown mode %d", mode);
+    ix->stats = rr_dense_stats{};
+    ix->stats.path = 1;
+    return dense_exact_locked(ix, d_q, B, pool, d_idx, d_sims, d_count, s);
+}
+
+extern "C" int rr_dense_topk(rr_index* ix, const float* d_q, int32_t B, int32_t pool, int32_t mode,
+                             int64_t* d_idx, float* d_sims, int32_t* d_count, rr_stream stream) {
+    if (!ix || !d_q || !d_idx || !d_sims || B < 0 || pool <= 0) return rr_fail(RR_EINVAL, "rr_dense_topk: bad argument");
+    if (pool > 8192) return rr_fail(RR_EINVAL, "rr_dense_topk: pool larger than 8192 is not supported");
+    if (B == 0) return RR_OK;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    RR_CUDA(cudaSetDevice(ix->device));
+    return dense_topk_locked(ix, d_q, B, pool, mode, d_idx, d_sims, d_count, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// fusion
+// ---------------------------------------------------------------------------------------------
+extern "C" int rr_fuse_topk(const rr_fusion_params* p, int32_t B, int32_t n_in, const int32_t* d_count,
+                            const float* d_dense, const float* d_bm25, const double* d_n_reviews,
+                            const double* d_avg_stars, const int64_t* d_global_row, const float* d_rerank,
+                            const float* d_best, const float* d_gate, int64_t* d_top_row, float* d_top_final,
+                            int32_t* d_top_pos, float* d_components, int device, rr_stream stream) {
+    RR_CUDA(cudaSetDevice(device));
+    return rr_launch_fuse(p, B, n_in, d_count, d_dense, d_bm25, d_n_reviews, d_avg_stars, d_global_row, d_rerank,
+                          d_best, d_gate, d_top_row, d_top_final, d_top_pos, d_components,
+                          static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// one-shot hybrid search
+// ---------------------------------------------------------------------------------------------
+static int hybrid_locked(rr_index* ix, const float* d_q, const int32_t* d_term_ids, const int32_t* d_n_terms,
+                         int32_t B, int32_t l_max, const rr_fusion_params* fp, int32_t dense_mode,
+                         int64_t* d_top_row, float* d_top_final, cudaStream_t s) {
+    const int pool = fp->pool;
+    const size_t bp = (size_t)B * pool;
+    size_t bytes = 0;
+    bytes += align_up(sizeof(int64_t) * bp, 256) * 2;   // cand, grow
+    bytes += align_up(sizeof(float) * bp, 256) * 2;     // dense, bm25
+    bytes += align_up(sizeof(double) * bp, 256) * 2;    // n, avg
+    bytes += align_up(sizeof(int32_t) * (size_t)B, 256);
+    RR_TRY(ix->tuples.ensure(bytes));
+    Carver c{static_cast<char*>(ix->tuples.p)};
+    int64_t* cand = c.take<int64_t>(bp);
+    int64_t* grow = c.take<int64_t>(bp);
+    float* dense = c.take<float>(bp);
+    float* bm25 = c.take<float>(bp);
+    double* nrev = c.take<double>(bp);
+    double* avg = c.take<double>(bp);
+    int32_t* count = c.take<int32_t>((size_t)B);
+    RR_TRY(dense_topk_locked(ix, d_q, B, pool, dense_mode, cand, dense, count, s));
+    RR_TRY(candidates_locked(ix, d_term_ids, d_n_terms, B, l_max, cand, pool, bm25, nrev, avg, grow, s));
+    return rr_launch_fuse(fp, B, pool, count, dense, bm25, nrev, avg, grow, nullptr, nullptr, nullptr, d_top_row,
+                          d_top_final, nullptr, nullptr, s);
+}
+
+static int check_hybrid_args(rr_index* ix, const void* q, const rr_fusion_params* fp, const void* top_row,
+                             const void* top_final, int32_t B) {
+    if (!ix || !q || !fp || !top_row || !top_final || B < 0) return rr_fail(RR_EINVAL, "rr_hybrid_search: bad argument");
+    if (fp->pool < fp->k) return rr_fail(RR_EINVAL, "rr_hybrid_search: pool must be >= k (pool = max(k, rerank_k, floor))");
+    return RR_OK;
+}
+
+extern "C" int rr_hybrid_search(rr_index* ix, const float* d_q, const int32_t* d_term_ids, const int32_t* d_n_terms,
+                                int32_t B, int32_t l_max, const rr_fusion_params* fp, int32_t dense_mode,
+                                int64_t* d_top_row, float* d_top_final, rr_stream stream) {
+    RR_TRY(check_hybrid_args(ix, d_q, fp, d_top_row, d_top_final, B));
+    if (B == 0) return RR_OK;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    RR_CUDA(cudaSetDevice(ix->device));
+    return hybrid_locked(ix, d_q, d_term_ids, d_n_terms, B, l_max, fp, dense_mode, d_top_row, d_top_final,
+                         static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rr_hybrid_search_host(rr_index* ix, const float* h_q, const int32_t* h_term_ids,
+                                     const int32_t* h_n_terms, int32_t B, int32_t l_max, const rr_fusion_params* fp,
+                                     int32_t dense_mode, int64_t* h_top_row, float* h_top_final, rr_stream stream) {
+    RR_TRY(check_hybrid_args(ix, h_q, fp, h_top_row, h_top_final, B));
+    if (B == 0) return RR_OK;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    RR_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t q_bytes = sizeof(float) * (size_t)B * ix->d.dim;
+    const bool have_terms = h_term_ids && h_n_terms && l_max > 0;
+    const size_t t_bytes = have_terms ? sizeof(int32_t) * (size_t)B * l_max : 0;
+    const size_t n_bytes = have_terms ? sizeof(int32_t) * (size_t)B : 0;
+    const size_t r_bytes = sizeof(int64_t) * (size_t)B * fp->k;
+    const size_t f_bytes = sizeof(float) * (size_t)B * fp->k;
+    RR_TRY(ix->staging.ensure(align_up(q_bytes, 256) + align_up(t_bytes, 256) + align_up(n_bytes, 256) +
+                              align_up(r_bytes, 256) + align_up(f_bytes, 256) + 256));
+    char* p = static_cast<char*>(ix->staging.p);
+    float* d_q = reinterpret_cast<float*>(p); p += align_up(q_bytes, 256);
+    int32_t* d_t = reinterpret_cast<int32_t*>(p); p += align_up(t_bytes, 256);
+    int32_t* d_n = reinterpret_cast<int32_t*>(p); p += align_up(n_bytes, 256);
+    int64_t* d_r = reinterpret_cast<int64_t*>(p); p += align_up(r_bytes, 256);
+    float* d_f = reinterpret_cast<float*>(p);
+    RR_CUDA(cudaMemcpyAsync(d_q, h_q, q_bytes, cudaMemcpyHostToDevice, s));
+    if (have_terms) {
+        RR_CUDA(cudaMemcpyAsync(d_t, h_term_ids, t_bytes, cudaMemcpyHostToDevice, s));
+        RR_CUDA(cudaMemcpyAsync(d_n, h_n_terms, n_bytes, cudaMemcpyHostToDevice, s));
+    }
+    RR_TRY(hybrid_locked(ix, d_q, have_terms ? d_t : nullptr, have_terms ? d_n : nullptr, B, l_max, fp, dense_mode,
+                         d_r, d_f, s));
+    RR_CUDA(cudaMemcpyAsync(h_top_row, d_r, r_bytes, cudaMemcpyDeviceToHost, s));
+    RR_CUDA(cudaMemcpyAsync(h_top_final, d_f, f_bytes, cudaMemcpyDeviceToHost, s));
+    RR_CUDA(cudaStreamSynchronize(s));
+    return RR_OK;
+}

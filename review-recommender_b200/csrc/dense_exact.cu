@@ -1,0 +1,389 @@
+// Exact fp32 dense scoring and selection (sm_100a).
+//
+// Stands behind cosine_similarity_search utils.py:111-124 (= cosine_search app/test.py:125-132,
+// _cosine_pool app/app_product_search.py:192-195):  sims = mat @ q ; top-k ; sort descending.
+//
+// CANONICAL DOT PRODUCT.  Every fp32 similarity this library returns is computed by
+// `canonical_dot`: lane j of a warp accumulates, with fmaf in ascending element order, the
+// float4 chunks c = j, j+32, j+64, ... of the row; the 32 partial sums are combined by the
+// xor-butterfly 16,8,4,2,1.  The exact path (this file), the shortlist rescoring of the tensor
+// path (K3) and every batch size therefore return bit-identical similarities, and differ from
+// BLAS sgemv only by fp32 summation order (<= ~1e-7 abs on unit vectors; tolerance 1e-6).
+//
+//  dense_scores_f32_kernel   HBM-bound multi-query GEMV: each warp streams corpus rows with
+//      16-byte loads (2 rows in flight), up to 8 queries per CTA sit in shared memory.
+//      Algorithmic bytes: 4*D per row per group of 8 queries.
+//  radix-select (rs_*)       exact top-k of every score row on 64-bit composite keys
+//      (score desc, row asc): 11/11/10-bit digit histograms, early exit once the pivot bucket
+//      is exactly consumed, then collect + bitonic sort of the k survivors.
+//  rescore_kernel (K3)       exact similarities of a shortlist (one warp per (query, row)).
+#include "rr_internal.h"
+#include "rr_kernels.h"
+
+namespace {
+
+constexpr int QB = 8;              // queries per CTA in the GEMV kernel
+constexpr int GEMV_THREADS = 256;  // 8 warps
+constexpr int GEMV_ROWS = 2;       // rows per warp iteration
+
+__device__ __forceinline__ float warp_xor_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+__device__ __forceinline__ float4 ldg_row16(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// lane-partial of the canonical dot for a row whose length is a multiple of 4 (16-byte aligned)
+__device__ __forceinline__ float lane_partial_v4(const float4* __restrict__ row, const float4* __restrict__ q,
+                                                 int n_chunks, int lane) {
+    float acc = 0.f;
+    for (int c = lane; c < n_chunks; c += 32) {
+        const float4 m = __ldg(row + c);
+        const float4 x = q[c];
+        acc = fmaf(x.x, m.x, acc);
+        acc = fmaf(x.y, m.y, acc);
+        acc = fmaf(x.z, m.z, acc);
+        acc = fmaf(x.w, m.w, acc);
+    }
+    return acc;
+}
+// generic (any D, any alignment): same chunking, scalar loads
+__device__ __forceinline__ float lane_partial_scalar(const float* __restrict__ row, const float* __restrict__ q,
+                                                     int D, int lane) {
+    float acc = 0.f;
+    for (int c = lane; c * 4 < D; c += 32) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = c * 4 + e;
+            if (i < D) acc = fmaf(q[i], __ldg(row + i), acc);
+        }
+    }
+    return acc;
+}
+
+// scores[b, row] for b in [0, nq), all rows.  Queries of the CTA's group live in smem.
+template <bool VEC4>
+__global__ void __launch_bounds__(GEMV_THREADS)
+dense_scores_f32_kernel(const float* __restrict__ emb, long long n_rows, int D,
+                        const float* __restrict__ queries, int n_queries,
+                        float* __restrict__ scores, long long ld_scores) {
+    extern __shared__ __align__(16) float s_q[];   // [QB][Dp]
+    const int Dp = (D + 3) & ~3;
+    const int q0 = blockIdx.y * QB;
+    const int nq = min(QB, n_queries - q0);
+    for (int i = threadIdx.x; i < QB * Dp; i += GEMV_THREADS) {
+        const int b = i / Dp, d = i - b * Dp;
+        s_q[i] = (b < nq && d < D) ? queries[(long long)(q0 + b) * D + d] : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long warps_total = (long long)gridDim.x * (GEMV_THREADS / 32);
+    const long long gw = (long long)blockIdx.x * (GEMV_THREADS / 32) + warp;
+
+    if constexpr (VEC4) {
+        const int n_chunks = D >> 2;
+        for (long long r0 = gw * GEMV_ROWS; r0 < n_rows; r0 += warps_total * GEMV_ROWS) {
+            float acc[GEMV_ROWS][QB];
+#pragma unroll
+            for (int rr = 0; rr < GEMV_ROWS; ++rr)
+#pragma unroll
+                for (int b = 0; b < QB; ++b) acc[rr][b] = 0.f;
+            for (int c = lane; c < n_chunks; c += 32) {
+                float4 m[GEMV_ROWS];
+#pragma unroll
+                for (int rr = 0; rr < GEMV_ROWS; ++rr) {
+                    const long long r = min(r0 + rr, n_rows - 1);
+                    m[rr] = ldg_row16(reinterpret_cast<const float4*>(emb + r * D) + c);
+                }
+#pragma unroll
+                for (int b = 0; b < QB; ++b) {
+                    const float4 x = reinterpret_cast<const float4*>(s_q + b * Dp)[c];
+#pragma unroll
+                    for (int rr = 0; rr < GEMV_ROWS; ++rr) {
+                        float a = acc[rr][b];
+                        a = fmaf(x.x, m[rr].x, a);
+                        a = fmaf(x.y, m[rr].y, a);
+                        a = fmaf(x.z, m[rr].z, a);
+                        a = fmaf(x.w, m[rr].w, a);
+                        acc[rr][b] = a;
+                    }
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < GEMV_ROWS; ++rr) {
+                const long long r = r0 + rr;
+#pragma unroll
+                for (int b = 0; b < QB; ++b) {
+                    const float s = warp_xor_sum(acc[rr][b]);
+                    if (lane == b && b < nq && r < n_rows) scores[(long long)(q0 + b) * ld_scores + r] = s;
+                }
+            }
+        }
+    } else {
+        for (long long r = gw; r < n_rows; r += warps_total) {
+            for (int b = 0; b < nq; ++b) {
+                const float s = warp_xor_sum(lane_partial_scalar(emb + r * D, s_q + b * Dp, D, lane));
+                if (lane == 0) scores[(long long)(q0 + b) * ld_scores + r] = s;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: exact similarity of shortlisted rows.  One warp per (query, slot).
+// rows int64[B, n_slots] (<0 = empty -> -inf).  q float[B, D].
+// ---------------------------------------------------------------------------------------------
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+rescore_kernel(const float* __restrict__ emb, long long n_rows, int D, const float* __restrict__ queries,
+               const long long* __restrict__ rows, int n_slots, int B, float* __restrict__ out) {
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= (long long)B * n_slots) return;
+    const int q = (int)(gw / n_slots);
+    const long long r = rows[gw];
+    float s;
+    if (r < 0 || r >= n_rows) {
+        s = -INFINITY;
+    } else if constexpr (VEC4) {
+        s = warp_xor_sum(lane_partial_v4(reinterpret_cast<const float4*>(emb + r * D),
+                                         reinterpret_cast<const float4*>(queries + (long long)q * D), D >> 2, lane));
+    } else {
+        s = warp_xor_sum(lane_partial_scalar(emb + r * D, queries + (long long)q * D, D, lane));
+    }
+    if (lane == 0) out[gw] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Radix select of the top-k composite keys of every row of a score matrix.
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_BINS = 2048;
+constexpr int RS_THREADS = 512;
+constexpr int RS_LEVELS = 6;
+__constant__ int c_rs_bits[RS_LEVELS] = {11, 11, 10, 11, 11, 10};
+
+struct RsRow {
+    unsigned long long prefix;   // digits chosen so far (top `bits_done` bits of the pivot)
+    int bits_done;
+    int k_rem;                   // how many of the pivot bucket's keys are still wanted
+    int done;                    // 1: every key with (key >> (64-bits_done)) >= prefix is selected
+    int out_count;
+};
+
+__global__ void rs_init_kernel(RsRow* st, unsigned* hist, int rows, int k) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) { st[i].prefix = 0; st[i].bits_done = 0; st[i].k_rem = k; st[i].done = 0; st[i].out_count = 0; }
+    for (long long j = i; j < (long long)rows * RS_BINS; j += (long long)gridDim.x * blockDim.x) hist[j] = 0;
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_hist_kernel(const float* __restrict__ scores, long long ld, long long n, const RsRow* __restrict__ st,
+               unsigned* __restrict__ hist, int level) {
+    const int row = blockIdx.y;
+    const RsRow s = st[row];
+    if (s.done) return;
+    __shared__ unsigned sh[RS_BINS];
+    for (int i = threadIdx.x; i < RS_BINS; i += RS_THREADS) sh[i] = 0;
+    __syncthreads();
+    const int bits = c_rs_bits[level];
+    const int shift = 64 - s.bits_done - bits;
+    const float* src = scores + (long long)row * ld;
+    const long long per = (n + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * per, hi = min(n, lo + per);
+    for (long long i = lo + threadIdx.x; i < hi; i += RS_THREADS) {
+        const unsigned long long key = rr_make_key(src[i], (uint32_t)i);
+        const bool in = s.bits_done == 0 ? true : ((key >> (64 - s.bits_done)) == s.prefix);
+        if (in) atomicAdd(&sh[(unsigned)((key >> shift) & ((1u << bits) - 1u))], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RS_BINS; i += RS_THREADS)
+        if (sh[i]) atomicAdd(&hist[(long long)row * RS_BINS + i], sh[i]);
+}
+
+__global__ void __launch_bounds__(RS_BINS / 2)
+rs_scan_kernel(RsRow* st, unsigned* hist, int level) {
+    const int row = blockIdx.x;
+    RsRow s = st[row];
+    unsigned* h = hist + (long long)row * RS_BINS;
+    if (s.done) return;
+    __shared__ unsigned sh[RS_BINS];
+    __shared__ int s_bucket;
+    const int bits = c_rs_bits[level];
+    const int nb = 1 << bits;
+    for (int i = threadIdx.x; i < RS_BINS; i += blockDim.x) { sh[i] = i < nb ? h[i] : 0u; h[i] = 0u; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // serial walk from the top bucket: nb <= 2048, once per row per level
+        unsigned above = 0;
+        int b = nb - 1;
+        for (; b > 0; --b) {
+            if (above + sh[b] >= (unsigned)s.k_rem) break;
+            above += sh[b];
+        }
+        s.k_rem -= (int)above;
+        s.prefix = (s.prefix << bits) | (unsigned long long)b;
+        s.bits_done += bits;
+        if ((int)sh[b] == s.k_rem || s.bits_done == 64) s.done = 1;
+        st[row] = s;
+        s_bucket = b;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_collect_kernel(const float* __restrict__ scores, long long ld, long long n, RsRow* st,
+                  unsigned long long* __restrict__ out_keys, int k_cap) {
+    const int row = blockIdx.y;
+    const unsigned long long prefix = st[row].prefix;
+    const int bits_done = st[row].bits_done;
+    const float* src = scores + (long long)row * ld;
+    const long long per = (n + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * per, hi = min(n, lo + per);
+    for (long long i = lo + threadIdx.x; i < hi; i += RS_THREADS) {
+        const unsigned long long key = rr_make_key(src[i], (uint32_t)i);
+        const bool sel = bits_done == 0 ? true : ((key >> (64 - bits_done)) >= prefix);
+        if (sel) {
+            const int slot = atomicAdd(&st[row].out_count, 1);
+            if (slot < k_cap) out_keys[(long long)row * k_cap + slot] = key;
+        }
+    }
+}
+
+// Bitonic sort (descending) of up to n_pad (power of two) 64-bit keys in shared memory, one CTA
+// per row; writes idx/score of the first k.  Missing entries are key 0 -> idx -1 / -inf.
+__global__ void __launch_bounds__(1024)
+sort_keys_kernel(const unsigned long long* __restrict__ keys, int k_cap, const RsRow* __restrict__ st,
+                 int k, int n_pad, long long* __restrict__ out_idx, float* __restrict__ out_score,
+                 int32_t* __restrict__ out_count, int out_ld) {
+    extern __shared__ unsigned long long sk[];
+    const int row = blockIdx.x;
+    const int cnt = min(st[row].out_count, k_cap);
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) sk[i] = i < cnt ? keys[(long long)row * k_cap + i] : 0ull;
+    __syncthreads();
+    for (int size = 2; size <= n_pad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < n_pad / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const unsigned long long a = sk[lo], b = sk[hi];
+                if ((a < b) == desc) { sk[lo] = b; sk[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    const int kk = min(k, cnt);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        if (i < kk) {
+            out_idx[(long long)row * out_ld + i] = (long long)rr_key_index(sk[i]);
+            out_score[(long long)row * out_ld + i] = rr_key_score(sk[i]);
+        } else {
+            out_idx[(long long)row * out_ld + i] = -1;
+            out_score[(long long)row * out_ld + i] = -INFINITY;
+        }
+    }
+    if (threadIdx.x == 0 && out_count) out_count[row] = kk;
+}
+
+int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+}  // namespace
+
+size_t rr_exact_scratch_bytes(int rows, int k) {
+    return sizeof(RsRow) * (size_t)rows + sizeof(unsigned) * (size_t)rows * RS_BINS +
+           sizeof(unsigned long long) * (size_t)rows * (size_t)k + 256;
+}
+
+int rr_launch_dense_scores_f32(const float* d_emb, int64_t n_rows, int D, const float* d_q, int n_queries,
+                               float* d_scores, int64_t ld_scores, int sm_count, cudaStream_t stream) {
+    if (n_queries <= 0 || n_rows <= 0) return RR_OK;
+    const int Dp = (D + 3) & ~3;
+    const size_t smem = sizeof(float) * (size_t)QB * Dp;
+    const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_emb) & 15) == 0);
+    const int warps_per_cta = GEMV_THREADS / 32;
+    long long want = (n_rows + (long long)warps_per_cta * GEMV_ROWS - 1) / ((long long)warps_per_cta * GEMV_ROWS);
+    const int groups = (n_queries + QB - 1) / QB;
+    long long cap = (long long)sm_count * 8;
+    unsigned gx = (unsigned)max(1ll, min(want, cap));
+    dim3 grid(gx, (unsigned)groups);
+    if (smem > 48 * 1024) {
+        RR_CUDA(cudaFuncSetAttribute(dense_scores_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RR_CUDA(cudaFuncSetAttribute(dense_scores_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (vec4)
+        dense_scores_f32_kernel<true><<<grid, GEMV_THREADS, smem, stream>>>(d_emb, n_rows, D, d_q, n_queries, d_scores, ld_scores);
+    else
+        dense_scores_f32_kernel<false><<<grid, GEMV_THREADS, smem, stream>>>(d_emb, n_rows, D, d_q, n_queries, d_scores, ld_scores);
+    RR_LAUNCH_CHECK();
+    return RR_OK;
+}
+
+int rr_launch_rescore(const float* d_emb, int64_t n_rows, int D, const float* d_q, const int64_t* d_rows,
+                      int n_slots, int B, float* d_out, cudaStream_t stream) {
+    const long long warps = (long long)B * n_slots;
+    if (warps <= 0) return RR_OK;
+    const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_emb) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(d_q) & 15) == 0);
+    const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+    if (vec4)
+        rescore_kernel<true><<<blocks, 256, 0, stream>>>(d_emb, n_rows, D, d_q, reinterpret_cast<const long long*>(d_rows), n_slots, B, d_out);
+    else
+        rescore_kernel<false><<<blocks, 256, 0, stream>>>(d_emb, n_rows, D, d_q, reinterpret_cast<const long long*>(d_rows), n_slots, B, d_out);
+    RR_LAUNCH_CHECK();
+    return RR_OK;
+}
+
+// top-k (k <= 8192) of each of `rows` score rows of length n; results ordered (score desc, idx asc)
+int rr_launch_topk_rows(const float* d_scores, int64_t ld, int64_t n, int rows, int k, void* d_scratch,
+                        int64_t* d_idx, float* d_score, int32_t* d_count, int out_ld, int sm_count,
+                        cudaStream_t stream) {
+    if (rows <= 0) return RR_OK;
+    if (k > 8192) return rr_fail(RR_EINVAL, "top-k larger than 8192 is not supported");
+    const int kk = (int)(k < n ? (int64_t)k : n);
+    char* p = static_cast<char*>(d_scratch);
+    RsRow* st = reinterpret_cast<RsRow*>(p);
+    p += (sizeof(RsRow) * (size_t)rows + 255) & ~(size_t)255;
+    unsigned* hist = reinterpret_cast<unsigned*>(p);
+    p += sizeof(unsigned) * (size_t)rows * RS_BINS;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(p);
+    const int k_cap = max(kk, 1);
+
+    rs_init_kernel<<<max(1, min(1024, rows * 8)), 256, 0, stream>>>(st, hist, rows, kk);
+    RR_LAUNCH_CHECK();
+    if (kk > 0 && kk < n) {
+        long long chunks = (n + (long long)RS_THREADS * 16 - 1) / ((long long)RS_THREADS * 16);
+        unsigned gx = (unsigned)max(1ll, min(chunks, (long long)max(1, sm_count * 4 / max(1, min(rows, 4)))));
+        for (int level = 0; level < RS_LEVELS; ++level) {
+            rs_hist_kernel<<<dim3(gx, (unsigned)rows), RS_THREADS, 0, stream>>>(d_scores, ld, n, st, hist, level);
+            RR_LAUNCH_CHECK();
+            rs_scan_kernel<<<rows, RS_BINS / 2, 0, stream>>>(st, hist, level);
+            RR_LAUNCH_CHECK();
+        }
+        rs_collect_kernel<<<dim3(gx, (unsigned)rows), RS_THREADS, 0, stream>>>(d_scores, ld, n, st, keys, k_cap);
+        RR_LAUNCH_CHECK();
+    } else if (kk > 0) {
+        // k >= n: everything is selected (bits_done == 0 selects all)
+        long long chunks = (n + (long long)RS_THREADS * 16 - 1) / ((long long)RS_THREADS * 16);
+        unsigned gx = (unsigned)max(1ll, min(chunks, (long long)sm_count));
+        rs_collect_kernel<<<dim3(gx, (unsigned)rows), RS_THREADS, 0, stream>>>(d_scores, ld, n, st, keys, k_cap);
+        RR_LAUNCH_CHECK();
+    }
+    const int n_pad = max(2, next_pow2(k_cap));
+    const size_t smem = sizeof(unsigned long long) * (size_t)n_pad;
+    if (smem > 48 * 1024) RR_CUDA(cudaFuncSetAttribute(sort_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = max(32, min(1024, n_pad / 2));
+    sort_keys_kernel<<<rows, threads, smem, stream>>>(keys, k_cap, st, k, n_pad, reinterpret_cast<long long*>(d_idx),
+                                                      d_score, d_count, out_ld);
+    RR_LAUNCH_CHECK();
+    return RR_OK;
+}

@@ -1,0 +1,18 @@
+// Tensor-core (tcgen05) shortlist path of rr_dense_topk; see dense_tc.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../../include/rr_b200.h"
+
+struct rr_tc_state;
+
+// exact-path callback used for queries the tensor path cannot certify
+typedef int (*rr_exact_fn)(void* ctx, const float* d_q, int32_t B, int32_t pool, int64_t* d_idx, float* d_sims,
+                           int32_t* d_count, cudaStream_t stream);
+
+bool rr_tc_supported(int cc_major, int cc_minor);
+int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, const float* d_q, int32_t B,
+                     int32_t pool, int64_t* d_idx, float* d_sims, int32_t* d_count, rr_dense_stats* stats,
+                     rr_exact_fn exact, void* exact_ctx, cudaStream_t stream);
+void rr_tc_destroy(rr_tc_state* state);

@@ -1,0 +1,37 @@
+// Launcher prototypes shared between the kernel translation units and api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/rr_b200.h"
+
+// bm25_kernels.cu
+int rr_launch_bm25_tile_scores(const uint64_t* d_postings, const uint64_t* d_tile_base, const uint32_t* d_blk_off,
+                               int V, int T, int n_tiles, int64_t n_docs, const int32_t* d_terms,
+                               const int32_t* d_nterms, int B, int l_max, float* d_out, int64_t ld_out,
+                               cudaStream_t stream);
+int rr_launch_bm25_candidates(const uint64_t* d_postings, const uint64_t* d_tile_base, const uint32_t* d_blk_off,
+                              int V, int T, int64_t n_docs, const int32_t* d_terms, const int32_t* d_nterms,
+                              int B, int l_max, const int64_t* d_cand, int pool, const double* d_nrev,
+                              const double* d_avg, int64_t row_offset, float* d_bm25, double* d_n_out,
+                              double* d_avg_out, int64_t* d_grow_out, cudaStream_t stream);
+
+// dense_exact.cu
+size_t rr_exact_scratch_bytes(int rows, int k);
+int rr_launch_dense_scores_f32(const float* d_emb, int64_t n_rows, int D, const float* d_q, int n_queries,
+                               float* d_scores, int64_t ld_scores, int sm_count, cudaStream_t stream);
+int rr_launch_rescore(const float* d_emb, int64_t n_rows, int D, const float* d_q, const int64_t* d_rows,
+                      int n_slots, int B, float* d_out, cudaStream_t stream);
+int rr_launch_topk_rows(const float* d_scores, int64_t ld, int64_t n, int rows, int k, void* d_scratch,
+                        int64_t* d_idx, float* d_score, int32_t* d_count, int out_ld, int sm_count,
+                        cudaStream_t stream);
+
+// fuse.cu
+int rr_launch_fuse(const rr_fusion_params* p, int B, int n_in, const int32_t* d_count, const float* d_dense,
+                   const float* d_bm25, const double* d_n, const double* d_avg, const int64_t* d_grow,
+                   const float* d_rerank, const float* d_best, const float* d_gate, int64_t* d_top_row,
+                   float* d_top_final, int32_t* d_top_pos, float* d_components, cudaStream_t stream);
+
+// dense_tc.cu (tcgen05 shortlist path)
+struct rr_tc_plan;

@@ -1,10 +1,632 @@
-// placeholder until the tcgen05 kernel lands
+// K2 -- tensor-core shortlist path of rr_dense_topk (sm_100a: tcgen05.mma + TMEM + TMA).
+//
+// Stands behind the `sims = mat @ q` + top-pool of cosine_similarity_search (utils.py:111-124,
+// = _cosine_pool app/app_product_search.py:192-195, cosine_search app/test.py:125-132) for a
+// BATCH of queries, where the contraction is a genuine GEMM (B x N x D).
+//
+// Pipeline per batch
+//   cvt_queries      fp32 queries -> bf16 [B_pad, dim_pad] (+ ||q||)
+//   tc_filter_kernel bf16 x bf16 -> fp32 scores on the tensor cores, never materialised:
+//                    CTA = 128 queries (UMMA M, one TMEM lane per query) x a strided set of
+//                    256-doc tiles (UMMA N).  The 128 x D query tile is loaded once by TMA and
+//                    stays in shared memory; 256 x 64 corpus k-blocks stream through a 4-stage
+//                    TMA/mbarrier ring; one thread issues tcgen05.mma (K=16) into a double-
+//                    buffered TMEM accumulator (2 x 256 columns); four epilogue warps read the
+//                    accumulator with tcgen05.ld (thread = query row) and keep only scores
+//                    >= the query's running threshold tau, appended as 64-bit (score, doc) keys.
+//   tc_select_kernel per query: merge kept list + new candidates, keep the best k', raise tau to
+//                    the k'-th score.  The corpus is scanned in geometrically growing segments
+//                    (filter launch + select launch per segment) so that the expected number of
+//                    candidates per segment stays ~ (growth-1) * k'.
+//   rescore (K3)     exact canonical fp32 similarity of the k' shortlisted rows (dense_exact.cu)
+//   tc_finalize      order by (exact desc, row asc), emit the top `pool`, and CERTIFY: every row
+//                    outside the shortlist has bf16 score <= c (the k'-th kept), hence exact score
+//                    <= c + eps; the result is exact if the pool-th exact score > c + eps.
+//                    Uncertified queries (near-ties denser than the margin, candidate overflow)
+//                    are recomputed by the exact fp32 path -- results never depend on bf16.
+//
+// eps = (2^-7 + 2^-15) * ||q|| * max||row||  (bf16 round-to-nearest of both operands, unit roundoff
+// 2^-8 each) + 1e-4 * ||q|| * max||row|| (fp32 accumulation slack for D <= 1024).
 #include "rr_internal.h"
+#include "rr_kernels.h"
 #include "dense_tc.h"
-struct rr_tc_state { int unused; };
-bool rr_tc_supported(int, int) { return false; }
-int rr_tc_dense_topk(rr_tc_state**, const rr_index_desc*, int, const float*, int32_t, int32_t, int64_t*, float*,
-                     int32_t*, rr_dense_stats*, rr_exact_fn, void*, cudaStream_t) {
-    return rr_fail(RR_EUNSUPPORTED, "tensor path not built");
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+namespace {
+
+constexpr int TC_BM = 128;      // queries per CTA tile (UMMA M)
+constexpr int TC_BN = 256;      // docs per tile (UMMA N)
+constexpr int TC_BK = 64;       // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int TC_STAGES = 4;
+constexpr int TC_MAX_KB = 6;    // dim_pad <= 384 keeps the query tile resident
+constexpr int TC_THREADS = 256;
+constexpr int TC_Q_KB_BYTES = TC_BM * TC_BK * 2;    // 16 KB
+constexpr int TC_B_KB_BYTES = TC_BN * TC_BK * 2;    // 32 KB
+constexpr int TC_SMEM_Q = TC_MAX_KB * TC_Q_KB_BYTES;
+constexpr int TC_SMEM_B = TC_STAGES * TC_B_KB_BYTES;
+constexpr int TC_SMEM_BAR = 256;
+constexpr int TC_SMEM_TOTAL = TC_SMEM_Q + TC_SMEM_B + TC_SMEM_BAR + 1024;   // + alignment slack
+constexpr int TC_CAP = 4096;    // candidate slots per query per segment
+constexpr int TC_SEG0_TILES = TC_CAP / TC_BN;   // first segment passes everything (tau = -inf)
+constexpr int TC_GROWTH = 4;    // corpus prefix grows x4 per segment
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-void rr_tc_destroy(rr_tc_state* s) { delete s; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc_512(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512(uint32_t addr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, M=128 N=256 K=16
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_tile) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem_tile) >> 4) & 0x3FFFu);   // start address
+    d |= (uint64_t)1 << 16;                                  // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                                  // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
+    return d;
+}
+constexpr uint32_t kInstrDesc = (1u << 4)      // D format: F32
+                                | (1u << 7)    // A format: BF16
+                                | (1u << 10)   // B format: BF16
+                                | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // K-major A and B
+
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// query conversion
+// ---------------------------------------------------------------------------------------------
+__global__ void cvt_queries_kernel(const float* __restrict__ q, int B, int D, int dim_pad, int B_pad,
+                                   __nv_bfloat16* __restrict__ out, float* __restrict__ qnorm) {
+    const int row = blockIdx.x;
+    float ss = 0.f;
+    for (int d = threadIdx.x; d < dim_pad; d += blockDim.x) {
+        float x = (row < B && d < D) ? q[(long long)row * D + d] : 0.f;
+        out[(long long)row * dim_pad + d] = __float2bfloat16_rn(x);
+        ss += x * x;
+    }
+    __shared__ float red[32];
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0 && row < B) {
+        float t = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        qnorm[row] = sqrtf(t);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the GEMM + threshold filter
+// ---------------------------------------------------------------------------------------------
+struct TcFilterArgs {
+    long long n_docs;
+    int n_kb;          // dim_pad / 64
+    int B;
+    int qt0, n_qt;     // query tiles handled by this launch
+    int reps;          // CTAs per query tile
+    int dt_lo, dt_hi;  // doc tiles of this segment
+    const float* tau;  // [B]
+    unsigned long long* cand_keys;   // [B, TC_CAP]
+    unsigned* cand_cnt;              // [B]
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
+                 const TcFilterArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;
+    uint8_t* sB = smem + TC_SMEM_Q;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_SMEM_Q + TC_SMEM_B);
+    uint64_t* full = bars;                  // [TC_STAGES]  TMA -> MMA
+    uint64_t* empty = bars + TC_STAGES;     // [TC_STAGES]  MMA -> TMA
+    uint64_t* tfull = bars + 2 * TC_STAGES; // [2]          MMA -> epilogue
+    uint64_t* tempty = tfull + 2;           // [2]          epilogue -> MMA
+    uint64_t* qfull = tempty + 2;           // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cta = blockIdx.x;
+    const int qt = a.qt0 + cta % a.n_qt;
+    const int j0 = cta / a.n_qt;
+    const int span = a.dt_hi - a.dt_lo;
+    const int n_tiles = j0 < span ? (span - j0 + a.reps - 1) / a.reps : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_c);
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        mbar_init(qfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_512(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (one thread) =====
+        if (lane == 0 && n_tiles > 0) {
+            mbar_expect_tx(qfull, (uint32_t)(a.n_kb * TC_Q_KB_BYTES));
+            for (int kb = 0; kb < a.n_kb; ++kb) tma_load_2d(&tmap_q, qfull, sQ + kb * TC_Q_KB_BYTES, kb * TC_BK, qt * TC_BM);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int dt = a.dt_lo + j0 + t * a.reps;
+                for (int kb = 0; kb < a.n_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_expect_tx(&full[stage], (uint32_t)TC_B_KB_BYTES);
+                    tma_load_2d(&tmap_c, &full[stage], sB + stage * TC_B_KB_BYTES, kb * TC_BK, dt * TC_BN);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0 && n_tiles > 0) {
+            mbar_wait(qfull, 0u);
+            tc_fence_after();
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int as = t & 1;
+                const uint32_t aphase = (uint32_t)((t >> 1) & 1);
+                mbar_wait(&tempty[as], aphase ^ 1u);       // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_BN);
+                for (int kb = 0; kb < a.n_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(sQ + kb * TC_Q_KB_BYTES);
+                    const uint64_t db = umma_desc_sw128(sB + stage * TC_B_KB_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k)       // +32 bytes (>>4 = 2) per K=16 step
+                        umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kInstrDesc, (uint32_t)((kb | k) != 0));
+                    umma_commit(&empty[stage]);               // smem slot reusable once these MMAs retire
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tfull[as]);                       // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: thread = query row, threshold filter =====
+        const int ew = warp - 4;                               // == warp % 4: TMEM lanes 32*ew .. 32*ew+31
+        const int q = qt * TC_BM + ew * 32 + lane;
+        const bool active = q < a.B;
+        const float tau = active ? a.tau[q] : INFINITY;
+        unsigned long long* my_keys = a.cand_keys + (size_t)(active ? q : 0) * TC_CAP;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int as = t & 1;
+            const uint32_t aphase = (uint32_t)((t >> 1) & 1);
+            const int dt = a.dt_lo + j0 + t * a.reps;
+            const long long doc_base = (long long)dt * TC_BN;
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * TC_BN);
+#pragma unroll 1
+            for (int chunk = 0; chunk < TC_BN / 32; ++chunk) {
+                uint32_t v[32];
+                tmem_ld_x32(taddr0 + (uint32_t)(chunk * 32), v);
+                tmem_ld_wait();
+                float m = __uint_as_float(v[0]);
+#pragma unroll
+                for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+                if (active && m >= tau) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float s = __uint_as_float(v[i]);
+                        if (s >= tau) {
+                            const long long doc = doc_base + chunk * 32 + i;
+                            if (doc < a.n_docs) {
+                                const unsigned slot = atomicAdd(&a.cand_cnt[q], 1u);
+                                if (slot < (unsigned)TC_CAP) my_keys[slot] = rr_make_key(s, (uint32_t)doc);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_512(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-query selection
+// ---------------------------------------------------------------------------------------------
+__device__ void bitonic_keys_desc(unsigned long long* key, int n_pad) {
+    for (int size = 2; size <= n_pad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < n_pad / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const unsigned long long x = key[lo], y = key[hi];
+                if ((x < y) == desc) { key[lo] = y; key[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tc_select_kernel(unsigned long long* __restrict__ cand_keys, unsigned* __restrict__ cand_cnt,
+                 unsigned long long* __restrict__ kept_keys, int* __restrict__ kept_cnt, int KP,
+                 float* __restrict__ tau, int* __restrict__ overflow, int final_pass,
+                 long long* __restrict__ rows_out) {
+    extern __shared__ unsigned long long sk[];
+    const int q = blockIdx.x;
+    const unsigned raw = cand_cnt[q];
+    const int c = (int)min(raw, (unsigned)TC_CAP);
+    const int kc = kept_cnt[q];
+    const int total = c + kc;
+    int n_pad = 2;
+    while (n_pad < total) n_pad <<= 1;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        unsigned long long k = 0ull;
+        if (i < kc) k = kept_keys[(size_t)q * KP + i];
+        else if (i < total) k = cand_keys[(size_t)q * TC_CAP + (i - kc)];
+        sk[i] = k;
+    }
+    __syncthreads();
+    bitonic_keys_desc(sk, n_pad);
+    const int newk = min(KP, total);
+    for (int i = threadIdx.x; i < newk; i += blockDim.x) kept_keys[(size_t)q * KP + i] = sk[i];
+    if (final_pass)
+        for (int i = threadIdx.x; i < KP; i += blockDim.x)
+            rows_out[(size_t)q * KP + i] = i < newk ? (long long)rr_key_index(sk[i]) : -1ll;
+    if (threadIdx.x == 0) {
+        kept_cnt[q] = newk;
+        tau[q] = newk == KP ? rr_key_score(sk[KP - 1]) : -INFINITY;
+        cand_cnt[q] = 0u;
+        if (raw > (unsigned)TC_CAP) overflow[q] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tc_finalize_kernel(const unsigned long long* __restrict__ kept_keys, const int* __restrict__ kept_cnt, int KP,
+                   const float* __restrict__ exact, const int* __restrict__ overflow, const float* __restrict__ qnorm,
+                   float eps_rel, int pool, long long* __restrict__ out_idx, float* __restrict__ out_sims,
+                   int32_t* __restrict__ out_count, int* __restrict__ n_flagged, int* __restrict__ flagged) {
+    extern __shared__ unsigned long long sk[];
+    const int q = blockIdx.x;
+    const int kc = kept_cnt[q];
+    int n_pad = 2;
+    while (n_pad < KP) n_pad <<= 1;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        unsigned long long k = 0ull;
+        if (i < kc) {
+            k = rr_make_key(exact[(size_t)q * KP + i], rr_key_index(kept_keys[(size_t)q * KP + i]));
+            if (k == 0ull) k = 1ull;
+        }
+        sk[i] = k;
+    }
+    __syncthreads();
+    bitonic_keys_desc(sk, n_pad);
+    const int P = min(pool, kc);
+    for (int i = threadIdx.x; i < pool; i += blockDim.x) {
+        out_idx[(size_t)q * pool + i] = i < P ? (long long)rr_key_index(sk[i]) : -1ll;
+        out_sims[(size_t)q * pool + i] = i < P ? rr_key_score(sk[i]) : -INFINITY;
+    }
+    if (threadIdx.x == 0) {
+        if (out_count) out_count[q] = P;
+        bool ok = overflow[q] == 0;
+        if (ok && kc == KP) {
+            // every row outside the shortlist has bf16 score <= c, so exact score <= c + eps
+            const float c = rr_key_score(kept_keys[(size_t)q * KP + KP - 1]);
+            const float eps = eps_rel * qnorm[q];
+            const float pth = P > 0 ? rr_key_score(sk[P - 1]) : INFINITY;
+            ok = pth > c + eps;
+        }
+        if (!ok) flagged[atomicAdd(n_flagged, 1)] = q;
+    }
+}
+
+__global__ void tc_reset_kernel(unsigned* cand_cnt, int* kept_cnt, float* tau, int* overflow, int* n_flagged, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) { cand_cnt[i] = 0u; kept_cnt[i] = 0; tau[i] = -INFINITY; overflow[i] = 0; }
+    if (i == 0) *n_flagged = 0;
+}
+__global__ void tc_gather_queries_kernel(const float* __restrict__ q, const int* __restrict__ flagged, int D,
+                                         float* __restrict__ out) {
+    const int src = flagged[blockIdx.x];
+    for (int d = threadIdx.x; d < D; d += blockDim.x) out[(size_t)blockIdx.x * D + d] = q[(size_t)src * D + d];
+}
+__global__ void tc_scatter_results_kernel(const int* __restrict__ flagged, int pool, const long long* __restrict__ idx_in,
+                                          const float* __restrict__ sims_in, const int32_t* __restrict__ cnt_in,
+                                          long long* __restrict__ idx, float* __restrict__ sims, int32_t* __restrict__ cnt) {
+    const int dst = flagged[blockIdx.x];
+    for (int i = threadIdx.x; i < pool; i += blockDim.x) {
+        idx[(size_t)dst * pool + i] = idx_in[(size_t)blockIdx.x * pool + i];
+        sims[(size_t)dst * pool + i] = sims_in[(size_t)blockIdx.x * pool + i];
+    }
+    if (threadIdx.x == 0 && cnt) cnt[dst] = cnt_in[blockIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+int make_tmap_bf16_rows(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return rr_fail(RR_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return rr_fail(RR_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return RR_OK;
+}
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return RR_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return rr_fail(RR_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cap = bytes;
+        return RR_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct rr_tc_state {
+    CUtensorMap tmap_c;
+    const void* tmap_c_base = nullptr;
+    Buf q_bf16, qnorm, cand_keys, cand_cnt, kept_keys, kept_cnt, tau, overflow, rows, exact, flags, fb_q, fb_idx, fb_sims, fb_cnt;
+    int* h_nflag = nullptr;   // pinned
+    bool attr_set = false;
+};
+
+bool rr_tc_supported(int cc_major, int) { return cc_major == 10; }
+
+void rr_tc_destroy(rr_tc_state* s) {
+    if (!s) return;
+    for (Buf* b : {&s->q_bf16, &s->qnorm, &s->cand_keys, &s->cand_cnt, &s->kept_keys, &s->kept_cnt, &s->tau, &s->overflow,
+                   &s->rows, &s->exact, &s->flags, &s->fb_q, &s->fb_idx, &s->fb_sims, &s->fb_cnt})
+        b->release();
+    if (s->h_nflag) cudaFreeHost(s->h_nflag);
+    delete s;
+}
+
+static int shortlist_size(int pool) {
+    const char* env = getenv("RR_TC_SHORTLIST_FACTOR");
+    double f = env ? atof(env) : 2.6;
+    if (!(f >= 1.0)) f = 2.6;
+    int kp = (int)std::ceil(pool * f);
+    kp = (kp + 63) / 64 * 64;
+    return std::max(kp, 64);
+}
+
+int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, const float* d_q, int32_t B,
+                     int32_t pool, int64_t* d_idx, float* d_sims, int32_t* d_count, rr_dense_stats* stats,
+                     rr_exact_fn exact_fn, void* exact_ctx, cudaStream_t s) {
+    if (d->dim_pad > TC_MAX_KB * TC_BK)
+        return rr_fail(RR_EUNSUPPORTED, "tensor path supports dim <= %d in this build", TC_MAX_KB * TC_BK);
+    const int KP = shortlist_size(pool);
+    if (KP + TC_CAP > 8192) return rr_fail(RR_EUNSUPPORTED, "tensor path supports pool <= %d", (int)((8192 - TC_CAP) / 2.6));
+    if (!*state) {
+        *state = new (std::nothrow) rr_tc_state();
+        if (!*state) return rr_fail(RR_ENOMEM, "out of host memory");
+    }
+    rr_tc_state* st = *state;
+    if (!st->h_nflag) RR_CUDA(cudaMallocHost(&st->h_nflag, sizeof(int)));
+    if (!st->attr_set) {
+        RR_CUDA(cudaFuncSetAttribute(tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
+        RR_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+        RR_CUDA(cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+        st->attr_set = true;
+    }
+    if (st->tmap_c_base != d->d_emb_bf16) {
+        RR_TRY(make_tmap_bf16_rows(&st->tmap_c, d->d_emb_bf16, (uint64_t)d->n_docs, (uint64_t)d->dim_pad, TC_BN));
+        st->tmap_c_base = d->d_emb_bf16;
+    }
+    const int n_qt = (B + TC_BM - 1) / TC_BM;
+    const int B_pad = n_qt * TC_BM;
+    RR_TRY(st->q_bf16.ensure(sizeof(__nv_bfloat16) * (size_t)B_pad * d->dim_pad));
+    RR_TRY(st->qnorm.ensure(sizeof(float) * (size_t)B_pad));
+    RR_TRY(st->cand_keys.ensure(sizeof(unsigned long long) * (size_t)B * TC_CAP));
+    RR_TRY(st->cand_cnt.ensure(sizeof(unsigned) * (size_t)B));
+    RR_TRY(st->kept_keys.ensure(sizeof(unsigned long long) * (size_t)B * KP));
+    RR_TRY(st->kept_cnt.ensure(sizeof(int) * (size_t)B));
+    RR_TRY(st->tau.ensure(sizeof(float) * (size_t)B));
+    RR_TRY(st->overflow.ensure(sizeof(int) * (size_t)B));
+    RR_TRY(st->rows.ensure(sizeof(long long) * (size_t)B * KP));
+    RR_TRY(st->exact.ensure(sizeof(float) * (size_t)B * KP));
+    RR_TRY(st->flags.ensure(sizeof(int) * ((size_t)B + 1)));
+    int* n_flagged = static_cast<int*>(st->flags.p);
+    int* flagged = n_flagged + 1;
+
+    CUtensorMap tmap_q;
+    RR_TRY(make_tmap_bf16_rows(&tmap_q, st->q_bf16.p, (uint64_t)B_pad, (uint64_t)d->dim_pad, TC_BM));
+
+    cvt_queries_kernel<<<B_pad, 128, 0, s>>>(d_q, B, d->dim, d->dim_pad, B_pad, static_cast<__nv_bfloat16*>(st->q_bf16.p),
+                                             static_cast<float*>(st->qnorm.p));
+    RR_LAUNCH_CHECK();
+    tc_reset_kernel<<<(B + 255) / 256, 256, 0, s>>>(static_cast<unsigned*>(st->cand_cnt.p), static_cast<int*>(st->kept_cnt.p),
+                                                    static_cast<float*>(st->tau.p), static_cast<int*>(st->overflow.p),
+                                                    n_flagged, B);
+    RR_LAUNCH_CHECK();
+
+    // split the query tiles into parts so that (tiles per part) x (CTAs per tile) fills the SMs
+    int best_parts = 1;
+    double best_cost = 1e30;
+    for (int parts = 1; parts <= 8 && parts <= n_qt; ++parts) {
+        double cost = 0;
+        bool ok = true;
+        for (int p = 0; p < parts; ++p) {
+            const int nq = n_qt / parts + (p < n_qt % parts ? 1 : 0);
+            if (nq > sm_count) { ok = false; break; }
+            cost += 1.0 / (double)(sm_count / nq);
+        }
+        if (ok && cost < best_cost - 1e-12) { best_cost = cost; best_parts = parts; }
+    }
+    if (best_cost > 1e29) return rr_fail(RR_EUNSUPPORTED, "batch too large for the tensor path (%d query tiles)", n_qt);
+
+    const int n_dt = (int)((d->n_docs + TC_BN - 1) / TC_BN);
+    int n_segments = 0;
+    int dt_lo = 0;
+    const size_t sel_smem = 8192 * 8;
+    while (dt_lo < n_dt) {
+        int dt_hi = dt_lo == 0 ? std::min(n_dt, TC_SEG0_TILES) : (int)std::min<long long>(n_dt, (long long)dt_lo * TC_GROWTH);
+        int qt0 = 0;
+        for (int p = 0; p < best_parts; ++p) {
+            const int nq = n_qt / best_parts + (p < n_qt % best_parts ? 1 : 0);
+            TcFilterArgs a;
+            a.n_docs = d->n_docs; a.n_kb = d->dim_pad / TC_BK; a.B = B; a.qt0 = qt0; a.n_qt = nq;
+            a.reps = std::max(1, std::min(sm_count / nq, dt_hi - dt_lo));
+            a.dt_lo = dt_lo; a.dt_hi = dt_hi; a.tau = static_cast<const float*>(st->tau.p);
+            a.cand_keys = static_cast<unsigned long long*>(st->cand_keys.p);
+            a.cand_cnt = static_cast<unsigned*>(st->cand_cnt.p);
+            tc_filter_kernel<<<nq * a.reps, TC_THREADS, TC_SMEM_TOTAL, s>>>(tmap_q, st->tmap_c, a);
+            RR_LAUNCH_CHECK();
+            qt0 += nq;
+        }
+        const int final_pass = dt_hi >= n_dt;
+        tc_select_kernel<<<B, 256, sel_smem, s>>>(static_cast<unsigned long long*>(st->cand_keys.p),
+                                                  static_cast<unsigned*>(st->cand_cnt.p),
+                                                  static_cast<unsigned long long*>(st->kept_keys.p),
+                                                  static_cast<int*>(st->kept_cnt.p), KP, static_cast<float*>(st->tau.p),
+                                                  static_cast<int*>(st->overflow.p), final_pass,
+                                                  static_cast<long long*>(st->rows.p));
+        RR_LAUNCH_CHECK();
+        dt_lo = dt_hi;
+        ++n_segments;
+    }
+    RR_TRY(rr_launch_rescore(d->d_emb_f32, d->n_docs, d->dim, d_q, static_cast<const int64_t*>(st->rows.p), KP, B,
+                             static_cast<float*>(st->exact.p), s));
+    const float eps_rel = (0.0078125f + 0.000030517578125f + 1e-4f) * d->max_row_norm;
+    tc_finalize_kernel<<<B, 256, sel_smem, s>>>(static_cast<const unsigned long long*>(st->kept_keys.p),
+                                                static_cast<const int*>(st->kept_cnt.p), KP,
+                                                static_cast<const float*>(st->exact.p), static_cast<const int*>(st->overflow.p),
+                                                static_cast<const float*>(st->qnorm.p), eps_rel, pool,
+                                                reinterpret_cast<long long*>(d_idx), d_sims, d_count, n_flagged, flagged);
+    RR_LAUNCH_CHECK();
+    RR_CUDA(cudaMemcpyAsync(st->h_nflag, n_flagged, sizeof(int), cudaMemcpyDeviceToHost, s));
+    RR_CUDA(cudaStreamSynchronize(s));
+    const int nf = *st->h_nflag;
+    if (stats) {
+        stats->path = 2; stats->n_uncertified = nf; stats->n_overflow = 0; stats->shortlist = KP;
+        stats->n_segments = n_segments; stats->eps = eps_rel;
+    }
+    if (nf > 0) {
+        // redo the uncertified queries on the exact fp32 path
+        RR_TRY(st->fb_q.ensure(sizeof(float) * (size_t)nf * d->dim));
+        RR_TRY(st->fb_idx.ensure(sizeof(long long) * (size_t)nf * pool));
+        RR_TRY(st->fb_sims.ensure(sizeof(float) * (size_t)nf * pool));
+        RR_TRY(st->fb_cnt.ensure(sizeof(int32_t) * (size_t)nf));
+        tc_gather_queries_kernel<<<nf, 128, 0, s>>>(d_q, flagged, d->dim, static_cast<float*>(st->fb_q.p));
+        RR_LAUNCH_CHECK();
+        RR_TRY(exact_fn(exact_ctx, static_cast<const float*>(st->fb_q.p), nf, pool, static_cast<int64_t*>(st->fb_idx.p),
+                        static_cast<float*>(st->fb_sims.p), static_cast<int32_t*>(st->fb_cnt.p), s));
+        tc_scatter_results_kernel<<<nf, 128, 0, s>>>(flagged, pool, static_cast<const long long*>(st->fb_idx.p),
+                                                     static_cast<const float*>(st->fb_sims.p),
+                                                     static_cast<const int32_t*>(st->fb_cnt.p),
+                                                     reinterpret_cast<long long*>(d_idx), d_sims, d_count);
+        RR_LAUNCH_CHECK();
+    }
+    return RR_OK;
+}

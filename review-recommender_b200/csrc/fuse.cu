@@ -359,7 +359,8 @@ int rr_launch_fuse(const rr_fusion_params* p, int B, int n_in, const int32_t* d_
     const int n_pad_in = next_pow2(n_in), n_pad_pool = next_pow2(p->pool);
     const int n_pad = n_pad_in > n_pad_pool ? n_pad_in : n_pad_pool;
     const size_t smem = (size_t)n_pad * 8 + (size_t)(n_pad + (n_pad & 1)) * 4 + (size_t)p->pool * (8 * 3 + 4 * 3) + 16;
-    if (smem > 48 * 1024)
+    // ~21 KB of static shared memory on top: opt in whenever the sum may pass the 48 KB default
+    if (smem > 24 * 1024)
         RR_CUDA(cudaFuncSetAttribute(fuse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fuse_topk_kernel<<<B, FUSE_THREADS, smem, stream>>>(a, n_pad_in, n_pad_pool);
     RR_LAUNCH_CHECK();

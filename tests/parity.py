@@ -87,7 +87,11 @@ def check_hybrid_against_oracle(n, d, v, b, l, k, device="cuda:0", driver="strea
     fusion = rr.engine.Fusion(k=k, driver=driver, **kw)
     nterms = np.full(b, l, dtype=np.int32)
     rows, final = ix.hybrid_search_host(q, qt.astype(np.int32), nterms, fusion, mode=mode)
-    ref = oracle_hybrid(c, q, qt, k, driver, **kw)
+    okw = dict(rerank_k=fusion.rerank_k, w_dense=fusion.w_dense, w_bm25=fusion.w_bm25, w_rerank=fusion.w_rerank,
+               w_prior=fusion.w_prior, w_best=fusion.w_best, prior_C=fusion.prior_C)
+    if driver == "streamlit":
+        okw["min_reviews"] = fusion.min_reviews
+    ref = oracle_hybrid(c, q, qt, k, driver, **okw)
     exact = 0
     for i, (top, pool) in enumerate(ref):
         ref_rows = top["_row"].values

@@ -1,0 +1,68 @@
+"""Tensor-core shortlist path (tcgen05 bf16 GEMM + threshold filter + exact rescoring +
+certification) against the exact fp32 path: results must be BIT-IDENTICAL (same rows, same
+similarities), because every similarity returned is the canonical fp32 dot product and
+uncertified queries are redone exactly."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle.primitives import cosine_topk_canonical
+from tests.parity import DENSE_ATOL, assert_ids_match_modulo_ties
+
+
+def _rr():
+    import review_recommender_b200 as rr
+    return rr
+
+
+def _both(ix, q, pool):
+    rr = _rr()
+    i1, s1, c1 = ix.dense_topk(q, pool, rr._lib.RR_DENSE_EXACT)
+    i2, s2, c2 = ix.dense_topk(q, pool, rr._lib.RR_DENSE_TENSOR)
+    st = ix.dense_stats()
+    return (i1.cpu().numpy(), s1.cpu().numpy(), c1.cpu().numpy()), (i2.cpu().numpy(), s2.cpu().numpy(), c2.cpu().numpy()), st
+
+
+@pytest.mark.parametrize("n,d,b,pool", [(5000, 64, 40, 20), (70_000, 384, 200, 150), (33_333, 100, 130, 150),
+                                         (300_000, 384, 256, 150), (1000, 128, 3, 150)])
+def test_tensor_path_equals_exact_path(n, d, b, pool):
+    rr = _rr()
+    emb = rr.synth.embeddings(n, d)
+    q = rr.synth.queries(b, d)
+    ix = rr.engine.HybridIndex(emb, device="cuda:0")
+    (i1, s1, c1), (i2, s2, c2), st = _both(ix, q, pool)
+    print("tensor path stats:", st)
+    assert st["path"] == 2
+    np.testing.assert_array_equal(c1, c2)
+    np.testing.assert_array_equal(i1, i2)
+    np.testing.assert_array_equal(s1, s2)
+    assert st["n_uncertified"] <= max(1, b // 10)
+    # and both agree with NumPy on a few queries
+    for i in range(min(b, 3)):
+        ref_idx, ref_sims = cosine_topk_canonical(q[i], emb, pool)
+        kk = len(ref_idx)
+        np.testing.assert_allclose(s2[i, :kk], ref_sims, rtol=0, atol=DENSE_ATOL)
+        assert_ids_match_modulo_ties(i2[i, :kk], s2[i, :kk], ref_idx, ref_sims, 2 * DENSE_ATOL)
+    ix.close()
+
+
+def test_near_duplicates_fall_back_to_exact_and_stay_exact():
+    """Rows that differ by less than the bf16 error bound cannot be certified from bf16 scores;
+    the query must be redone by the exact path and still return the exact answer."""
+    rr = _rr()
+    n, d = 40_000, 128
+    emb = rr.synth.embeddings(n, d)
+    rng = np.random.default_rng(3)
+    base = emb[17].copy()
+    for r in range(1000, 1600):                       # 600 rows within 1e-4 of row 17
+        v = base + 1e-4 * rng.standard_normal(d).astype(np.float32)
+        emb[r] = v / np.linalg.norm(v)
+    q = np.stack([base, rr.synth.queries(1, d)[0]])
+    ix = rr.engine.HybridIndex(emb, device="cuda:0")
+    (i1, s1, c1), (i2, s2, c2), st = _both(ix, q, 150)
+    print("tensor path stats:", st)
+    assert st["n_uncertified"] >= 1
+    np.testing.assert_array_equal(i1, i2)
+    np.testing.assert_array_equal(s1, s2)
+    ix.close()

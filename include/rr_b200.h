@@ -148,7 +148,7 @@ int rr_candidate_tuples(rr_index*, const int32_t* d_term_ids, const int32_t* d_n
  * order -- only meaningful when n_in == pool), d_best, d_gate.
  * Outputs: d_top_row int64[B, k] global rows (-1 padding), d_top_final float[B, k],
  * d_top_pos int32[B, k] pool positions; d_components float[B, pool, 8] or NULL:
- * {dense_mm, bm25_mm, prior, trust, final, dense_raw, bm25_raw, (float)global_row_low}. */
+ * {dense_mm, bm25_mm, prior, trust, final, dense_raw, bm25_raw, volume}. */
 typedef struct rr_fusion_params {
     double w_dense, w_bm25, w_rerank, w_prior, w_best;
     double prior_C;
@@ -167,6 +167,15 @@ int rr_fuse_topk(const rr_fusion_params*, int32_t B, int32_t n_in, const int32_t
                  const float* d_rerank, const float* d_best, const float* d_gate,
                  int64_t* d_top_row, float* d_top_final, int32_t* d_top_pos, float* d_components,
                  int device, rr_stream);
+
+/* Same, for tuples received from n_shards row shards (the cross-shard merge of a row-sharded
+ * corpus): shard s holds its [B, per_shard] block of every field at byte offset
+ * s*shard_stride_bytes from the field's base pointer (n_in = n_shards*per_shard). */
+int rr_fuse_topk_sharded(const rr_fusion_params*, int32_t B, int32_t n_shards, int32_t per_shard,
+                         int64_t shard_stride_bytes,
+                         const float* d_dense, const float* d_bm25, const double* d_n_reviews,
+                         const double* d_avg_stars, const int64_t* d_global_row,
+                         int64_t* d_top_row, float* d_top_final, int device, rr_stream);
 
 /* One-shot single-shard search (rerank/best/gate absent): dense top-pool -> tuples -> fuse. */
 int rr_hybrid_search(rr_index*, const float* d_q, const int32_t* d_term_ids, const int32_t* d_n_terms,
@@ -192,6 +201,23 @@ typedef struct rr_dense_stats {
     float   eps;             /* bf16 score error bound used for certification */
 } rr_dense_stats;
 int rr_dense_last_stats(rr_index*, rr_dense_stats* out);
+
+/* Per-kernel-class device timing for bench.py: while enabled, every launch of the classes below is
+ * bracketed by CUDA events on its own stream.  rr_profile_collect synchronises those events and
+ * returns, per class, the summed milliseconds and the number of launches since the last collect. */
+#define RR_PROF_BM25_TILE   0
+#define RR_PROF_BM25_CAND   1
+#define RR_PROF_DENSE_GEMV  2
+#define RR_PROF_SELECT_ROWS 3
+#define RR_PROF_TC_FILTER   4
+#define RR_PROF_TC_SELECT   5
+#define RR_PROF_RESCORE     6
+#define RR_PROF_TC_FINALIZE 7
+#define RR_PROF_FUSE        8
+#define RR_PROF_MISC        9
+#define RR_PROF_CLASSES    10
+int rr_profile_enable(int on);
+int rr_profile_collect(double* h_ms, int64_t* h_launches, int32_t n_classes);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,8 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "librr_b200.so"
 
 RR_DENSE_AUTO, RR_DENSE_EXACT, RR_DENSE_TENSOR = 0, 1, 2
+PROF_CLASSES = ["bm25_tile", "bm25_cand", "dense_gemv", "select_rows", "tc_filter", "tc_select", "rescore",
+                "tc_finalize", "fuse", "misc"]
 
 
 class RRError(RuntimeError):
@@ -66,6 +68,10 @@ SIGNATURES = {
     "rr_candidate_tuples": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "rr_fuse_topk": (C.c_int, [C.POINTER(FusionParams), C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                _P, _P, _P, _P, C.c_int, _P]),
+    "rr_fuse_topk_sharded": (C.c_int, [C.POINTER(FusionParams), C.c_int32, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P,
+                                       _P, _P, _P, _P, C.c_int, _P]),
+    "rr_profile_enable": (C.c_int, [C.c_int]),
+    "rr_profile_collect": (C.c_int, [_P, _P, C.c_int32]),
     "rr_hybrid_search": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(FusionParams), C.c_int32,
                                    _P, _P, _P]),
     "rr_hybrid_search_host": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(FusionParams), C.c_int32,

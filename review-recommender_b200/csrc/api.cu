@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <vector>
 
 // ---------------------------------------------------------------------------------------------
 // errors / counters
@@ -28,6 +29,62 @@ extern "C" const char* rr_last_error(void) { return t_err; }
 extern "C" int rr_abi_version(void) { return 1; }
 extern "C" int64_t rr_launch_count(int reset) {
     return reset ? g_rr_launches.exchange(0) : g_rr_launches.load();
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-class kernel timing (bench.py): CUDA events on the launching stream
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct ProfRec { int cls; cudaEvent_t a, b; };
+std::mutex g_prof_mu;
+std::atomic<int> g_prof_on{0};
+std::vector<ProfRec*> g_prof_live, g_prof_free;
+}  // namespace
+
+RrProfScope::RrProfScope(int cls_, cudaStream_t s) : cls(cls_), stream(s), rec(nullptr) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfRec* r = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_prof_mu);
+        if (!g_prof_free.empty()) { r = g_prof_free.back(); g_prof_free.pop_back(); }
+    }
+    if (!r) {
+        r = new (std::nothrow) ProfRec();
+        if (!r) return;
+        if (cudaEventCreate(&r->a) != cudaSuccess || cudaEventCreate(&r->b) != cudaSuccess) { delete r; return; }
+    }
+    r->cls = cls;
+    cudaEventRecord(r->a, stream);
+    rec = r;
+}
+RrProfScope::~RrProfScope() {
+    if (!rec) return;
+    ProfRec* r = static_cast<ProfRec*>(rec);
+    cudaEventRecord(r->b, stream);
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    g_prof_live.push_back(r);
+}
+
+extern "C" int rr_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); return RR_OK; }
+
+extern "C" int rr_profile_collect(double* h_ms, int64_t* h_launches, int32_t n_classes) {
+    if (!h_ms || !h_launches || n_classes < RR_PROF_CLASSES) return rr_fail(RR_EINVAL, "rr_profile_collect: need %d classes", RR_PROF_CLASSES);
+    for (int i = 0; i < n_classes; ++i) { h_ms[i] = 0.0; h_launches[i] = 0; }
+    std::vector<ProfRec*> live;
+    {
+        std::lock_guard<std::mutex> lock(g_prof_mu);
+        live.swap(g_prof_live);
+    }
+    for (ProfRec* r : live) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r->b) == cudaSuccess && cudaEventElapsedTime(&ms, r->a, r->b) == cudaSuccess) {
+            h_ms[r->cls] += ms;
+            h_launches[r->cls] += 1;
+        }
+    }
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    for (ProfRec* r : live) g_prof_free.push_back(r);
+    return RR_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -238,9 +295,21 @@ extern "C" int rr_fuse_topk(const rr_fusion_params* p, int32_t B, int32_t n_in, 
                             const float* d_best, const float* d_gate, int64_t* d_top_row, float* d_top_final,
                             int32_t* d_top_pos, float* d_components, int device, rr_stream stream) {
     RR_CUDA(cudaSetDevice(device));
-    return rr_launch_fuse(p, B, n_in, d_count, d_dense, d_bm25, d_n_reviews, d_avg_stars, d_global_row, d_rerank,
+    return rr_launch_fuse(p, B, n_in, 1, 0, d_count, d_dense, d_bm25, d_n_reviews, d_avg_stars, d_global_row, d_rerank,
                           d_best, d_gate, d_top_row, d_top_final, d_top_pos, d_components,
                           static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rr_fuse_topk_sharded(const rr_fusion_params* p, int32_t B, int32_t n_shards, int32_t per_shard,
+                                    int64_t shard_stride_bytes, const float* d_dense, const float* d_bm25,
+                                    const double* d_n_reviews, const double* d_avg_stars, const int64_t* d_global_row,
+                                    int64_t* d_top_row, float* d_top_final, int device, rr_stream stream) {
+    if (n_shards <= 0 || per_shard <= 0 || (shard_stride_bytes & 7))
+        return rr_fail(RR_EINVAL, "rr_fuse_topk_sharded: bad shard geometry");
+    RR_CUDA(cudaSetDevice(device));
+    return rr_launch_fuse(p, B, n_shards * per_shard, n_shards, shard_stride_bytes, nullptr, d_dense, d_bm25,
+                          d_n_reviews, d_avg_stars, d_global_row, nullptr, nullptr, nullptr, d_top_row, d_top_final,
+                          nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -267,7 +336,7 @@ static int hybrid_locked(rr_index* ix, const float* d_q, const int32_t* d_term_i
     int32_t* count = c.take<int32_t>((size_t)B);
     RR_TRY(dense_topk_locked(ix, d_q, B, pool, dense_mode, cand, dense, count, s));
     RR_TRY(candidates_locked(ix, d_term_ids, d_n_terms, B, l_max, cand, pool, bm25, nrev, avg, grow, s));
-    return rr_launch_fuse(fp, B, pool, count, dense, bm25, nrev, avg, grow, nullptr, nullptr, nullptr, d_top_row,
+    return rr_launch_fuse(fp, B, pool, 1, 0, count, dense, bm25, nrev, avg, grow, nullptr, nullptr, nullptr, d_top_row,
                           d_top_final, nullptr, nullptr, s);
 }
 

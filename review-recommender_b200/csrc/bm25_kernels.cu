@@ -221,6 +221,7 @@ int rr_launch_bm25_tile_scores(const uint64_t* d_postings, const uint64_t* d_til
     for (int b0 = 0; b0 < B; b0 += 65535) {
         const int nb = min(65535, B - b0);
         dim3 grid((unsigned)n_tiles, (unsigned)nb);
+        RrProfScope prof(RR_PROF_BM25_TILE, stream);
         bm25_tile_scores_kernel<<<grid, BM25_THREADS, smem, stream>>>(
             reinterpret_cast<const uint4*>(d_postings), d_tile_base, d_blk_off, V, T, (long long)n_docs,
             d_terms + (int64_t)b0 * l_max, d_nterms + b0, l_max, d_out + (int64_t)b0 * ld_out, (long long)ld_out);
@@ -238,6 +239,7 @@ int rr_launch_bm25_candidates(const uint64_t* d_postings, const uint64_t* d_tile
     if (total <= 0) return RR_OK;
     const int threads = 256;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    RrProfScope prof(RR_PROF_BM25_CAND, stream);
     bm25_candidates_kernel<<<blocks, threads, 0, stream>>>(
         reinterpret_cast<const uint2*>(d_postings), d_tile_base, d_blk_off, V, T, (long long)n_docs, d_terms, d_nterms,
         l_max, reinterpret_cast<const long long*>(d_cand), pool, B, d_nrev, d_avg, (long long)row_offset, d_bm25,

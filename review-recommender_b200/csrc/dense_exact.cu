@@ -320,6 +320,7 @@ int rr_launch_dense_scores_f32(const float* d_emb, int64_t n_rows, int D, const 
         RR_CUDA(cudaFuncSetAttribute(dense_scores_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RR_CUDA(cudaFuncSetAttribute(dense_scores_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+    RrProfScope prof(RR_PROF_DENSE_GEMV, stream);
     if (vec4)
         dense_scores_f32_kernel<true><<<grid, GEMV_THREADS, smem, stream>>>(d_emb, n_rows, D, d_q, n_queries, d_scores, ld_scores);
     else
@@ -335,6 +336,7 @@ int rr_launch_rescore(const float* d_emb, int64_t n_rows, int D, const float* d_
     const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_emb) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(d_q) & 15) == 0);
     const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+    RrProfScope prof(RR_PROF_RESCORE, stream);
     if (vec4)
         rescore_kernel<true><<<blocks, 256, 0, stream>>>(d_emb, n_rows, D, d_q, reinterpret_cast<const long long*>(d_rows), n_slots, B, d_out);
     else
@@ -357,6 +359,7 @@ int rr_launch_topk_rows(const float* d_scores, int64_t ld, int64_t n, int rows, 
     p += sizeof(unsigned) * (size_t)rows * RS_BINS;
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(p);
     const int k_cap = max(kk, 1);
+    RrProfScope prof(RR_PROF_SELECT_ROWS, stream);
 
     rs_init_kernel<<<max(1, min(1024, rows * 8)), 256, 0, stream>>>(st, hist, rows, kk);
     RR_LAUNCH_CHECK();

@@ -581,11 +581,15 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
             a.dt_lo = dt_lo; a.dt_hi = dt_hi; a.tau = static_cast<const float*>(st->tau.p);
             a.cand_keys = static_cast<unsigned long long*>(st->cand_keys.p);
             a.cand_cnt = static_cast<unsigned*>(st->cand_cnt.p);
-            tc_filter_kernel<<<nq * a.reps, TC_THREADS, TC_SMEM_TOTAL, s>>>(tmap_q, st->tmap_c, a);
+            {
+                RrProfScope prof(RR_PROF_TC_FILTER, s);
+                tc_filter_kernel<<<nq * a.reps, TC_THREADS, TC_SMEM_TOTAL, s>>>(tmap_q, st->tmap_c, a);
+            }
             RR_LAUNCH_CHECK();
             qt0 += nq;
         }
         const int final_pass = dt_hi >= n_dt;
+        RrProfScope prof_sel(RR_PROF_TC_SELECT, s);
         tc_select_kernel<<<B, 256, sel_smem, s>>>(static_cast<unsigned long long*>(st->cand_keys.p),
                                                   static_cast<unsigned*>(st->cand_cnt.p),
                                                   static_cast<unsigned long long*>(st->kept_keys.p),
@@ -599,11 +603,13 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
     RR_TRY(rr_launch_rescore(d->d_emb_f32, d->n_docs, d->dim, d_q, static_cast<const int64_t*>(st->rows.p), KP, B,
                              static_cast<float*>(st->exact.p), s));
     const float eps_rel = (0.0078125f + 0.000030517578125f + 1e-4f) * d->max_row_norm;
+    RrProfScope* prof_fin = new RrProfScope(RR_PROF_TC_FINALIZE, s);
     tc_finalize_kernel<<<B, 256, sel_smem, s>>>(static_cast<const unsigned long long*>(st->kept_keys.p),
                                                 static_cast<const int*>(st->kept_cnt.p), KP,
                                                 static_cast<const float*>(st->exact.p), static_cast<const int*>(st->overflow.p),
                                                 static_cast<const float*>(st->qnorm.p), eps_rel, pool,
                                                 reinterpret_cast<long long*>(d_idx), d_sims, d_count, n_flagged, flagged);
+    delete prof_fin;
     RR_LAUNCH_CHECK();
     RR_CUDA(cudaMemcpyAsync(st->h_nflag, n_flagged, sizeof(int), cudaMemcpyDeviceToHost, s));
     RR_CUDA(cudaStreamSynchronize(s));

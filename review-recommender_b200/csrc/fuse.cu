@@ -32,6 +32,8 @@ constexpr int FUSE_MAX_LEAVES = 256;
 struct FuseArgs {
     rr_fusion_params p;
     int B, n_in;
+    int n_shards;            // tuples come from n_shards blocks of per_shard = n_in / n_shards entries
+    long long shard_stride;  // bytes between consecutive shard blocks of one field
     const int32_t* count;
     const float* dense;
     const float* bm25;
@@ -125,17 +127,22 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
     __shared__ double s_g;
 
     const int b = blockIdx.x, tid = threadIdx.x;
-    const long long in0 = (long long)b * a.n_in;
+    const int per_shard = a.n_in / a.n_shards;
     const int cnt_in = a.count ? min(a.count[b], a.n_in) : a.n_in;
+    // element index of input slot i for a field whose elements are `esz` bytes wide
+    auto at = [&](int i, int esz) -> long long {
+        const int s = i / per_shard, j = i - s * per_shard;
+        return (long long)s * (a.shard_stride / esz) + (long long)b * per_shard + j;
+    };
 
     // ---- 1. order candidates by (dense desc, global row asc), cut to pool -----------------------
     int n_valid_local = 0;
     for (int i = tid; i < n_pad_in; i += FUSE_THREADS) {
         unsigned long long k = 0ull;
         if (i < a.n_in) {
-            const long long g = a.grow[in0 + i];
+            const long long g = a.grow[at(i, 8)];
             const bool ok = g >= 0 && (a.count == nullptr || a.n_in != a.p.pool || i < cnt_in);
-            if (ok) { k = rr_make_key(a.dense[in0 + i], (uint32_t)g) | 0ull; if (k == 0ull) k = 1ull; ++n_valid_local; }
+            if (ok) { k = rr_make_key(a.dense[at(i, 4)], (uint32_t)g); if (k == 0ull) k = 1ull; ++n_valid_local; }
         }
         key[i] = k;
         val[i] = (unsigned)i;
@@ -147,16 +154,16 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
 
     // ---- 2. load the pool -----------------------------------------------------------------------
     for (int i = tid; i < P; i += FUSE_THREADS) {
-        const long long s = in0 + val[i];
-        s_dense[i] = a.dense[s];
-        s_bm25[i] = a.bm25 ? a.bm25[s] : 0.f;
-        s_n[i] = a.n ? a.n[s] : 0.0;
-        s_avg[i] = a.avg ? a.avg[s] : nan64();
+        const int s = (int)val[i];
+        s_dense[i] = a.dense[at(s, 4)];
+        s_bm25[i] = a.bm25 ? a.bm25[at(s, 4)] : 0.f;
+        s_n[i] = a.n ? a.n[at(s, 8)] : 0.0;
+        s_avg[i] = a.avg ? a.avg[at(s, 8)] : nan64();
     }
     __syncthreads();
     // keep the slot of every pool position (val is reused by the second sort)
     // -> stash global rows in key[] after the sort is consumed
-    for (int i = tid; i < P; i += FUSE_THREADS) key[i] = (unsigned long long)a.grow[in0 + val[i]];
+    for (int i = tid; i < P; i += FUSE_THREADS) key[i] = (unsigned long long)a.grow[at((int)val[i], 8)];
     __syncthreads();
 
     // ---- 3. min-max of dense and bm25 (float32 semantics) ----------------------------------------
@@ -296,7 +303,7 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
         if (a.components) {
             float* c = a.components + ((long long)b * a.p.pool + i) * 8;
             c[0] = dm; c[1] = bm; c[2] = (float)prior; c[3] = trust; c[4] = fin;
-            c[5] = s_dense[i]; c[6] = s_bm25[i]; c[7] = (float)(unsigned)(key[i] & 0xFFFFFFull);
+            c[5] = s_dense[i]; c[6] = s_bm25[i]; c[7] = (float)vol;
         }
     }
     if (a.components) {
@@ -339,7 +346,8 @@ int next_pow2(int v) { int p = 2; while (p < v) p <<= 1; return p; }
 
 }  // namespace
 
-int rr_launch_fuse(const rr_fusion_params* p, int B, int n_in, const int32_t* d_count, const float* d_dense,
+int rr_launch_fuse(const rr_fusion_params* p, int B, int n_in, int n_shards, int64_t shard_stride_bytes,
+                   const int32_t* d_count, const float* d_dense,
                    const float* d_bm25, const double* d_n, const double* d_avg, const int64_t* d_grow,
                    const float* d_rerank, const float* d_best, const float* d_gate, int64_t* d_top_row,
                    float* d_top_final, int32_t* d_top_pos, float* d_components, cudaStream_t stream) {
@@ -352,7 +360,9 @@ int rr_launch_fuse(const rr_fusion_params* p, int B, int n_in, const int32_t* d_
         return rr_fail(RR_EINVAL, "rr_fuse_topk: rerank/best/gate are given in pool order and need n_in == pool");
     if (B == 0) return RR_OK;
     FuseArgs a;
-    a.p = *p; a.B = B; a.n_in = n_in; a.count = d_count; a.dense = d_dense; a.bm25 = d_bm25; a.n = d_n; a.avg = d_avg;
+    a.p = *p; a.B = B; a.n_in = n_in; a.n_shards = n_shards > 0 ? n_shards : 1; a.shard_stride = shard_stride_bytes;
+    if (n_in % a.n_shards) return rr_fail(RR_EINVAL, "rr_fuse_topk: n_in must be a multiple of n_shards");
+    a.count = d_count; a.dense = d_dense; a.bm25 = d_bm25; a.n = d_n; a.avg = d_avg;
     a.grow = reinterpret_cast<const long long*>(d_grow); a.rerank = d_rerank; a.best = d_best; a.gate = d_gate;
     a.top_row = reinterpret_cast<long long*>(d_top_row); a.top_final = d_top_final; a.top_pos = d_top_pos;
     a.components = d_components;
@@ -362,7 +372,10 @@ int rr_launch_fuse(const rr_fusion_params* p, int B, int n_in, const int32_t* d_
     // ~21 KB of static shared memory on top: opt in whenever the sum may pass the 48 KB default
     if (smem > 24 * 1024)
         RR_CUDA(cudaFuncSetAttribute(fuse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fuse_topk_kernel<<<B, FUSE_THREADS, smem, stream>>>(a, n_pad_in, n_pad_pool);
+    {
+        RrProfScope prof(RR_PROF_FUSE, stream);
+        fuse_topk_kernel<<<B, FUSE_THREADS, smem, stream>>>(a, n_pad_in, n_pad_pool);
+    }
     RR_LAUNCH_CHECK();
     return RR_OK;
 }

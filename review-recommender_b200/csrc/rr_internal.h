@@ -39,6 +39,13 @@ inline void rr_count_launch(int n = 1) { g_rr_launches.fetch_add(n, std::memory_
         if (_rc != RR_OK) return _rc; \
     } while (0)
 
+// device-side timing of one kernel class (no-op unless rr_profile_enable(1))
+struct RrProfScope {
+    int cls; cudaStream_t stream; void* rec;
+    RrProfScope(int cls_, cudaStream_t s);
+    ~RrProfScope();
+};
+
 // order-preserving map float -> uint32 (larger float => larger key); NaN maps below -inf
 __host__ __device__ inline uint32_t rr_float_key(float f) {
     uint32_t u;

@@ -28,7 +28,8 @@ int rr_launch_topk_rows(const float* d_scores, int64_t ld, int64_t n, int rows, 
                         cudaStream_t stream);
 
 // fuse.cu
-int rr_launch_fuse(const rr_fusion_params* p, int B, int n_in, const int32_t* d_count, const float* d_dense,
+int rr_launch_fuse(const rr_fusion_params* p, int B, int n_in, int n_shards, int64_t shard_stride_bytes,
+                   const int32_t* d_count, const float* d_dense,
                    const float* d_bm25, const double* d_n, const double* d_avg, const int64_t* d_grow,
                    const float* d_rerank, const float* d_best, const float* d_gate, int64_t* d_top_row,
                    float* d_top_final, int32_t* d_top_pos, float* d_components, cudaStream_t stream);

@@ -1,0 +1,118 @@
+"""Row-sharded hybrid search: one process per GPU, `torch.distributed` (NCCL over NVLink) for the
+single exchange step the path has.
+
+The reference has no distributed code; the sharding follows BASELINE.json's
+north_star: the corpus is cut row-wise, every rank holds rows [row_offset, row_offset+n) with the
+postings of those rows and GLOBAL BM25 statistics, and per batch
+
+  1. every rank computes, for ALL B queries, its local exact top-`pool` by dense similarity and the
+     candidate tuples (dense, bm25, n_reviews, avg_stars, global row) -- K2/K3 + K1 candidates;
+  2. ONE all-to-all ships, to rank r, the tuples of query slice r from every shard
+     (B*pool*32 bytes leave each rank; an all-gather would move G times more);
+  3. rank r merges its G*pool tuples per query by (dense desc, global row asc), keeps `pool`
+     (exact: the global top-pool is a subset of the union of local top-pools) and runs the fusion
+     kernel (K4) on the merged pool -- min-max and nanmean are pool-global, so they must run after
+     the merge;
+  4. one small all-gather returns the [B, k] results to every rank.
+
+The pack / exchange / unpack helpers are device-agnostic so that the plumbing is tested on CPU
+with gloo (tests/test_dist_cpu.py); the compute calls need the CUDA library.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+TUPLE_BYTES = 32   # int64 row + float64 n + float64 avg + float32 dense + float32 bm25
+
+
+def all_reduce_stats(stats, group=None, device="cpu"):
+    """Sum / min the per-shard BM25 statistics (engine.BM25Stats.local) over the ranks, in place."""
+    import numpy as np
+    df = torch.from_numpy(stats.df).to(device)
+    fp = torch.from_numpy(stats.first_pos).to(device)
+    tot = torch.tensor([stats.total_tokens, stats.n_docs], dtype=torch.int64, device=device)
+    dist.all_reduce(df, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(fp, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    stats.df = np.ascontiguousarray(df.cpu().numpy())
+    stats.first_pos = np.ascontiguousarray(fp.cpu().numpy())
+    stats.total_tokens, stats.n_docs = int(tot[0].item()), int(tot[1].item())
+    return stats
+
+
+def pack_tuples(world: int, grow: torch.Tensor, n: torch.Tensor, avg: torch.Tensor, dense: torch.Tensor,
+                bm25: torch.Tensor) -> torch.Tensor:
+    """[B, pool] field tensors -> uint8 [world, (B/world)*pool*32]: block g holds, for the query
+    slice owned by rank g, the five fields back to back (rows, n, avg, dense, bm25)."""
+    B = grow.shape[0]
+    assert B % world == 0, "pad the batch to a multiple of the world size"
+
+    def blk(t):
+        return t.contiguous().view(world, -1).view(torch.uint8)
+    return torch.cat([blk(grow), blk(n), blk(avg), blk(dense), blk(bm25)], dim=1).contiguous()
+
+
+def exchange(send: torch.Tensor, group=None) -> torch.Tensor:
+    """all-to-all of the packed blocks: recv[s] = block that shard s addressed to this rank."""
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
+    return recv
+
+
+def field_views(recv: torch.Tensor, per_rank_queries: int, pool: int):
+    """Views of the received buffer: for each field the [bytes] tensor starting at shard 0's block of
+    that field; shard s's block of the same field starts `stride` bytes later."""
+    bp = per_rank_queries * pool
+    flat = recv.view(-1)
+    stride = bp * TUPLE_BYTES
+    off = {"grow": 0, "n": bp * 8, "avg": bp * 16, "dense": bp * 24, "bm25": bp * 28}
+    return {k: flat[v:] for k, v in off.items()}, stride
+
+
+def unpack_shard(recv: torch.Tensor, shard: int, per_rank_queries: int, pool: int):
+    """(grow i64, n f64, avg f64, dense f32, bm25 f32) [per_rank_queries, pool] of one source shard
+    (used by tests and debugging; the fusion kernel reads the packed buffer directly)."""
+    views, stride = field_views(recv, per_rank_queries, pool)
+    bp = per_rank_queries * pool
+
+    def take(name, dtype, esz):
+        b = views[name][shard * stride: shard * stride + bp * esz]
+        return b.view(dtype).view(per_rank_queries, pool)
+    return (take("grow", torch.int64, 8), take("n", torch.float64, 8), take("avg", torch.float64, 8),
+            take("dense", torch.float32, 4), take("bm25", torch.float32, 4))
+
+
+class ShardedSearcher:
+    """Hybrid search over a row-sharded corpus; call `search` collectively on every rank."""
+
+    def __init__(self, index, group=None):
+        self.ix = index
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def search(self, q: torch.Tensor, term_ids: Optional[torch.Tensor], n_terms: Optional[torch.Tensor], fusion,
+               mode: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """q float32[B, D] (identical on every rank, B % world == 0) -> (global rows int64[B, k],
+        final float32[B, k]) on every rank."""
+        ix, G = self.ix, self.world
+        B, pool, k = int(q.shape[0]), fusion.pool, fusion.k
+        if B % G:
+            raise ValueError("batch size must be a multiple of the world size")
+        Bg = B // G
+        cand, dense, _cnt = ix.dense_topk(q, pool, mode)
+        bm25, n, avg, grow = ix.candidate_tuples(term_ids, n_terms, cand)
+        recv = exchange(pack_tuples(G, grow, n, avg, dense, bm25), self.group)
+        views, stride = field_views(recv, Bg, pool)
+        rows, final = ix.fuse_sharded(fusion, G, pool, stride, Bg, views["dense"], views["bm25"], views["n"],
+                                      views["avg"], views["grow"])
+        # one collective for both outputs: [Bg, k] int64 rows | [Bg, k] float32 finals (as int64 words)
+        mine = torch.cat([rows.view(-1), final.view(-1).view(torch.int32).to(torch.int64)])
+        out = torch.empty((G, mine.numel()), dtype=torch.int64, device=mine.device)
+        dist.all_gather_into_tensor(out.view(-1), mine, group=self.group)
+        all_rows = out[:, :Bg * k].reshape(B, k)
+        all_final = out[:, Bg * k:].to(torch.int32).view(torch.float32).reshape(B, k)
+        return all_rows, all_final

@@ -340,6 +340,19 @@ class HybridIndex:
                                     _ptr(pos), _ptr(comp), self.device.index or 0, _stream()))
         return rows, final, pos, comp
 
+    def fuse_sharded(self, fusion: Fusion, n_shards: int, per_shard: int, shard_stride_bytes: int, B: int,
+                     dense, bm25, n, avg, grow):
+        """K4 over tuples received from `n_shards` row shards (cross-shard merge + fusion).  The field
+        tensors are views into one exchange buffer; shard s's [B, per_shard] block of a field starts
+        s*shard_stride_bytes after the field's base."""
+        p = fusion.to_c()
+        rows = torch.empty((B, fusion.k), dtype=torch.int64, device=self.device)
+        final = torch.empty((B, fusion.k), dtype=torch.float32, device=self.device)
+        check(self.lib.rr_fuse_topk_sharded(C.byref(p), B, n_shards, per_shard, shard_stride_bytes, _ptr(dense),
+                                            _ptr(bm25), _ptr(n), _ptr(avg), _ptr(grow), _ptr(rows), _ptr(final),
+                                            self.device.index or 0, _stream()))
+        return rows, final
+
     # ---- one-shot ------------------------------------------------------------------------------
     def hybrid_search(self, q, term_ids, n_terms, fusion: Fusion, mode: int = _lib.RR_DENSE_AUTO):
         """Device tensors in, device tensors out: (global rows int64[B,k], final f32[B,k])."""
@@ -375,6 +388,19 @@ class HybridIndex:
         check(self.lib.rr_hybrid_search_host(self._h, _ptr(q), _ptr(term_ids), _ptr(n_terms), B, lmax, C.byref(p),
                                              mode, _ptr(rows), _ptr(final), _stream()))
         return rows, final
+
+
+def profile_enable(on: bool) -> None:
+    check(_lib.load().rr_profile_enable(1 if on else 0))
+
+
+def profile_collect() -> Dict[str, Tuple[float, int]]:
+    """{kernel class: (summed device milliseconds, launches)} since the last collect."""
+    n = len(_lib.PROF_CLASSES)
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    check(_lib.load().rr_profile_collect(ms, cnt, n))
+    return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(_lib.PROF_CLASSES)}
 
 
 def launch_count(reset: bool = False) -> int:

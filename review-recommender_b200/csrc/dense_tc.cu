@@ -46,16 +46,18 @@ constexpr int TC_BN = 256;      // docs per tile (UMMA N)
 constexpr int TC_BK = 64;       // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int TC_STAGES = 4;
 constexpr int TC_MAX_KB = 6;    // dim_pad <= 384 keeps the query tile resident
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;     // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue (2 x 4 warps)
+constexpr int TC_EPI_THREADS = 256;
 constexpr int TC_Q_KB_BYTES = TC_BM * TC_BK * 2;    // 16 KB
 constexpr int TC_B_KB_BYTES = TC_BN * TC_BK * 2;    // 32 KB
 constexpr int TC_SMEM_Q = TC_MAX_KB * TC_Q_KB_BYTES;
 constexpr int TC_SMEM_B = TC_STAGES * TC_B_KB_BYTES;
 constexpr int TC_SMEM_BAR = 256;
 constexpr int TC_SMEM_TOTAL = TC_SMEM_Q + TC_SMEM_B + TC_SMEM_BAR + 1024;   // + alignment slack
-constexpr int TC_CAP = 4096;    // candidate slots per query per segment
-constexpr int TC_SEG0_TILES = TC_CAP / TC_BN;   // first segment passes everything (tau = -inf)
-constexpr int TC_GROWTH = 4;    // corpus prefix grows x4 per segment
+constexpr int TC_CAP_TOTAL = 16384;  // candidate slots per query per segment, split evenly over the CTAs
+                                     // that scan for that query (each owns a private sub-list: no atomics)
+constexpr int TC_SORT_MAX = 8192;    // largest per-query sort in tc_select_kernel (64 KB of keys)
+constexpr int TC_GROWTH = 4;         // corpus prefix grows x4 per segment
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -178,8 +180,9 @@ struct TcFilterArgs {
     int reps;          // CTAs per query tile
     int dt_lo, dt_hi;  // doc tiles of this segment
     const float* tau;  // [B]
-    unsigned long long* cand_keys;   // [B, TC_CAP]
-    unsigned* cand_cnt;              // [B]
+    int n_sub, cap_sub;              // sub-lists per query (2 per scanning CTA) and slots per sub-list
+    unsigned long long* cand_keys;   // [B, n_sub, cap_sub]
+    unsigned* cand_cnt;              // [B, n_sub]
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -208,7 +211,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_c);
         for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_THREADS); }
         mbar_init(qfull, 1);
         fence_barrier_init();
     }
@@ -263,37 +266,60 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: thread = query row, threshold filter =====
-        const int ew = warp - 4;                               // == warp % 4: TMEM lanes 32*ew .. 32*ew+31
+        // ===== epilogue: thread = (query row, column half), threshold filter =====
+        // Warps 4..7 read accumulator columns 0..127, warps 8..11 columns 128..255 (a warp may only touch
+        // TMEM lanes 32*(warp%4)..+31).  Every (CTA, query, half) owns a private candidate sub-list, so an
+        // append is a plain store with a register counter: no atomics, nothing to wait for.
+        const int ew = (warp - 4) & 3;
+        const int half = (warp - 4) >> 2;
         const int q = qt * TC_BM + ew * 32 + lane;
         const bool active = q < a.B;
         const float tau = active ? a.tau[q] : INFINITY;
-        unsigned long long* my_keys = a.cand_keys + (size_t)(active ? q : 0) * TC_CAP;
+        const int sub = j0 * 2 + half;
+        unsigned long long* my_keys = a.cand_keys + ((size_t)(active ? q : 0) * a.n_sub + sub) * a.cap_sub;
+        unsigned cnt = 0;
+        const unsigned cap = (unsigned)a.cap_sub;
         for (int t = 0; t < n_tiles; ++t) {
             const int as = t & 1;
             const uint32_t aphase = (uint32_t)((t >> 1) & 1);
             const int dt = a.dt_lo + j0 + t * a.reps;
             const long long doc_base = (long long)dt * TC_BN;
+            const int n_valid = (int)min((long long)TC_BN, a.n_docs - doc_base);   // rows past the corpus end are zero-filled
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * TC_BN);
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * TC_BN + half * (TC_BN / 2));
 #pragma unroll 1
-            for (int chunk = 0; chunk < TC_BN / 32; ++chunk) {
-                uint32_t v[32];
-                tmem_ld_x32(taddr0 + (uint32_t)(chunk * 32), v);
+            for (int chunk = 0; chunk < TC_BN / 64; chunk += 2) {
+                uint32_t v[2][32];
+                tmem_ld_x32(taddr0 + (uint32_t)(chunk * 32), v[0]);
+                tmem_ld_x32(taddr0 + (uint32_t)(chunk * 32 + 32), v[1]);
                 tmem_ld_wait();
-                float m = __uint_as_float(v[0]);
 #pragma unroll
-                for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-                if (active && m >= tau) {
+                for (int h = 0; h < 2; ++h) {
+                    // maxima of the four groups of 8, then descend only into groups that can hold a pass
+                    float m8[4];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float s = __uint_as_float(v[i]);
-                        if (s >= tau) {
-                            const long long doc = doc_base + chunk * 32 + i;
-                            if (doc < a.n_docs) {
-                                const unsigned slot = atomicAdd(&a.cand_cnt[q], 1u);
-                                if (slot < (unsigned)TC_CAP) my_keys[slot] = rr_make_key(s, (uint32_t)doc);
+                    for (int g = 0; g < 4; ++g) {
+                        float m = __uint_as_float(v[h][8 * g]);
+#pragma unroll
+                        for (int e = 1; e < 8; ++e) m = fmaxf(m, __uint_as_float(v[h][8 * g + e]));
+                        m8[g] = m;
+                    }
+                    const float m32 = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+                    if (active && m32 >= tau) {
+                        const int c0 = half * (TC_BN / 2) + (chunk + h) * 32;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (m8[g] >= tau) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const float s = __uint_as_float(v[h][8 * g + e]);
+                                    const int col = c0 + 8 * g + e;
+                                    if (s >= tau && col < n_valid) {
+                                        if (cnt < cap) my_keys[cnt] = rr_make_key(s, (uint32_t)(doc_base + col));
+                                        ++cnt;
+                                    }
+                                }
                             }
                         }
                     }
@@ -302,6 +328,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             tc_fence_before();
             mbar_arrive(&tempty[as]);
         }
+        if (active) a.cand_cnt[(size_t)q * a.n_sub + sub] = cnt;
     }
     tc_fence_before();
     __syncthreads();
@@ -329,44 +356,183 @@ __device__ void bitonic_keys_desc(unsigned long long* key, int n_pad) {
     }
 }
 
+// Per query: pool = kept list + the candidate sub-lists of this segment.  Keeps the KP largest 64-bit keys
+// (unordered) and raises tau to the KP-th score.  Selection is an MSB-first radix select over the key
+// bits below the common prefix of (min, max): 8-bit digits, warp-aggregated shared-memory histogram,
+// early exit as soon as the pivot bucket is consumed exactly.  O(n) per pass instead of a full sort.
+constexpr int TC_MAX_SUB = 320;
+
 __global__ void __launch_bounds__(256)
-tc_select_kernel(unsigned long long* __restrict__ cand_keys, unsigned* __restrict__ cand_cnt,
-                 unsigned long long* __restrict__ kept_keys, int* __restrict__ kept_cnt, int KP,
+tc_select_kernel(const unsigned long long* __restrict__ cand_keys, unsigned* __restrict__ cand_cnt, int n_sub,
+                 int cap_sub, unsigned long long* __restrict__ kept_keys, int* __restrict__ kept_cnt, int KP,
                  float* __restrict__ tau, int* __restrict__ overflow, int final_pass,
                  long long* __restrict__ rows_out) {
     extern __shared__ unsigned long long sk[];
-    const int q = blockIdx.x;
-    const unsigned raw = cand_cnt[q];
-    const int c = (int)min(raw, (unsigned)TC_CAP);
+    __shared__ int s_off[TC_MAX_SUB + 1];
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned long long s_red[16];
+    __shared__ unsigned long long s_prefix, s_minsel;
+    __shared__ int s_bits, s_krem, s_done, s_over, s_out;
+    __shared__ int s_wsum[8], s_wsum1[8], s_tail;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int kc = kept_cnt[q];
-    const int total = c + kc;
-    int n_pad = 2;
-    while (n_pad < total) n_pad <<= 1;
-    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
-        unsigned long long k = 0ull;
-        if (i < kc) k = kept_keys[(size_t)q * KP + i];
-        else if (i < total) k = cand_keys[(size_t)q * TC_CAP + (i - kc)];
-        sk[i] = k;
+
+    // sub-list sizes -> offsets (block scan over n_sub <= 320 entries, up to two per thread)
+    int c0 = 0, c1 = 0, over = 0;
+    if (tid < n_sub) {
+        const unsigned raw = cand_cnt[(size_t)q * n_sub + tid];
+        c0 = (int)min(raw, (unsigned)cap_sub);
+        over |= raw > (unsigned)cap_sub;
+    }
+    if (tid + 256 < n_sub) {
+        const unsigned raw = cand_cnt[(size_t)q * n_sub + tid + 256];
+        c1 = (int)min(raw, (unsigned)cap_sub);
+        over |= raw > (unsigned)cap_sub;
+    }
+    int x0 = c0, x1 = c1;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y0 = __shfl_up_sync(0xffffffffu, x0, o);
+        const int y1 = __shfl_up_sync(0xffffffffu, x1, o);
+        if (lane >= o) { x0 += y0; x1 += y1; }
+    }
+    if (lane == 31) { s_wsum[wid] = x0; s_wsum1[wid] = x1; }
+    if (tid == 0) { s_over = 0; s_done = 0; s_out = 0; s_minsel = ~0ull; }
+    __syncthreads();
+    int wbase0 = 0, wbase1 = 0, tot0 = 0, tot1 = 0;
+    for (int w = 0; w < 8; ++w) {
+        if (w < wid) { wbase0 += s_wsum[w]; wbase1 += s_wsum1[w]; }
+        tot0 += s_wsum[w];
+        tot1 += s_wsum1[w];
+    }
+    if (tid < n_sub) s_off[tid] = kc + wbase0 + x0 - c0;
+    if (tid + 256 < n_sub) s_off[tid + 256] = kc + tot0 + wbase1 + x1 - c1;
+    const int total_all = kc + tot0 + tot1;
+    if (tid == 0) s_off[n_sub] = total_all;
+    if (over || (tid == 0 && total_all > TC_SORT_MAX)) s_over = 1;
+    __syncthreads();
+    const int total = min(total_all, TC_SORT_MAX);
+
+    // gather into shared memory
+    for (int i = tid; i < kc; i += 256) sk[i] = kept_keys[(size_t)q * KP + i];
+    for (int r = wid; r < n_sub; r += 8) {
+        const int lo = s_off[r];
+        const int n = min(s_off[r + 1], TC_SORT_MAX) - lo;
+        const unsigned long long* src = cand_keys + ((size_t)q * n_sub + r) * cap_sub;
+        for (int i = lane; i < n; i += 32) sk[lo + i] = src[i];
     }
     __syncthreads();
-    bitonic_keys_desc(sk, n_pad);
-    const int newk = min(KP, total);
-    for (int i = threadIdx.x; i < newk; i += blockDim.x) kept_keys[(size_t)q * KP + i] = sk[i];
+
+    int newk = total;
+    unsigned long long thr_prefix = 0ull;
+    int thr_bits = 0;                      // select keys with (key >> (64-thr_bits)) >= thr_prefix; 0 = all
+    if (total > KP) {
+        // common prefix of all keys
+        unsigned long long kmin = ~0ull, kmax = 0ull;
+        for (int i = tid; i < total; i += 256) { const unsigned long long k = sk[i]; kmin = min(kmin, k); kmax = max(kmax, k); }
+        for (int o = 16; o > 0; o >>= 1) {
+            kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        }
+        if (lane == 0) { s_red[wid] = kmin; s_red[8 + wid] = kmax; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 8; ++w) { kmin = min(kmin, s_red[w]); kmax = max(kmax, s_red[8 + w]); }
+            const int common = kmin == kmax ? 56 : __clzll((long long)(kmin ^ kmax));
+            const int bits = min(common, 56);
+            s_bits = bits;
+            s_prefix = bits ? (kmax >> (64 - bits)) : 0ull;
+            s_krem = KP;
+        }
+        __syncthreads();
+        for (int pass = 0; pass < 9; ++pass) {
+            const int bits = s_bits;
+            const unsigned long long prefix = s_prefix;
+            const int dig = min(8, 64 - bits);
+            if (dig <= 0 || s_done) break;
+            s_hist[tid] = 0u;
+            __syncthreads();
+            const int shift = 64 - bits - dig;
+            for (int i0 = 0; i0 < total; i0 += 256) {
+                const int i = i0 + tid;
+                bool in = false;
+                unsigned b = 0;
+                if (i < total) {
+                    const unsigned long long k = sk[i];
+                    in = bits == 0 || (k >> (64 - bits)) == prefix;
+                    b = (unsigned)((k >> shift) & ((1u << dig) - 1u));
+                }
+                // warp-aggregated histogram update
+                const unsigned act = __ballot_sync(0xffffffffu, in);
+                if (in) {
+                    const unsigned peers = __match_any_sync(act, b);
+                    if ((int)(__ffs(peers) - 1) == lane) atomicAdd(&s_hist[b], (unsigned)__popc(peers));
+                }
+            }
+            __syncthreads();
+            if (wid == 0) {
+                // walk buckets from the top: lane l owns buckets 255-8l .. 248-8l
+                unsigned loc[8], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { loc[j] = s_hist[255 - (lane * 8 + j)]; sum += loc[j]; }
+                unsigned incl = sum;
+                for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                const unsigned excl = incl - sum;
+                const unsigned krem = (unsigned)s_krem;
+                const bool mine = excl < krem && krem <= incl;
+                if (mine) {
+                    unsigned above = excl;
+                    int j = 0;
+                    for (; j < 7; ++j) { if (above + loc[j] >= krem) break; above += loc[j]; }
+                    const int bucket = 255 - (lane * 8 + j);
+                    s_krem = (int)(krem - above);
+                    s_prefix = (prefix << dig) | (unsigned long long)bucket;
+                    s_bits = bits + dig;
+                    if (loc[j] == krem - above || bits + dig >= 64) s_done = 1;
+                }
+            }
+            __syncthreads();
+        }
+        thr_prefix = s_prefix;
+        thr_bits = s_bits;
+        newk = KP;
+    }
+    // compact the selected keys to the kept list (unordered) and find the smallest selected key
+    unsigned long long mymin = ~0ull;
+    for (int i0 = 0; i0 < total; i0 += 256) {
+        const int i = i0 + tid;
+        bool sel = false;
+        unsigned long long k = 0ull;
+        if (i < total) { k = sk[i]; sel = thr_bits == 0 || (k >> (64 - thr_bits)) >= thr_prefix; }
+        const unsigned m = __ballot_sync(0xffffffffu, sel);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_out, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (sel) {
+            const int slot = base + __popc(m & ((1u << lane) - 1u));
+            if (slot < KP) {
+                kept_keys[(size_t)q * KP + slot] = k;
+                if (final_pass) rows_out[(size_t)q * KP + slot] = (long long)rr_key_index(k);
+            }
+            mymin = min(mymin, k);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) mymin = min(mymin, __shfl_xor_sync(0xffffffffu, mymin, o));
+    if (lane == 0) atomicMin(&s_minsel, mymin);
     if (final_pass)
-        for (int i = threadIdx.x; i < KP; i += blockDim.x)
-            rows_out[(size_t)q * KP + i] = i < newk ? (long long)rr_key_index(sk[i]) : -1ll;
-    if (threadIdx.x == 0) {
+        for (int i = newk + tid; i < KP; i += 256) rows_out[(size_t)q * KP + i] = -1ll;
+    for (int r = tid; r < n_sub; r += 256) cand_cnt[(size_t)q * n_sub + r] = 0u;
+    __syncthreads();
+    if (tid == 0) {
         kept_cnt[q] = newk;
-        tau[q] = newk == KP ? rr_key_score(sk[KP - 1]) : -INFINITY;
-        cand_cnt[q] = 0u;
-        if (raw > (unsigned)TC_CAP) overflow[q] = 1;
+        tau[q] = newk == KP ? rr_key_score(s_minsel) : -INFINITY;
+        if (s_over) overflow[q] = 1;
     }
 }
 
 __global__ void __launch_bounds__(256)
 tc_finalize_kernel(const unsigned long long* __restrict__ kept_keys, const int* __restrict__ kept_cnt, int KP,
                    const float* __restrict__ exact, const int* __restrict__ overflow, const float* __restrict__ qnorm,
-                   float eps_rel, int pool, long long* __restrict__ out_idx, float* __restrict__ out_sims,
+                   const float* __restrict__ tau, float eps_rel, int pool, long long* __restrict__ out_idx, float* __restrict__ out_sims,
                    int32_t* __restrict__ out_count, int* __restrict__ n_flagged, int* __restrict__ flagged) {
     extern __shared__ unsigned long long sk[];
     const int q = blockIdx.x;
@@ -393,7 +559,7 @@ tc_finalize_kernel(const unsigned long long* __restrict__ kept_keys, const int* 
         bool ok = overflow[q] == 0;
         if (ok && kc == KP) {
             // every row outside the shortlist has bf16 score <= c, so exact score <= c + eps
-            const float c = rr_key_score(kept_keys[(size_t)q * KP + KP - 1]);
+            const float c = tau[q];                   // the KP-th best bf16 score
             const float eps = eps_rel * qnorm[q];
             const float pth = P > 0 ? rr_key_score(sk[P - 1]) : INFINITY;
             ok = pth > c + eps;
@@ -402,9 +568,11 @@ tc_finalize_kernel(const unsigned long long* __restrict__ kept_keys, const int* 
     }
 }
 
-__global__ void tc_reset_kernel(unsigned* cand_cnt, int* kept_cnt, float* tau, int* overflow, int* n_flagged, int B) {
+__global__ void tc_reset_kernel(unsigned* cand_cnt, int n_cnt, int* kept_cnt, float* tau, int* overflow,
+                                int* n_flagged, int B) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B) { cand_cnt[i] = 0u; kept_cnt[i] = 0; tau[i] = -INFINITY; overflow[i] = 0; }
+    if (i < n_cnt) cand_cnt[i] = 0u;
+    if (i < B) { kept_cnt[i] = 0; tau[i] = -INFINITY; overflow[i] = 0; }
     if (i == 0) *n_flagged = 0;
 }
 __global__ void tc_gather_queries_kernel(const float* __restrict__ q, const int* __restrict__ flagged, int D,
@@ -507,7 +675,7 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
     if (d->dim_pad > TC_MAX_KB * TC_BK)
         return rr_fail(RR_EUNSUPPORTED, "tensor path supports dim <= %d in this build", TC_MAX_KB * TC_BK);
     const int KP = shortlist_size(pool);
-    if (KP + TC_CAP > 8192) return rr_fail(RR_EUNSUPPORTED, "tensor path supports pool <= %d", (int)((8192 - TC_CAP) / 2.6));
+    if (KP > TC_SORT_MAX / 4) return rr_fail(RR_EUNSUPPORTED, "tensor path supports pool <= %d", (int)(TC_SORT_MAX / 4 / 2.6));
     if (!*state) {
         *state = new (std::nothrow) rr_tc_state();
         if (!*state) return rr_fail(RR_ENOMEM, "out of host memory");
@@ -516,8 +684,8 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
     if (!st->h_nflag) RR_CUDA(cudaMallocHost(&st->h_nflag, sizeof(int)));
     if (!st->attr_set) {
         RR_CUDA(cudaFuncSetAttribute(tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
-        RR_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
-        RR_CUDA(cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+        RR_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SORT_MAX * 8));
+        RR_CUDA(cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SORT_MAX * 8));
         st->attr_set = true;
     }
     if (st->tmap_c_base != d->d_emb_bf16) {
@@ -526,10 +694,36 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
     }
     const int n_qt = (B + TC_BM - 1) / TC_BM;
     const int B_pad = n_qt * TC_BM;
+
+    // Split the query tiles into parts so that (tiles per part) x (CTAs per tile) fills the SMs; an extra
+    // part re-reads the corpus from HBM, so it has to buy at least 5 % more SM occupancy.
+    int best_parts = 0;
+    double best_cost = 1e30;
+    for (int parts = 1; parts <= 8 && parts <= n_qt; ++parts) {
+        double cost = 0;
+        bool ok = true;
+        for (int p = 0; p < parts; ++p) {
+            const int nq = n_qt / parts + (p < n_qt % parts ? 1 : 0);
+            if (nq > sm_count) { ok = false; break; }
+            cost += 1.0 / (double)(sm_count / nq);
+        }
+        if (ok && cost < best_cost * 0.95) { best_cost = cost; best_parts = parts; }
+    }
+    if (best_parts == 0) return rr_fail(RR_EUNSUPPORTED, "batch too large for the tensor path (%d query tiles)", n_qt);
+    int reps_max = 1, reps_min = sm_count;
+    for (int p = 0; p < best_parts; ++p) {
+        const int nq = n_qt / best_parts + (p < n_qt % best_parts ? 1 : 0);
+        reps_max = std::max(reps_max, sm_count / nq);
+        reps_min = std::min(reps_min, sm_count / nq);
+    }
+    const int n_sub = 2 * reps_max;                                              // one sub-list per (CTA, column half)
+    if (n_sub > TC_MAX_SUB) return rr_fail(RR_EUNSUPPORTED, "too many SMs for the candidate sub-list table");
+    const int cap_sub = std::max(TC_BN / 2, TC_CAP_TOTAL / n_sub / 32 * 32);     // >= half of an all-pass tile
+
     RR_TRY(st->q_bf16.ensure(sizeof(__nv_bfloat16) * (size_t)B_pad * d->dim_pad));
     RR_TRY(st->qnorm.ensure(sizeof(float) * (size_t)B_pad));
-    RR_TRY(st->cand_keys.ensure(sizeof(unsigned long long) * (size_t)B * TC_CAP));
-    RR_TRY(st->cand_cnt.ensure(sizeof(unsigned) * (size_t)B));
+    RR_TRY(st->cand_keys.ensure(sizeof(unsigned long long) * (size_t)B * n_sub * cap_sub));
+    RR_TRY(st->cand_cnt.ensure(sizeof(unsigned) * (size_t)B * n_sub));
     RR_TRY(st->kept_keys.ensure(sizeof(unsigned long long) * (size_t)B * KP));
     RR_TRY(st->kept_cnt.ensure(sizeof(int) * (size_t)B));
     RR_TRY(st->tau.ensure(sizeof(float) * (size_t)B));
@@ -543,35 +737,27 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
     CUtensorMap tmap_q;
     RR_TRY(make_tmap_bf16_rows(&tmap_q, st->q_bf16.p, (uint64_t)B_pad, (uint64_t)d->dim_pad, TC_BM));
 
-    cvt_queries_kernel<<<B_pad, 128, 0, s>>>(d_q, B, d->dim, d->dim_pad, B_pad, static_cast<__nv_bfloat16*>(st->q_bf16.p),
-                                             static_cast<float*>(st->qnorm.p));
-    RR_LAUNCH_CHECK();
-    tc_reset_kernel<<<(B + 255) / 256, 256, 0, s>>>(static_cast<unsigned*>(st->cand_cnt.p), static_cast<int*>(st->kept_cnt.p),
-                                                    static_cast<float*>(st->tau.p), static_cast<int*>(st->overflow.p),
-                                                    n_flagged, B);
-    RR_LAUNCH_CHECK();
-
-    // split the query tiles into parts so that (tiles per part) x (CTAs per tile) fills the SMs
-    int best_parts = 1;
-    double best_cost = 1e30;
-    for (int parts = 1; parts <= 8 && parts <= n_qt; ++parts) {
-        double cost = 0;
-        bool ok = true;
-        for (int p = 0; p < parts; ++p) {
-            const int nq = n_qt / parts + (p < n_qt % parts ? 1 : 0);
-            if (nq > sm_count) { ok = false; break; }
-            cost += 1.0 / (double)(sm_count / nq);
-        }
-        if (ok && cost < best_cost - 1e-12) { best_cost = cost; best_parts = parts; }
+    {
+        RrProfScope prof(RR_PROF_MISC, s);
+        cvt_queries_kernel<<<B_pad, 128, 0, s>>>(d_q, B, d->dim, d->dim_pad, B_pad,
+                                                 static_cast<__nv_bfloat16*>(st->q_bf16.p), static_cast<float*>(st->qnorm.p));
+        RR_LAUNCH_CHECK();
+        const int n_cnt = B * n_sub;
+        tc_reset_kernel<<<(std::max(n_cnt, B) + 255) / 256, 256, 0, s>>>(
+            static_cast<unsigned*>(st->cand_cnt.p), n_cnt, static_cast<int*>(st->kept_cnt.p),
+            static_cast<float*>(st->tau.p), static_cast<int*>(st->overflow.p), n_flagged, B);
+        RR_LAUNCH_CHECK();
     }
-    if (best_cost > 1e29) return rr_fail(RR_EUNSUPPORTED, "batch too large for the tensor path (%d query tiles)", n_qt);
 
     const int n_dt = (int)((d->n_docs + TC_BN - 1) / TC_BN);
+    // first segment: tau = -inf, everything passes -> at most one tile per CTA and a sortable total
+    const int seg0_tiles = std::max(1, std::min(reps_min, (TC_SORT_MAX - KP) / TC_BN));
     int n_segments = 0;
     int dt_lo = 0;
-    const size_t sel_smem = 8192 * 8;
+    const size_t sel_smem = (size_t)TC_SORT_MAX * 8;
     while (dt_lo < n_dt) {
-        int dt_hi = dt_lo == 0 ? std::min(n_dt, TC_SEG0_TILES) : (int)std::min<long long>(n_dt, (long long)dt_lo * TC_GROWTH);
+        const int dt_hi = dt_lo == 0 ? std::min(n_dt, seg0_tiles)
+                                     : (int)std::min<long long>(n_dt, (long long)dt_lo * TC_GROWTH);
         int qt0 = 0;
         for (int p = 0; p < best_parts; ++p) {
             const int nq = n_qt / best_parts + (p < n_qt % best_parts ? 1 : 0);
@@ -579,6 +765,7 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
             a.n_docs = d->n_docs; a.n_kb = d->dim_pad / TC_BK; a.B = B; a.qt0 = qt0; a.n_qt = nq;
             a.reps = std::max(1, std::min(sm_count / nq, dt_hi - dt_lo));
             a.dt_lo = dt_lo; a.dt_hi = dt_hi; a.tau = static_cast<const float*>(st->tau.p);
+            a.n_sub = n_sub; a.cap_sub = cap_sub;
             a.cand_keys = static_cast<unsigned long long*>(st->cand_keys.p);
             a.cand_cnt = static_cast<unsigned*>(st->cand_cnt.p);
             {
@@ -589,13 +776,15 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
             qt0 += nq;
         }
         const int final_pass = dt_hi >= n_dt;
-        RrProfScope prof_sel(RR_PROF_TC_SELECT, s);
-        tc_select_kernel<<<B, 256, sel_smem, s>>>(static_cast<unsigned long long*>(st->cand_keys.p),
-                                                  static_cast<unsigned*>(st->cand_cnt.p),
-                                                  static_cast<unsigned long long*>(st->kept_keys.p),
-                                                  static_cast<int*>(st->kept_cnt.p), KP, static_cast<float*>(st->tau.p),
-                                                  static_cast<int*>(st->overflow.p), final_pass,
-                                                  static_cast<long long*>(st->rows.p));
+        {
+            RrProfScope prof(RR_PROF_TC_SELECT, s);
+            tc_select_kernel<<<B, 256, sel_smem, s>>>(static_cast<const unsigned long long*>(st->cand_keys.p),
+                                                      static_cast<unsigned*>(st->cand_cnt.p), n_sub, cap_sub,
+                                                      static_cast<unsigned long long*>(st->kept_keys.p),
+                                                      static_cast<int*>(st->kept_cnt.p), KP, static_cast<float*>(st->tau.p),
+                                                      static_cast<int*>(st->overflow.p), final_pass,
+                                                      static_cast<long long*>(st->rows.p));
+        }
         RR_LAUNCH_CHECK();
         dt_lo = dt_hi;
         ++n_segments;
@@ -603,13 +792,16 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
     RR_TRY(rr_launch_rescore(d->d_emb_f32, d->n_docs, d->dim, d_q, static_cast<const int64_t*>(st->rows.p), KP, B,
                              static_cast<float*>(st->exact.p), s));
     const float eps_rel = (0.0078125f + 0.000030517578125f + 1e-4f) * d->max_row_norm;
-    RrProfScope* prof_fin = new RrProfScope(RR_PROF_TC_FINALIZE, s);
-    tc_finalize_kernel<<<B, 256, sel_smem, s>>>(static_cast<const unsigned long long*>(st->kept_keys.p),
-                                                static_cast<const int*>(st->kept_cnt.p), KP,
-                                                static_cast<const float*>(st->exact.p), static_cast<const int*>(st->overflow.p),
-                                                static_cast<const float*>(st->qnorm.p), eps_rel, pool,
-                                                reinterpret_cast<long long*>(d_idx), d_sims, d_count, n_flagged, flagged);
-    delete prof_fin;
+    {
+        RrProfScope prof(RR_PROF_TC_FINALIZE, s);
+        tc_finalize_kernel<<<B, 256, sel_smem, s>>>(static_cast<const unsigned long long*>(st->kept_keys.p),
+                                                    static_cast<const int*>(st->kept_cnt.p), KP,
+                                                    static_cast<const float*>(st->exact.p),
+                                                    static_cast<const int*>(st->overflow.p),
+                                                    static_cast<const float*>(st->qnorm.p),
+                                                    static_cast<const float*>(st->tau.p), eps_rel, pool,
+                                                    reinterpret_cast<long long*>(d_idx), d_sims, d_count, n_flagged, flagged);
+    }
     RR_LAUNCH_CHECK();
     RR_CUDA(cudaMemcpyAsync(st->h_nflag, n_flagged, sizeof(int), cudaMemcpyDeviceToHost, s));
     RR_CUDA(cudaStreamSynchronize(s));

@@ -1,0 +1,295 @@
+"""Drop-in replacements for the reference's search functions (same names, argument meaning and
+error behaviour), backed by librr_b200.so.  NumPy arrays / DataFrames in and out, exactly like the
+functions they replace; the GPU index behind them is built once per artifact and cached, the way
+the reference caches its own loads (st.cache_resource / st.cache_data).
+
+    reference seam                                                   replacement here
+    ---------------------------------------------------------------  ------------------------------
+    utils.cosine_similarity_search(q, mat, top_k)      utils.py:111   cosine_similarity_search
+    cosine_search(qvec, mat, topk)              app/test.py:125      cosine_search
+    _cosine_pool(qvec, mat, pool)   app/app_product_search.py:192    _cosine_pool
+    rank_bm25.BM25Okapi(corpus).get_scores(tokens)                   BM25Okapi (also importable as the
+        (app/test.py:156,170; app/app_product_search.py:142,206)      module `rank_bm25`, see shims/)
+    bm25_scores(bm25, toks, order_idx, top_idx) app/test.py:168      bm25_scores
+    _bm25_for_candidates(blob, query, cand_skus)          :201       _bm25_for_candidates
+    run_search(query, k, rerank_k, w_*, prior_C, use_snips,
+               max_scan, min_reviews, gate_penalty)       :245       SearchEngine.run_search
+    search(args)                                app/test.py:228      SearchEngine.search
+
+There is no CPU fallback: without the CUDA library or a GPU these raise RRError.
+"""
+from __future__ import annotations
+
+import re
+import weakref
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib, engine
+from ._lib import RRError
+
+# utils.py:11-12 (query-side tokenizer; the index-side tokenizer lives in nlp/12_product_prep.py)
+TOKEN_RE = re.compile(r"[a-z0-9]+(?:'[a-z0-9]+)?")
+STOP_WORDS = {"a", "an", "the", "and", "or", "of", "for", "to", "in", "on", "with", "is", "are", "it", "this", "that"}
+
+
+def tokenize_query(query: str) -> List[str]:
+    """utils.py:57-60."""
+    return [t for t in TOKEN_RE.findall(query.lower()) if t not in STOP_WORDS]
+
+
+# --------------------------------------------------------------------------------------------
+# dense
+# --------------------------------------------------------------------------------------------
+_dense_cache: Dict[Tuple, "engine.HybridIndex"] = {}
+
+
+def _dense_index_for(mat: np.ndarray, device: str = "cuda:0") -> "engine.HybridIndex":
+    """One GPU copy per embeddings matrix (keyed on its buffer, shape and strides: the reference
+    passes the same cached `Vn` on every call)."""
+    if not isinstance(mat, np.ndarray) or mat.ndim != 2:
+        raise RRError("embeddings_matrix must be a 2-D NumPy array")
+    key = (mat.__array_interface__["data"][0], mat.shape, mat.strides, mat.dtype.str, device)
+    ix = _dense_cache.get(key)
+    if ix is None:
+        if len(_dense_cache) >= 4:
+            _dense_cache.pop(next(iter(_dense_cache))).close()
+        ix = engine.HybridIndex(np.ascontiguousarray(mat, dtype=np.float32), device=device,
+                                make_bf16=mat.shape[0] >= 65536 and mat.shape[1] <= 384)
+        _dense_cache[key] = ix
+    return ix
+
+
+def cosine_similarity_search(query_vector: np.ndarray, embeddings_matrix: np.ndarray, top_k: int
+                             ) -> Tuple[np.ndarray, np.ndarray]:
+    """utils.py:111-124: (indices int64[k], similarities float32[k]) by descending similarity, k clamped
+    to the number of rows.  Ties are ordered by ascending row (the reference leaves them unordered)."""
+    ix = _dense_index_for(embeddings_matrix)
+    k = int(min(int(top_k), ix.n_docs))
+    if k <= 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.float32)
+    idx, sims, _ = ix.dense_topk(np.asarray(query_vector, dtype=np.float32)[None, :], k, _lib.RR_DENSE_EXACT)
+    return idx[0].cpu().numpy(), sims[0].cpu().numpy()
+
+
+def cosine_search(qvec: np.ndarray, mat: np.ndarray, topk: int):
+    """app/test.py:125-132."""
+    return cosine_similarity_search(qvec, mat, topk)
+
+
+def _cosine_pool(qvec: np.ndarray, mat: np.ndarray, pool: int):
+    """app/app_product_search.py:192-195."""
+    return cosine_similarity_search(qvec, mat, pool)
+
+
+# --------------------------------------------------------------------------------------------
+# sparse
+# --------------------------------------------------------------------------------------------
+class BM25Okapi:
+    """rank_bm25.BM25Okapi drop-in: same constructor and `get_scores(tokens) -> float64[N]`.
+
+    The corpus (list of token lists, `blob["corpus"]` of product_bm25.pkl) is turned into integer
+    term ids (first-appearance order, like the library's dict), the statistics and the tile-blocked
+    postings are built by the host builder (bm25_build.cpp) and scoring runs in K1 on the GPU.
+    Scores are accumulated in fp32 (impacts are the correctly rounded fp32 of the library's float64
+    terms) and returned as float64, so they agree with the library to ~1e-7 relative; both call
+    sites cast to float32 immediately (app/test.py:170, app/app_product_search.py:206).
+    """
+
+    def __init__(self, corpus: Sequence[Sequence[str]], tokenizer: Optional[Callable] = None,
+                 k1: float = 1.5, b: float = 0.75, epsilon: float = 0.25, device: str = "cuda:0",
+                 tile_docs: int = engine.DEFAULT_TILE_DOCS):
+        if tokenizer:
+            corpus = [tokenizer(doc) for doc in corpus]
+        self.k1, self.b, self.epsilon = k1, b, epsilon
+        self.tokenizer = tokenizer
+        vocab: Dict[str, int] = {}
+        ids: List[int] = []
+        offs = [0]
+        for doc in corpus:
+            for w in doc:
+                i = vocab.get(w)
+                if i is None:
+                    i = len(vocab)
+                    vocab[w] = i
+                ids.append(i)
+            offs.append(len(ids))
+        self.corpus_size = len(offs) - 1
+        if self.corpus_size == 0:
+            raise ZeroDivisionError("division by zero")          # what rank_bm25 raises for an empty corpus
+        self.vocab = vocab
+        self._offs = np.asarray(offs, dtype=np.int64)
+        self._ids = np.asarray(ids, dtype=np.int32)
+        self.doc_len = np.diff(self._offs).tolist()
+        v = max(1, len(vocab))
+        stats = engine.BM25Stats.local(self._offs, self._ids, v).finalize(epsilon)
+        self.avgdl = stats.avgdl
+        self.average_idf = stats.average_idf
+        self.idf = {w: float(stats.idf[i]) for w, i in vocab.items()}
+        placeholder = np.zeros((self.corpus_size, 4), dtype=np.float32)
+        self._ix = engine.HybridIndex(placeholder, self._offs, self._ids, v, device=device, stats=stats, k1=k1, b=b,
+                                      tile_docs=tile_docs, make_bf16=False)
+
+    def term_ids(self, tokens: Sequence[str]) -> List[int]:
+        return [self.vocab.get(t, -1) for t in tokens]
+
+    def get_scores(self, query: Sequence[str]) -> np.ndarray:
+        ids, n = engine.HybridIndex.pack_terms([self.term_ids(list(query))])
+        out = self._ix.bm25_get_scores(ids, n)
+        return out[0].cpu().numpy().astype(np.float64)
+
+    def get_batch_scores(self, query: Sequence[str], doc_ids: Sequence[int]) -> List[float]:
+        """rank_bm25's get_batch_scores: scores of the given documents only (K1 candidate mode)."""
+        ids, n = engine.HybridIndex.pack_terms([self.term_ids(list(query))])
+        cand = np.asarray(list(doc_ids), dtype=np.int64)[None, :]
+        return self._ix.bm25_candidates(ids, n, cand)[0].cpu().numpy().astype(np.float64).tolist()
+
+
+def bm25_scores(bm25, query_tokens: List[str], order_idx: Optional[List[int]], top_idx: np.ndarray) -> np.ndarray:
+    """app/test.py:168-173: full scores cast to float32, optional permutation into meta order, gather."""
+    scores_all = np.array(bm25.get_scores(query_tokens), dtype=np.float32)
+    if order_idx is not None:
+        scores_all = scores_all[np.array(order_idx)]
+    return scores_all[top_idx]
+
+
+def _bm25_for_candidates(bm25_blob, query: str, cand_skus: List[str]) -> np.ndarray:
+    """app/app_product_search.py:201-208 (missing blob or empty token list -> zeros; SKU absent from
+    the blob -> 0.0; duplicate SKUs: the last one wins)."""
+    if not bm25_blob:
+        return np.zeros(len(cand_skus), dtype=np.float32)
+    toks = tokenize_query(query)
+    if not toks:
+        return np.zeros(len(cand_skus), dtype=np.float32)
+    bm25, skus = bm25_blob["bm25"], bm25_blob["skus"]
+    lut = bm25_blob.get("_sku_to_doc")
+    if lut is None:
+        lut = {skus[i]: i for i in range(len(skus))}
+        bm25_blob["_sku_to_doc"] = lut
+    docs = [lut.get(str(s), -1) for s in cand_skus]
+    if isinstance(bm25, BM25Okapi):
+        return np.asarray(bm25.get_batch_scores(toks, docs), dtype=np.float32)     # -1 -> 0.0 on the device
+    scores_all = np.array(bm25.get_scores(toks), dtype=np.float32)
+    return np.array([scores_all[d] if d >= 0 else 0.0 for d in docs], dtype=np.float32)
+
+
+# --------------------------------------------------------------------------------------------
+# the two search drivers
+# --------------------------------------------------------------------------------------------
+class SearchEngine:
+    """Holds what `_product_index()` + `_bm25_loader()` hold in the reference and answers queries
+    with the reference's signatures.  `encode(query) -> float32[D]` stands in for the sentence
+    transformer (`normalize_embeddings=True`), `rerank(query, texts) -> scores` for the cross-encoder
+    (None = unavailable: zeros, app/app_product_search.py:275), `gate(text, query, penalty) -> factor`
+    for the attribute gates (None = 1.0)."""
+
+    def __init__(self, meta, Vn: np.ndarray, bm25_corpus: Optional[Sequence[Sequence[str]]] = None,
+                 bm25_skus: Optional[Sequence[str]] = None, encode: Optional[Callable] = None,
+                 rerank: Optional[Callable] = None, gate: Optional[Callable] = None, device: str = "cuda:0"):
+        import pandas as pd
+        self.meta = meta.reset_index(drop=True)
+        self.encode, self.rerank, self.gate = encode, rerank, gate
+        n = len(self.meta)
+        if n != Vn.shape[0]:
+            raise SystemExit(f"[ERR] length mismatch: meta={n} vs emb_rows={Vn.shape[0]}")     # app/test.py:142
+        nrev = pd.to_numeric(self.meta.get("n_reviews", pd.Series([np.nan] * n)), errors="coerce").fillna(0).values
+        avg = pd.to_numeric(self.meta.get("avg_stars", pd.Series([np.nan] * n)), errors="coerce").values
+        self.vocab: Dict[str, int] = {}
+        offs = toks = None
+        self.bm25_active = bm25_corpus is not None
+        if bm25_corpus is not None:
+            # align BM25 documents to meta rows: by SKU (run_search, :207-208: last duplicate wins, missing -> 0)
+            sku_to_doc = {str(s): i for i, s in enumerate(bm25_skus)}
+            ids: List[int] = []
+            o = [0]
+            # term ids in first-appearance order OF THE BLOB (the library's dict order decides the idf mean)
+            for doc in bm25_corpus:
+                for w in doc:
+                    if w not in self.vocab:
+                        self.vocab[w] = len(self.vocab)
+            v = max(1, len(self.vocab))
+            flat_offs = [0]
+            flat_ids: List[int] = []
+            for doc in bm25_corpus:
+                flat_ids.extend(self.vocab[w] for w in doc)
+                flat_offs.append(len(flat_ids))
+            stats = engine.BM25Stats.local(np.asarray(flat_offs, dtype=np.int64), np.asarray(flat_ids, dtype=np.int32),
+                                           v).finalize()
+            for s in self.meta["sku"].astype(str).tolist():
+                d = sku_to_doc.get(s, -1)
+                if d >= 0:
+                    ids.extend(flat_ids[flat_offs[d]:flat_offs[d + 1]])
+                o.append(len(ids))
+            # document lengths / statistics are those of the blob; rows without a BM25 doc get no postings
+            offs, toks = np.asarray(o, dtype=np.int64), np.asarray(ids, dtype=np.int32)
+            self._stats = stats
+            self.ix = engine.HybridIndex(Vn, offs, toks, v, nrev, avg, device=device, stats=stats)
+        else:
+            self.ix = engine.HybridIndex(Vn, n_reviews=nrev, avg_stars=avg, device=device)
+
+    def _terms(self, query: str):
+        toks = tokenize_query(query)
+        ids = [self.vocab.get(t, -1) for t in toks]
+        return toks, engine.HybridIndex.pack_terms([ids])
+
+    def _search(self, query: str, fusion: "engine.Fusion", gate_penalty: float):
+        import torch
+        qvec = np.asarray(self.encode(query), dtype=np.float32)
+        toks, (tid, nt) = self._terms(query)
+        pool = fusion.pool
+        cand, dense, cnt = self.ix.dense_topk(qvec[None, :], pool)
+        if self.bm25_active and toks:
+            bm25, n, avg, grow = self.ix.candidate_tuples(tid, nt, cand)
+        else:
+            bm25, n, avg, grow = self.ix.candidate_tuples(None, None, cand)
+        P = int(cnt[0].item())
+        rows = cand[0, :P].cpu().numpy()
+        frame = self.meta.iloc[rows].reset_index(drop=True)
+        rerank = gate = None
+        if fusion.rerank_k > 0:
+            rr_k = min(fusion.rerank_k, P)
+            z = np.zeros(pool, dtype=np.float32)
+            if self.rerank is not None:
+                texts = frame["agg_text"].astype(str).str.slice(0, 2000).tolist()[:rr_k]
+                rr = np.array(self.rerank(query, texts), dtype=np.float32)
+                lo, hi = float(np.min(rr)), float(np.max(rr))
+                if np.isfinite(lo) and np.isfinite(hi) and hi - lo >= 1e-12:
+                    z[:rr_k] = ((rr - lo) / (hi - lo + 1e-12)).astype(np.float32)      # _minmax, :182-187
+            rerank = z[None, :]
+        if self.gate is not None and "agg_text" in frame:
+            g = np.ones(pool, dtype=np.float32)
+            texts = frame["agg_text"].astype(str).str.slice(0, 6000).tolist()
+            g[:P] = np.array([self.gate(t, query, gate_penalty) for t in texts], dtype=np.float32)
+            gate = g[None, :]
+        top_rows, final, pos, comp = self.ix.fuse(fusion, dense, bm25, n, avg, grow, count=cnt, rerank=rerank,
+                                                  gate=gate, want_components=True)
+        pos = pos[0].cpu().numpy()
+        pos = pos[pos >= 0]
+        comp = comp[0].cpu().numpy()
+        out = frame.iloc[pos].reset_index(drop=True).copy()
+        out["_dense"], out["_bm25"], out["_prior"] = comp[pos, 0], comp[pos, 1], comp[pos, 2]
+        out["_trust"], out["_final"] = comp[pos, 3], comp[pos, 4]
+        out["_rerank"] = rerank[0][pos] if rerank is not None else 0.0
+        out["_best"] = np.zeros(len(pos), dtype=np.float32)
+        out["_gate"] = gate[0][pos] if gate is not None else np.ones(len(pos), dtype=np.float32)
+        return out, toks
+
+    def run_search(self, query: str, k: int, rerank_k: int, w_dense: float, w_bm25: float, w_rerank: float,
+                   w_prior: float, w_best: float, prior_C: float, use_snips: bool, max_scan: int,
+                   min_reviews: int, gate_penalty: float):
+        """Signature and return shape of run_search (app/app_product_search.py:245-317):
+        (DataFrame of the top k rows in rank order, snippets dict, debug dict)."""
+        fusion = engine.Fusion(k=k, rerank_k=rerank_k, w_dense=w_dense, w_bm25=w_bm25, w_rerank=w_rerank,
+                               w_prior=w_prior, w_best=w_best, prior_C=prior_C, min_reviews=min_reviews,
+                               driver="streamlit", bm25_absent=not self.bm25_active)
+        out, toks = self._search(query, fusion, gate_penalty)
+        return out, {}, {"bm25_active": self.bm25_active, "tokens": toks, "groups": [], "pool": fusion.pool}
+
+    def search(self, args):
+        """The numeric core of search(args) (app/test.py:228-309); returns the top-k DataFrame."""
+        fusion = engine.Fusion(k=args.k, rerank_k=args.rerank_k, w_dense=args.w_dense, w_bm25=args.w_bm25,
+                               w_rerank=args.w_rerank, w_prior=args.w_prior, w_best=args.w_best,
+                               prior_C=args.prior_C, driver="cli", bm25_absent=not self.bm25_active)
+        out, _ = self._search(args.query, fusion, getattr(args, "gate_penalty", 0.5))
+        return out

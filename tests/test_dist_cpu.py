@@ -1,0 +1,89 @@
+"""Multi-rank plumbing of the row-sharded search, on CPU with gloo (world size 2): BM25 statistics
+all-reduce, tuple pack -> all-to-all -> unpack, and the property the merge relies on (the global
+top-pool by dense score is contained in the union of the per-shard top-pools)."""
+import os
+import subprocess
+import sys
+import textwrap
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent.parent
+
+WORKER = textwrap.dedent('''
+    import os, sys
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.environ["RR_REPO"])
+    import review_recommender_b200 as rr
+    from oracle.primitives import cosine_topk_canonical
+
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    N, D, V, B, pool = 3000, 32, 200, 8, 40
+    syn = rr.synth
+    row0 = N * rank // world
+    n_local = N * (rank + 1) // world - row0
+    full_offs, full_toks = syn.corpus_tokens(N, V)
+    offs, toks = syn.corpus_tokens(n_local, V, row0)
+
+    # ---- global BM25 statistics from per-shard statistics --------------------------------------
+    st = rr.engine.BM25Stats.local(offs, toks, V, token_pos0=int(full_offs[row0]))
+    rr.dist.all_reduce_stats(st)
+    st.finalize()
+    whole = rr.engine.BM25Stats.local(full_offs, full_toks, V).finalize()
+    assert np.array_equal(st.idf, whole.idf) and st.avgdl == whole.avgdl and st.n_docs == N
+
+    # ---- local top-pool tuples (NumPy stands in for the GPU kernels), exchange, merge -------------
+    emb = syn.embeddings(n_local, D, row0)
+    q = syn.queries(B, D)
+    grow = np.empty((B, pool), dtype=np.int64); dense = np.empty((B, pool), dtype=np.float32)
+    for b in range(B):
+        idx, sims = cosine_topk_canonical(q[b], emb, pool)
+        grow[b], dense[b] = idx + row0, sims
+    n = (grow % 17).astype(np.float64); avg = (grow % 5).astype(np.float64); bm25 = (grow % 3).astype(np.float32)
+    t = torch.from_numpy
+    send = rr.dist.pack_tuples(world, t(grow), t(n), t(avg), t(dense), t(bm25))
+    recv = rr.dist.exchange(send)
+    Bg = B // world
+    views, stride = rr.dist.field_views(recv, Bg, pool)
+    assert stride == Bg * pool * rr.dist.TUPLE_BYTES
+    full_emb = syn.embeddings(N, D)
+    for b in range(Bg):
+        gq = rank * Bg + b                                        # the global query this rank owns
+        rows, scores = [], []
+        for s in range(world):
+            g_, n_, a_, d_, b_ = rr.dist.unpack_shard(recv, s, Bg, pool)
+            assert np.array_equal(n_[b].numpy(), (g_[b].numpy() % 17).astype(np.float64))
+            assert np.array_equal(b_[b].numpy(), (g_[b].numpy() % 3).astype(np.float32))
+            lo, hi = N * s // world, N * (s + 1) // world
+            assert np.all((g_[b].numpy() >= lo) & (g_[b].numpy() < hi))
+            rows.append(g_[b].numpy()); scores.append(d_[b].numpy())
+        rows, scores = np.concatenate(rows), np.concatenate(scores)
+        order = np.lexsort((rows, -scores.astype(np.float64)))[:pool]
+        ref_idx, ref_sims = cosine_topk_canonical(q[gq], full_emb, pool)
+        assert np.array_equal(rows[order], ref_idx), (rank, b)
+        assert np.allclose(scores[order], ref_sims, atol=1e-6)
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+''')
+
+
+def test_two_rank_exchange_and_stats(tmp_path):
+    from __graft_entry__ import build
+    build()
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, RR_REPO=str(REPO), OMP_NUM_THREADS="1")
+    import socket
+    with socket.socket() as sock:                     # a free port, so reruns never collide
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout

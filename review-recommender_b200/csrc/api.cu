@@ -256,8 +256,9 @@ static int dense_exact_locked(rr_index* ix, const float* d_q, int32_t B, int32_t
 static int dense_topk_locked(rr_index* ix, const float* d_q, int32_t B, int32_t pool, int32_t mode,
                              int64_t* d_idx, float* d_sims, int32_t* d_count, cudaStream_t s) {
     if (mode == RR_DENSE_AUTO) {
-        const bool tc_ok = rr_tc_supported(ix->cc_major, ix->cc_minor) && ix->d.d_emb_bf16 != nullptr;
-        mode = (tc_ok && B >= 32 && ix->d.n_docs >= 65536 && pool <= 1024) ? RR_DENSE_TENSOR : RR_DENSE_EXACT;
+        const bool tc_ok = rr_tc_supported(ix->cc_major, ix->cc_minor) && ix->d.d_emb_bf16 != nullptr &&
+                           rr_tc_can_handle(ix->d.dim_pad, pool);
+        mode = (tc_ok && B >= 32 && ix->d.n_docs >= 65536) ? RR_DENSE_TENSOR : RR_DENSE_EXACT;
     }
     if (mode == RR_DENSE_TENSOR) {
         if (!ix->d.d_emb_bf16) return rr_fail(RR_EUNSUPPORTED, "tensor path needs the bf16 corpus copy (d_emb_bf16)");

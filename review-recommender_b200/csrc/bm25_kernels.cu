@@ -26,9 +26,10 @@
 
 namespace {
 
-constexpr int BM25_THREADS = 512;
-constexpr int BM25_U = 4;       // 16-byte units per thread per round
+constexpr int BM25_THREADS = 256;
+constexpr int BM25_U = 4;       // 16-byte units (2 postings each) per thread per round
 constexpr int BM25_MAXL = 64;   // query terms staged per pass over the accumulators
+constexpr int BM25_MIN_CTAS = 4;
 
 __device__ __forceinline__ uint4 ldg_stream16(const uint4* p) {
     uint4 r;
@@ -38,13 +39,10 @@ __device__ __forceinline__ uint4 ldg_stream16(const uint4* p) {
     return r;
 }
 
-struct Slot {
-    uint4 p;
-    uint32_t i0;   // posting index (relative to the tile) of p.x/p.y; p.z/p.w is i0+1
-    int seg;       // staged term this unit belongs to, -1 = none
-};
-
-__global__ void __launch_bounds__(BM25_THREADS)
+// One CTA per (doc tile, query).  Latency is hidden by residency (>= 4 CTAs of 256 threads per SM, each
+// with 4 x 16 B loads in flight per thread = 64 KB in flight per SM), not by register double-buffering:
+// the r01 profile showed the double-buffered 512-thread version at 92 registers -> 1 CTA/SM -> 31 % of HBM.
+__global__ void __launch_bounds__(BM25_THREADS, BM25_MIN_CTAS)
 bm25_tile_scores_kernel(const uint4* __restrict__ postings, const uint64_t* __restrict__ tile_base,
                         const uint32_t* __restrict__ blk_off, int V, int T, long long n_docs,
                         const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_len, int l_max,
@@ -58,13 +56,13 @@ bm25_tile_scores_kernel(const uint4* __restrict__ postings, const uint64_t* __re
     const uint32_t doc0u = (uint32_t)doc0;
     const int tile_n = (int)min((long long)T, n_docs - doc0);
 
-    for (int i = tid; i < T / 4; i += BM25_THREADS) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-
     int L = q_len[q];
     if (L > l_max) L = l_max;
     const uint4* base = postings + (tile_base[tile] >> 1);
     const uint32_t* off = blk_off + (long long)tile * (V + 1);
     constexpr int R = BM25_THREADS * BM25_U;
+
+    for (int i = tid; i < T / 4; i += BM25_THREADS) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (int l0 = 0; l0 < L; l0 += BM25_MAXL) {
         const int nl = min(BM25_MAXL, L - l0);
@@ -77,52 +75,45 @@ bm25_tile_scores_kernel(const uint4* __restrict__ postings, const uint64_t* __re
             s_hi[tid] = hi;
         }
         __syncthreads();
-        if (tid == 0) {
-            uint32_t run = 0;
-            for (int i = 0; i < nl; ++i) {
-                s_ustart[i] = run;
-                const uint32_t lo = s_lo[i], hi = s_hi[i];
-                run += hi > lo ? ((hi + 1) >> 1) - (lo >> 1) : 0u;
+        if (tid < 32) {
+            // exclusive scan of the per-term unit counts (nl <= 64: two per lane)
+            const int i0 = tid, i1 = tid + 32;
+            uint32_t u0 = 0, u1 = 0;
+            if (i0 < nl) { const uint32_t lo = s_lo[i0], hi = s_hi[i0]; u0 = hi > lo ? ((hi + 1) >> 1) - (lo >> 1) : 0u; }
+            if (i1 < nl) { const uint32_t lo = s_lo[i1], hi = s_hi[i1]; u1 = hi > lo ? ((hi + 1) >> 1) - (lo >> 1) : 0u; }
+            uint32_t x0 = u0, x1 = u1;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o);
+                if (tid >= o) { x0 += y0; x1 += y1; }
             }
-            s_ustart[nl] = run;
+            const uint32_t tot0 = __shfl_sync(0xffffffffu, x0, 31);
+            if (i0 < nl) s_ustart[i0] = x0 - u0;
+            if (i1 < nl) s_ustart[i1] = tot0 + x1 - u1;
+            if (tid == 31) s_ustart[nl] = tot0 + x1;      // lane 31's inclusive sums are the totals
         }
         __syncthreads();
         const uint32_t total = s_ustart[nl];
         if (total == 0) continue;
         const int n_rounds = (int)((total + R - 1) / R);
 
-        Slot cur[BM25_U], nxt[BM25_U];
         int load_cursor = 0;     // per-thread, monotone
         int phase_first = 0;     // block-uniform, monotone
         int prev_seg = -1;       // block-uniform: last term accumulated
 
-        // prologue: round 0
-#pragma unroll
-        for (int u = 0; u < BM25_U; ++u) {
-            const uint32_t v = (uint32_t)(u * BM25_THREADS + tid);
-            cur[u].seg = -1;
-            if (v < total) {
-                while (v >= s_ustart[load_cursor + 1]) ++load_cursor;
-                const uint32_t unit = (s_lo[load_cursor] >> 1) + (v - s_ustart[load_cursor]);
-                cur[u].p = ldg_stream16(base + unit);
-                cur[u].i0 = unit * 2u;
-                cur[u].seg = load_cursor;
-            }
-        }
         for (int r = 0; r < n_rounds; ++r) {
-            // issue the next round's loads before touching shared memory
-            if (r + 1 < n_rounds) {
+            uint4 p[BM25_U];
+            uint32_t unit_of[BM25_U];
+            int seg[BM25_U];
 #pragma unroll
-                for (int u = 0; u < BM25_U; ++u) {
-                    const uint32_t v = (uint32_t)((r + 1) * R + u * BM25_THREADS + tid);
-                    nxt[u].seg = -1;
-                    if (v < total) {
-                        while (v >= s_ustart[load_cursor + 1]) ++load_cursor;
-                        const uint32_t unit = (s_lo[load_cursor] >> 1) + (v - s_ustart[load_cursor]);
-                        nxt[u].p = ldg_stream16(base + unit);
-                        nxt[u].i0 = unit * 2u;
-                        nxt[u].seg = load_cursor;
-                    }
+            for (int u = 0; u < BM25_U; ++u) {
+                const uint32_t v = (uint32_t)(r * R + u * BM25_THREADS + tid);
+                seg[u] = -1;
+                if (v < total) {
+                    while (v >= s_ustart[load_cursor + 1]) ++load_cursor;
+                    const uint32_t unit = (s_lo[load_cursor] >> 1) + (v - s_ustart[load_cursor]);
+                    p[u] = ldg_stream16(base + unit);
+                    unit_of[u] = unit;
+                    seg[u] = load_cursor;
                 }
             }
             // terms covered by this round (block-uniform)
@@ -140,21 +131,19 @@ bm25_tile_scores_kernel(const uint4* __restrict__ postings, const uint64_t* __re
                 const uint32_t lo = s_lo[s], hi = s_hi[s];
 #pragma unroll
                 for (int u = 0; u < BM25_U; ++u) {
-                    if (cur[u].seg == s) {
-                        const uint32_t i0 = cur[u].i0;
+                    if (seg[u] == s) {
+                        const uint32_t i0 = unit_of[u] * 2u;
                         if (i0 >= lo && i0 < hi) {
-                            const uint32_t d = cur[u].p.x - doc0u;
-                            acc[d] = __fadd_rn(acc[d], __uint_as_float(cur[u].p.y));
+                            const uint32_t d = p[u].x - doc0u;
+                            acc[d] = __fadd_rn(acc[d], __uint_as_float(p[u].y));
                         }
                         if (i0 + 1u >= lo && i0 + 1u < hi) {
-                            const uint32_t d = cur[u].p.z - doc0u;
-                            acc[d] = __fadd_rn(acc[d], __uint_as_float(cur[u].p.w));
+                            const uint32_t d = p[u].z - doc0u;
+                            acc[d] = __fadd_rn(acc[d], __uint_as_float(p[u].w));
                         }
                     }
                 }
             }
-#pragma unroll
-            for (int u = 0; u < BM25_U; ++u) cur[u] = nxt[u];
         }
     }
     __syncthreads();
@@ -214,9 +203,11 @@ int rr_launch_bm25_tile_scores(const uint64_t* d_postings, const uint64_t* d_til
     if (B <= 0 || n_tiles <= 0) return RR_OK;
     const size_t smem = (size_t)T * sizeof(float);
     static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (configured == 0 || smem > configured) {
         RR_CUDA(cudaFuncSetAttribute(bm25_tile_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        // without this the driver sizes the shared-memory carveout for ONE resident CTA (ncu r01: occupancy limit 1)
+        RR_CUDA(cudaFuncSetAttribute(bm25_tile_scores_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured = smem > 0 ? smem : 1;
     }
     for (int b0 = 0; b0 < B; b0 += 65535) {
         const int nb = min(65535, B - b0);

@@ -144,6 +144,16 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
 }
+// predicated 8-byte global store (no branch): used by the epilogue's candidate appends
+__device__ __forceinline__ void st_pred_v2(unsigned long long* p, uint32_t lo, uint32_t hi, bool pred) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.u32 p, %3, 0;\n\t"
+        "@p st.global.v2.u32 [%0], {%1, %2};\n\t"
+        "}" ::"l"(p), "r"(lo), "r"(hi), "r"((uint32_t)pred)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
@@ -284,6 +294,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const uint32_t aphase = (uint32_t)((t >> 1) & 1);
             const int dt = a.dt_lo + j0 + t * a.reps;
             const long long doc_base = (long long)dt * TC_BN;
+            const uint32_t doc_base_u = (uint32_t)doc_base;
             const int n_valid = (int)min((long long)TC_BN, a.n_docs - doc_base);   // rows past the corpus end are zero-filled
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
@@ -313,12 +324,12 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             if (m8[g] >= tau) {
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
-                                    const float s = __uint_as_float(v[h][8 * g + e]);
+                                    // branch-free: predicated 8-byte store of (score bits, doc), counter += pass
+                                    const uint32_t sb = v[h][8 * g + e];
                                     const int col = c0 + 8 * g + e;
-                                    if (s >= tau && col < n_valid) {
-                                        if (cnt < cap) my_keys[cnt] = rr_make_key(s, (uint32_t)(doc_base + col));
-                                        ++cnt;
-                                    }
+                                    const bool pass = __uint_as_float(sb) >= tau && col < n_valid;
+                                    st_pred_v2(my_keys + cnt, sb, doc_base_u + (uint32_t)col, pass && cnt < cap);
+                                    cnt += pass ? 1u : 0u;
                                 }
                             }
                         }
@@ -418,7 +429,11 @@ tc_select_kernel(const unsigned long long* __restrict__ cand_keys, unsigned* __r
         const int lo = s_off[r];
         const int n = min(s_off[r + 1], TC_SORT_MAX) - lo;
         const unsigned long long* src = cand_keys + ((size_t)q * n_sub + r) * cap_sub;
-        for (int i = lane; i < n; i += 32) sk[lo + i] = src[i];
+        for (int i = lane; i < n; i += 32) {
+            const unsigned long long raw = src[i];               // {score bits, doc} as written by the epilogue
+            unsigned long long k = rr_make_key(__uint_as_float((uint32_t)raw), (uint32_t)(raw >> 32));
+            sk[lo + i] = k ? k : 1ull;
+        }
     }
     __syncthreads();
 
@@ -669,6 +684,10 @@ static int shortlist_size(int pool) {
     return std::max(kp, 64);
 }
 
+bool rr_tc_can_handle(int dim_pad, int pool) {
+    return dim_pad > 0 && dim_pad <= TC_MAX_KB * TC_BK && shortlist_size(pool) <= TC_SORT_MAX / 4;
+}
+
 int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, const float* d_q, int32_t B,
                      int32_t pool, int64_t* d_idx, float* d_sims, int32_t* d_count, rr_dense_stats* stats,
                      rr_exact_fn exact_fn, void* exact_ctx, cudaStream_t s) {
@@ -686,6 +705,8 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
         RR_CUDA(cudaFuncSetAttribute(tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
         RR_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SORT_MAX * 8));
         RR_CUDA(cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SORT_MAX * 8));
+        RR_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        RR_CUDA(cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         st->attr_set = true;
     }
     if (st->tmap_c_base != d->d_emb_bf16) {

@@ -12,6 +12,8 @@ typedef int (*rr_exact_fn)(void* ctx, const float* d_q, int32_t B, int32_t pool,
                            int32_t* d_count, cudaStream_t stream);
 
 bool rr_tc_supported(int cc_major, int cc_minor);
+// true if this build's tensor path can serve (dim_pad, pool); AUTO mode falls back to the exact path otherwise
+bool rr_tc_can_handle(int dim_pad, int pool);
 int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, const float* d_q, int32_t B,
                      int32_t pool, int64_t* d_idx, float* d_sims, int32_t* d_count, rr_dense_stats* stats,
                      rr_exact_fn exact, void* exact_ctx, cudaStream_t stream);

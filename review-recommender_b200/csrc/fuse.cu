@@ -372,6 +372,7 @@ int rr_launch_fuse(const rr_fusion_params* p, int B, int n_in, int n_shards, int
     // ~21 KB of static shared memory on top: opt in whenever the sum may pass the 48 KB default
     if (smem > 24 * 1024)
         RR_CUDA(cudaFuncSetAttribute(fuse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RR_CUDA(cudaFuncSetAttribute(fuse_topk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     {
         RrProfScope prof(RR_PROF_FUSE, stream);
         fuse_topk_kernel<<<B, FUSE_THREADS, smem, stream>>>(a, n_pad_in, n_pad_pool);

@@ -24,7 +24,7 @@ from . import _lib
 from ._lib import FusionParams, IndexDesc, RRError, check
 
 K1_DEFAULT, B_DEFAULT, EPSILON_DEFAULT = 1.5, 0.75, 0.25      # rank_bm25.BM25Okapi defaults
-DEFAULT_TILE_DOCS = 16384
+DEFAULT_TILE_DOCS = int(__import__("os").environ.get("RR_TILE_DOCS", "16384"))
 INT64_MAX = np.iinfo(np.int64).max
 
 

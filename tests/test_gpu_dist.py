@@ -1,0 +1,79 @@
+"""Row-sharded search on >= 2 GPUs (NCCL): results must equal the single-GPU search bit for bit
+(same global rows, same fused scores).  Skipped on a single-GPU box."""
+import os
+import subprocess
+import sys
+import textwrap
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+REPO = Path(__file__).resolve().parent.parent
+
+WORKER = textwrap.dedent('''
+    import os, sys
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.environ["RR_REPO"])
+    import review_recommender_b200 as rr
+
+    local = int(os.environ["LOCAL_RANK"])
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    N, D, V, B, L, K = 200_000, 384, 5000, 256, 4, 100
+    syn = rr.synth
+    full = syn.make_corpus(N, D, V)
+    q = syn.queries(B, D)
+    qt = syn.query_terms(B, L, full.doc_offsets, full.token_ids, V).astype(np.int32)
+    nt = np.full(B, L, dtype=np.int32)
+    fusion = rr.engine.Fusion(k=K, rerank_k=0, w_rerank=0.0, w_best=0.0)
+
+    row0 = N * rank // world
+    row1 = N * (rank + 1) // world
+    offs = full.doc_offsets[row0:row1 + 1] - full.doc_offsets[row0]
+    toks = full.token_ids[full.doc_offsets[row0]:full.doc_offsets[row1]]
+    st = rr.engine.BM25Stats.local(offs, toks, V, token_pos0=int(full.doc_offsets[row0]))
+    rr.dist.all_reduce_stats(st, device=dev)
+    st.finalize()
+    ix = rr.engine.HybridIndex(full.emb[row0:row1], offs, toks, V, full.n_reviews[row0:row1], full.avg_stars[row0:row1],
+                               device=dev, row_offset=row0, stats=st)
+    searcher = rr.dist.ShardedSearcher(ix)
+    for mode in (rr._lib.RR_DENSE_EXACT, rr._lib.RR_DENSE_TENSOR):
+        rows, final = searcher.search(torch.from_numpy(q).to(dev), torch.from_numpy(qt).to(dev),
+                                      torch.from_numpy(nt).to(dev), fusion, mode=mode)
+        if rank == 0:
+            whole = rr.engine.HybridIndex(full.emb, full.doc_offsets, full.token_ids, V, full.n_reviews, full.avg_stars,
+                                          device=dev)
+            r1, f1 = whole.hybrid_search(q, qt, nt, fusion, mode=rr._lib.RR_DENSE_EXACT)
+            assert torch.equal(rows, r1), (mode, int((rows != r1).sum()))
+            assert torch.equal(final, f1), mode
+            whole.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+''')
+
+
+def test_sharded_equals_single_gpu(tmp_path):
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 4 else 4
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    import socket
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    env = dict(os.environ, RR_REPO=str(REPO))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-4000:]
+    for k in range(world):
+        assert f"rank {k} ok" in r.stdout

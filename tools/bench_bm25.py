@@ -1,0 +1,82 @@
+#!/usr/bin/env python3
+"""K1 sweep at BASELINE.json configs[3]: BM25-only, 20M docs, 200k Zipf vocabulary, 16-term queries,
+get_scores mode (every doc scored), B in {1, 64, 256}.  Reports achieved HBM GB/s against the
+algorithmic bytes of SURVEY.md section 8d:  8 B per posting of the query's terms + 4 B per doc per query.
+
+    python tools/bench_bm25.py [--docs 20000000] [--vocab 200000] [--terms 16] [--tile-docs 16384]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--docs", type=int, default=20_000_000)
+    ap.add_argument("--vocab", type=int, default=200_000)
+    ap.add_argument("--terms", type=int, default=16)
+    ap.add_argument("--tile-docs", type=int, default=16384)
+    ap.add_argument("--batches", default="1,64,256")
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+
+    import torch
+    import review_recommender_b200 as rr
+    import bench as B
+    dev = torch.device("cuda:0")
+    cfg = dict(docs=args.docs, dim=8, vocab=args.vocab, terms=args.terms)
+    t0 = time.perf_counter()
+    emb, offs, toks, nrev, avg = B.device_shard(cfg, 0, args.docs, dev)
+    t1 = time.perf_counter()
+    stats = rr.engine.BM25Stats.local(offs, toks, args.vocab).finalize()
+    ix = rr.engine.HybridIndex(emb, offs, toks, args.vocab, device=dev, stats=stats, tile_docs=args.tile_docs,
+                               make_bf16=False)
+    t2 = time.perf_counter()
+    peaks = B.load_peaks()
+    bmax = max(int(b) for b in args.batches.split(","))
+    qt = rr.synth.query_terms(bmax, args.terms, offs, toks, args.vocab).astype(np.int32)
+    out = {"docs": args.docs, "vocab": args.vocab, "terms": args.terms, "tile_docs": args.tile_docs,
+           "gen_s": t1 - t0, "build_s": t2 - t1, "nnz": int(ix.post.numel()), "sweep": []}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for b in [int(x) for x in args.batches.split(",")]:
+        ids = torch.from_numpy(qt[:b]).to(dev)
+        nts = torch.full((b,), args.terms, dtype=torch.int32, device=dev)
+        ld = (args.docs + 3) // 4 * 4
+        buf = torch.empty((b, ld), dtype=torch.float32, device=dev)
+        lib = rr._lib.load()
+        import ctypes as C
+
+        def run():
+            rr._lib.check(lib.rr_bm25_get_scores(ix._h, C.c_void_p(ids.data_ptr()), C.c_void_p(nts.data_ptr()), b,
+                                                 args.terms, C.c_void_p(buf.data_ptr()), ld,
+                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.reps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.reps
+        postings = int(stats.df[qt[:b]].sum())
+        nbytes = 8 * postings + 4 * args.docs * b
+        out["sweep"].append({"B": b, "ms": ms, "postings_per_query": postings / b, "algorithmic_bytes": nbytes,
+                             "achieved_gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peaks["hbm_gbs"],
+                             "queries_per_s": b / ms * 1e3})
+        del buf
+    out["hbm_peak_gbs"] = peaks["hbm_gbs"]
+    out["peak_source"] = peaks["source"]
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -75,6 +75,10 @@ int32_t         rr_postings_n_tiles(const rr_postings*);
 const uint64_t* rr_postings_data(const rr_postings*);       /* host, nnz x {u32 doc, f32 impact} */
 const uint64_t* rr_postings_tile_base(const rr_postings*);  /* host, n_tiles+1 */
 const uint32_t* rr_postings_blk_off(const rr_postings*);    /* host, n_tiles*(vocab_size+1) */
+/* Forward (doc-major) copy of the same impacts for candidate-mode scoring: doc d's entries
+ * {u32 term, f32 impact}, term-ascending, are fwd_data[fwd_off[d] .. fwd_off[d+1]). */
+const uint64_t* rr_postings_fwd_off(const rr_postings*);    /* host, n_docs+1 */
+const uint64_t* rr_postings_fwd_data(const rr_postings*);   /* host, fwd_off[n_docs] entries */
 void            rr_postings_free(rr_postings*);
 
 /* ------------------------------------------------------------------------------------------
@@ -94,6 +98,8 @@ typedef struct rr_index_desc {
     const uint64_t* d_postings;  /* as rr_postings_data */
     const uint64_t* d_tile_base;
     const uint32_t* d_blk_off;
+    const uint64_t* d_fwd_off;   /* [n_docs+1] forward index (optional: NULL = candidate mode searches the postings) */
+    const uint64_t* d_fwd_data;  /* {u32 term, f32 impact} per (doc, term), term-ascending inside a doc */
     const double*   d_n_reviews; /* [n_docs] n_reviews with NaN already mapped to 0 (:264), or NULL */
     const double*   d_avg_stars; /* [n_docs] avg_stars, NaN allowed (:265), or NULL */
 } rr_index_desc;

@@ -27,6 +27,7 @@ class IndexDesc(C.Structure):
         ("d_emb_f32", C.c_void_p), ("d_emb_bf16", C.c_void_p), ("max_row_norm", C.c_float),
         ("vocab_size", C.c_int32), ("tile_docs", C.c_int32), ("n_tiles", C.c_int32),
         ("d_postings", C.c_void_p), ("d_tile_base", C.c_void_p), ("d_blk_off", C.c_void_p),
+        ("d_fwd_off", C.c_void_p), ("d_fwd_data", C.c_void_p),
         ("d_n_reviews", C.c_void_p), ("d_avg_stars", C.c_void_p),
     ]
 
@@ -59,6 +60,8 @@ SIGNATURES = {
     "rr_postings_data": (_P, [_P]),
     "rr_postings_tile_base": (_P, [_P]),
     "rr_postings_blk_off": (_P, [_P]),
+    "rr_postings_fwd_off": (_P, [_P]),
+    "rr_postings_fwd_data": (_P, [_P]),
     "rr_postings_free": (None, [_P]),
     "rr_index_create": (C.c_int, [C.POINTER(_P), C.POINTER(IndexDesc), C.c_int]),
     "rr_index_destroy": (None, [_P]),

@@ -205,7 +205,7 @@ static int candidates_locked(rr_index* ix, const int32_t* d_term_ids, const int3
                              double* d_avg, int64_t* d_grow, cudaStream_t s) {
     const bool have = ix->d.vocab_size > 0 && l_max > 0 && d_term_ids && d_n_terms;
     return rr_launch_bm25_candidates(ix->d.d_postings, ix->d.d_tile_base, ix->d.d_blk_off,
-                                     have ? ix->d.vocab_size : 0, std::max(ix->d.tile_docs, 1), ix->d.n_docs,
+                                     ix->d.d_fwd_off, ix->d.d_fwd_data, have ? ix->d.vocab_size : 0, std::max(ix->d.tile_docs, 1), ix->d.n_docs,
                                      have ? d_term_ids : nullptr, d_n_terms, B, l_max, d_cand, pool, ix->d.d_n_reviews,
                                      ix->d.d_avg_stars, ix->d.row_offset, d_bm25, d_n, d_avg, d_grow, s);
 }

@@ -23,6 +23,8 @@ struct rr_postings {
     std::vector<uint64_t> data;
     std::vector<uint64_t> tile_base;
     std::vector<uint32_t> blk_off;
+    std::vector<uint64_t> fwd_off;
+    std::vector<uint64_t> fwd_data;
 };
 
 namespace {
@@ -151,8 +153,9 @@ extern "C" int rr_bm25_build_postings(const int64_t* h_doc_offsets, const int32_
         const int64_t base = h_doc_offsets[0];
         const int nt = pick_threads(n_threads, n_tiles);
 
-        // pass 1: postings per (tile, term), then per-tile exclusive scan
+        // pass 1: postings per (tile, term), then per-tile exclusive scan; unique terms per doc for the forward index
         std::vector<uint64_t> tile_nnz((size_t)n_tiles, 0);
+        p->fwd_off.assign((size_t)n_docs + 1, 0ull);
         parallel_for(nt, n_tiles, [&](int, int64_t lo, int64_t hi) {
             std::vector<int32_t> scratch;
             std::vector<std::pair<int32_t, int32_t>> tf;
@@ -163,6 +166,7 @@ extern "C" int rr_bm25_build_postings(const int64_t* h_doc_offsets, const int32_
                     doc_term_freqs(h_token_ids + (h_doc_offsets[doc] - base),
                                    h_doc_offsets[doc + 1] - h_doc_offsets[doc], vocab_size, scratch, tf);
                     for (auto& e : tf) cnt[e.first] += 1;
+                    p->fwd_off[doc + 1] = tf.size();
                 }
                 uint64_t run = 0;
                 for (int64_t w = 0; w < vocab_size; ++w) {
@@ -183,6 +187,8 @@ extern "C" int rr_bm25_build_postings(const int64_t* h_doc_offsets, const int32_
         p->tile_base[n_tiles] = total;
         p->nnz = (int64_t)total;
         p->data.assign((size_t)total, pack_posting(0xFFFFFFFFu, 0.0f));
+        for (int64_t doc = 0; doc < n_docs; ++doc) p->fwd_off[doc + 1] += p->fwd_off[doc];
+        p->fwd_data.assign((size_t)p->fwd_off[n_docs], 0ull);
 
         // pass 2: scatter, docs ascending inside every (tile, term) segment
         parallel_for(nt, n_tiles, [&](int, int64_t lo, int64_t hi) {
@@ -204,6 +210,7 @@ extern "C" int rr_bm25_build_postings(const int64_t* h_doc_offsets, const int32_
                         const double idf = h_idf[e.first];
                         const double v = idf * (f * (k1 + 1.0) / (f + norm));
                         dst[cursor[e.first]++] = pack_posting((uint32_t)doc, (float)v);
+                        p->fwd_data[p->fwd_off[doc] + (size_t)(&e - tf.data())] = pack_posting((uint32_t)e.first, (float)v);
                     }
                 }
             }
@@ -221,4 +228,6 @@ extern "C" int32_t rr_postings_n_tiles(const rr_postings* p) { return p ? p->n_t
 extern "C" const uint64_t* rr_postings_data(const rr_postings* p) { return p ? p->data.data() : nullptr; }
 extern "C" const uint64_t* rr_postings_tile_base(const rr_postings* p) { return p ? p->tile_base.data() : nullptr; }
 extern "C" const uint32_t* rr_postings_blk_off(const rr_postings* p) { return p ? p->blk_off.data() : nullptr; }
+extern "C" const uint64_t* rr_postings_fwd_off(const rr_postings* p) { return p ? p->fwd_off.data() : nullptr; }
+extern "C" const uint64_t* rr_postings_fwd_data(const rr_postings* p) { return p ? p->fwd_data.data() : nullptr; }
 extern "C" void rr_postings_free(rr_postings* p) { delete p; }

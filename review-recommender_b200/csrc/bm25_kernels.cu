@@ -155,7 +155,8 @@ bm25_tile_scores_kernel(const uint4* __restrict__ postings, const uint64_t* __re
 
 __global__ void __launch_bounds__(256)
 bm25_candidates_kernel(const uint2* __restrict__ postings, const uint64_t* __restrict__ tile_base,
-                       const uint32_t* __restrict__ blk_off, int V, int T, long long n_docs,
+                       const uint32_t* __restrict__ blk_off, const unsigned long long* __restrict__ fwd_off,
+                       const uint2* __restrict__ fwd_data, int V, int T, long long n_docs,
                        const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_len, int l_max,
                        const long long* __restrict__ cand, int pool, int B,
                        const double* __restrict__ n_reviews, const double* __restrict__ avg_stars, long long row_offset,
@@ -167,7 +168,27 @@ bm25_candidates_kernel(const uint2* __restrict__ postings, const uint64_t* __res
     const long long doc = cand[gid];
     const bool valid = doc >= 0 && doc < n_docs;
     float sum = 0.f;
-    if (valid && V > 0 && q_terms != nullptr) {
+    if (valid && V > 0 && q_terms != nullptr && fwd_off != nullptr) {
+        // forward index: the doc's own {term, impact} list (term-ascending, ~35 entries, contiguous)
+        const unsigned long long f0 = fwd_off[doc], f1 = fwd_off[doc + 1];
+        const uint2* list = fwd_data + f0;
+        const int n = (int)(f1 - f0);
+        int L = q_len[q];
+        if (L > l_max) L = l_max;
+        for (int l = 0; l < L; ++l) {
+            const int t = q_terms[(long long)q * l_max + l];
+            if (t < 0 || t >= V) continue;
+            int lo = 0, hi = n;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(&list[mid].x) < (uint32_t)t) lo = mid + 1; else hi = mid;
+            }
+            if (lo < n) {
+                const uint2 e = __ldg(&list[lo]);
+                if (e.x == (uint32_t)t) sum = __fadd_rn(sum, __uint_as_float(e.y));
+            }
+        }
+    } else if (valid && V > 0 && q_terms != nullptr) {
         const int tile = (int)(doc / T);
         const uint2* base = postings + tile_base[tile];
         const uint32_t* off = blk_off + (long long)tile * (V + 1);
@@ -222,7 +243,7 @@ int rr_launch_bm25_tile_scores(const uint64_t* d_postings, const uint64_t* d_til
 }
 
 int rr_launch_bm25_candidates(const uint64_t* d_postings, const uint64_t* d_tile_base, const uint32_t* d_blk_off,
-                              int V, int T, int64_t n_docs, const int32_t* d_terms, const int32_t* d_nterms,
+                              const uint64_t* d_fwd_off, const uint64_t* d_fwd_data, int V, int T, int64_t n_docs, const int32_t* d_terms, const int32_t* d_nterms,
                               int B, int l_max, const int64_t* d_cand, int pool, const double* d_nrev,
                               const double* d_avg, int64_t row_offset, float* d_bm25, double* d_n_out,
                               double* d_avg_out, int64_t* d_grow_out, cudaStream_t stream) {
@@ -232,7 +253,9 @@ int rr_launch_bm25_candidates(const uint64_t* d_postings, const uint64_t* d_tile
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
     RrProfScope prof(RR_PROF_BM25_CAND, stream);
     bm25_candidates_kernel<<<blocks, threads, 0, stream>>>(
-        reinterpret_cast<const uint2*>(d_postings), d_tile_base, d_blk_off, V, T, (long long)n_docs, d_terms, d_nterms,
+        reinterpret_cast<const uint2*>(d_postings), d_tile_base, d_blk_off,
+        reinterpret_cast<const unsigned long long*>(d_fwd_off), reinterpret_cast<const uint2*>(d_fwd_data), V, T,
+        (long long)n_docs, d_terms, d_nterms,
         l_max, reinterpret_cast<const long long*>(d_cand), pool, B, d_nrev, d_avg, (long long)row_offset, d_bm25,
         d_n_out, d_avg_out, reinterpret_cast<long long*>(d_grow_out));
     RR_LAUNCH_CHECK();

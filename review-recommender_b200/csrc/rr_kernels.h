@@ -12,7 +12,7 @@ int rr_launch_bm25_tile_scores(const uint64_t* d_postings, const uint64_t* d_til
                                const int32_t* d_nterms, int B, int l_max, float* d_out, int64_t ld_out,
                                cudaStream_t stream);
 int rr_launch_bm25_candidates(const uint64_t* d_postings, const uint64_t* d_tile_base, const uint32_t* d_blk_off,
-                              int V, int T, int64_t n_docs, const int32_t* d_terms, const int32_t* d_nterms,
+                              const uint64_t* d_fwd_off, const uint64_t* d_fwd_data, int V, int T, int64_t n_docs, const int32_t* d_terms, const int32_t* d_nterms,
                               int B, int l_max, const int64_t* d_cand, int pool, const double* d_nrev,
                               const double* d_avg, int64_t row_offset, float* d_bm25, double* d_n_out,
                               double* d_avg_out, int64_t* d_grow_out, cudaStream_t stream);

@@ -94,6 +94,8 @@ class HostPostings:
     n_tiles: int
     tile_docs: int
     vocab_size: int
+    fwd_off: Optional[np.ndarray] = None    # uint64[N+1]
+    fwd_data: Optional[np.ndarray] = None   # uint64[fwd_off[N]]  {u32 term, f32 impact}
 
 
 def build_postings(doc_offsets: np.ndarray, token_ids: np.ndarray, stats: BM25Stats,
@@ -120,9 +122,11 @@ def build_postings(doc_offsets: np.ndarray, token_ids: np.ndarray, stats: BM25St
         data = view(lib.rr_postings_data(h), nnz, np.uint64)
         tile_base = view(lib.rr_postings_tile_base(h), n_tiles + 1, np.uint64)
         blk_off = view(lib.rr_postings_blk_off(h), n_tiles * (stats.vocab_size + 1), np.uint32)
+        fwd_off = view(lib.rr_postings_fwd_off(h), n + 1, np.uint64)
+        fwd_data = view(lib.rr_postings_fwd_data(h), int(fwd_off[-1]) if n > 0 else 0, np.uint64)
     finally:
         lib.rr_postings_free(h)
-    return HostPostings(data, tile_base, blk_off, n_tiles, tile_docs, stats.vocab_size)
+    return HostPostings(data, tile_base, blk_off, n_tiles, tile_docs, stats.vocab_size, fwd_off, fwd_data)
 
 
 # --------------------------------------------------------------------------------------------
@@ -169,7 +173,7 @@ class HybridIndex:
                  vocab_size: int = 0, n_reviews=None, avg_stars=None, device: str | torch.device = "cuda:0",
                  row_offset: int = 0, stats: Optional[BM25Stats] = None, k1: float = K1_DEFAULT,
                  b: float = B_DEFAULT, epsilon: float = EPSILON_DEFAULT, tile_docs: int = DEFAULT_TILE_DOCS,
-                 make_bf16: bool = True, postings: Optional[HostPostings] = None):
+                 make_bf16: bool = True, postings: Optional[HostPostings] = None, forward_index: bool = True):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RRError("HybridIndex needs a CUDA device (no CPU fallback)")
@@ -194,7 +198,7 @@ class HybridIndex:
         self.vocab_size = 0
         self.stats = stats
         self.k1, self.b = k1, b
-        self.post = self.tile_base = self.blk_off = None
+        self.post = self.tile_base = self.blk_off = self.fwd_off = self.fwd_data = None
         self.tile_docs, self.n_tiles = 0, 0
         if postings is None and doc_offsets is not None and vocab_size > 0:
             if stats is None:
@@ -209,6 +213,10 @@ class HybridIndex:
             self.blk_off = torch.from_numpy(postings.blk_off.view(np.int32)).to(self.device)
             if self.post.numel() == 0:
                 self.post = torch.zeros(2, dtype=torch.int64, device=self.device)
+            if forward_index and postings.fwd_off is not None:
+                self.fwd_off = torch.from_numpy(postings.fwd_off.view(np.int64)).to(self.device)
+                fd = postings.fwd_data if postings.fwd_data.size else np.zeros(1, dtype=np.uint64)
+                self.fwd_data = torch.from_numpy(fd.view(np.int64)).to(self.device)
 
         def meta(x, nan_to_zero):
             if x is None:
@@ -226,6 +234,8 @@ class HybridIndex:
                          self.post.data_ptr() if self.post is not None else None,
                          self.tile_base.data_ptr() if self.tile_base is not None else None,
                          self.blk_off.data_ptr() if self.blk_off is not None else None,
+                         self.fwd_off.data_ptr() if self.fwd_off is not None else None,
+                         self.fwd_data.data_ptr() if self.fwd_data is not None else None,
                          self.n_reviews.data_ptr() if self.n_reviews is not None else None,
                          self.avg_stars.data_ptr() if self.avg_stars is not None else None)
         h = C.c_void_p(0)

@@ -15,12 +15,13 @@ def _rr():
     return rr
 
 
-def _index(offs, toks, v, tile=16384):
+def _index(offs, toks, v, tile=16384, forward_index=True):
     rr = _rr()
     n = offs.shape[0] - 1
     emb = np.zeros((n, 4), dtype=np.float32)
     emb[:, 0] = 1.0
-    return rr.engine.HybridIndex(emb, offs, toks, v, device="cuda:0", tile_docs=tile, make_bf16=False)
+    return rr.engine.HybridIndex(emb, offs, toks, v, device="cuda:0", tile_docs=tile, make_bf16=False,
+                                 forward_index=forward_index)
 
 
 def _check(ix, csr, term_lists, atol=0.0):
@@ -65,11 +66,14 @@ def test_get_scores_matches_oracle(n, v, tile):
     cand = rng.integers(0, n, size=(len(term_lists), 37)).astype(np.int64)
     cand[0, :3] = [-1, n, 0]
     ids, nt = rr.engine.HybridIndex.pack_terms(term_lists)
-    cm = ix.bm25_candidates(ids, nt, cand).cpu().numpy()
-    for i in range(len(term_lists)):
-        ok = (cand[i] >= 0) & (cand[i] < n)
-        np.testing.assert_array_equal(cm[i][ok], got[i][cand[i][ok]])
-        assert np.all(cm[i][~ok] == 0)
+    ix_search = _index(offs, toks, v, tile, forward_index=False)     # candidate mode by postings search
+    for index in (ix, ix_search):                                    # ... and through the forward index
+        cm = index.bm25_candidates(ids, nt, cand).cpu().numpy()
+        for i in range(len(term_lists)):
+            ok = (cand[i] >= 0) & (cand[i] < n)
+            np.testing.assert_array_equal(cm[i][ok], got[i][cand[i][ok]])
+            assert np.all(cm[i][~ok] == 0)
+    ix_search.close()
     ix.close()
 
 

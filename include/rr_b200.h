@@ -176,12 +176,16 @@ int rr_fuse_topk(const rr_fusion_params*, int32_t B, int32_t n_in, const int32_t
 
 /* Same, for tuples received from n_shards row shards (the cross-shard merge of a row-sharded
  * corpus): shard s holds its [B, per_shard] block of every field at byte offset
- * s*shard_stride_bytes from the field's base pointer (n_in = n_shards*per_shard). */
+ * s*shard_stride_bytes from the field's base pointer (n_in = n_shards*per_shard).
+ * per_shard may be SMALLER than pool (each shard sends only its local top-m): d_incomplete[b]
+ * (optional) is then set to 1 when some shard sent all m of its tuples and its weakest one still
+ * reaches the merged pool's cut-off, i.e. that shard may hold further pool members and the query has
+ * to be repeated with per_shard = pool; 0 means the merged pool is provably the exact global pool. */
 int rr_fuse_topk_sharded(const rr_fusion_params*, int32_t B, int32_t n_shards, int32_t per_shard,
                          int64_t shard_stride_bytes,
                          const float* d_dense, const float* d_bm25, const double* d_n_reviews,
                          const double* d_avg_stars, const int64_t* d_global_row,
-                         int64_t* d_top_row, float* d_top_final, int device, rr_stream);
+                         int64_t* d_top_row, float* d_top_final, int32_t* d_incomplete, int device, rr_stream);
 
 /* One-shot single-shard search (rerank/best/gate absent): dense top-pool -> tuples -> fuse. */
 int rr_hybrid_search(rr_index*, const float* d_q, const int32_t* d_term_ids, const int32_t* d_n_terms,

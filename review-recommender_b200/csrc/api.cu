@@ -297,20 +297,21 @@ extern "C" int rr_fuse_topk(const rr_fusion_params* p, int32_t B, int32_t n_in, 
                             int32_t* d_top_pos, float* d_components, int device, rr_stream stream) {
     RR_CUDA(cudaSetDevice(device));
     return rr_launch_fuse(p, B, n_in, 1, 0, d_count, d_dense, d_bm25, d_n_reviews, d_avg_stars, d_global_row, d_rerank,
-                          d_best, d_gate, d_top_row, d_top_final, d_top_pos, d_components,
+                          d_best, d_gate, d_top_row, d_top_final, d_top_pos, d_components, nullptr,
                           static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int rr_fuse_topk_sharded(const rr_fusion_params* p, int32_t B, int32_t n_shards, int32_t per_shard,
                                     int64_t shard_stride_bytes, const float* d_dense, const float* d_bm25,
                                     const double* d_n_reviews, const double* d_avg_stars, const int64_t* d_global_row,
-                                    int64_t* d_top_row, float* d_top_final, int device, rr_stream stream) {
+                                    int64_t* d_top_row, float* d_top_final, int32_t* d_incomplete, int device,
+                                    rr_stream stream) {
     if (n_shards <= 0 || per_shard <= 0 || (shard_stride_bytes & 7))
         return rr_fail(RR_EINVAL, "rr_fuse_topk_sharded: bad shard geometry");
     RR_CUDA(cudaSetDevice(device));
     return rr_launch_fuse(p, B, n_shards * per_shard, n_shards, shard_stride_bytes, nullptr, d_dense, d_bm25,
                           d_n_reviews, d_avg_stars, d_global_row, nullptr, nullptr, nullptr, d_top_row, d_top_final,
-                          nullptr, nullptr, static_cast<cudaStream_t>(stream));
+                          nullptr, nullptr, d_incomplete, static_cast<cudaStream_t>(stream));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -338,7 +339,7 @@ static int hybrid_locked(rr_index* ix, const float* d_q, const int32_t* d_term_i
     RR_TRY(dense_topk_locked(ix, d_q, B, pool, dense_mode, cand, dense, count, s));
     RR_TRY(candidates_locked(ix, d_term_ids, d_n_terms, B, l_max, cand, pool, bm25, nrev, avg, grow, s));
     return rr_launch_fuse(fp, B, pool, 1, 0, count, dense, bm25, nrev, avg, grow, nullptr, nullptr, nullptr, d_top_row,
-                          d_top_final, nullptr, nullptr, s);
+                          d_top_final, nullptr, nullptr, nullptr, s);
 }
 
 static int check_hybrid_args(rr_index* ix, const void* q, const rr_fusion_params* fp, const void* top_row,

@@ -47,6 +47,7 @@ struct FuseArgs {
     float* top_final;
     int32_t* top_pos;
     float* components;
+    int32_t* incomplete;
 };
 
 __device__ __forceinline__ double nan64() { return __longlong_as_double(0x7FF8000000000000ll); }
@@ -151,6 +152,28 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
     const int n_valid = block_reduce<int>(n_valid_local, [](int x, int y) { return x + y; }, red_i);
     bitonic_desc(key, val, n_pad_in);
     const int P = min(a.p.pool, n_valid);
+
+    // ---- 1b. sharded input with local top-m < pool: is the merged pool provably the global pool? -------
+    if (a.incomplete != nullptr) {
+        __shared__ int s_incomplete;
+        if (tid == 0) s_incomplete = 0;
+        __syncthreads();
+        if (a.n_shards > 1 && per_shard < a.p.pool) {
+            const float cut = n_valid >= a.p.pool ? rr_key_score(key[P - 1]) : -INFINITY;
+            for (int s = tid; s < a.n_shards; s += FUSE_THREADS) {
+                int cnt = 0;
+                float weakest = INFINITY;
+                for (int j = 0; j < per_shard; ++j) {
+                    const int i = s * per_shard + j;
+                    if (a.grow[at(i, 8)] >= 0) { ++cnt; weakest = fminf(weakest, a.dense[at(i, 4)]); }
+                }
+                // a shard that sent everything it was allowed to may still hold rows scoring >= cut
+                if (cnt == per_shard && weakest >= cut) s_incomplete = 1;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) a.incomplete[b] = s_incomplete;
+    }
 
     // ---- 2. load the pool -----------------------------------------------------------------------
     for (int i = tid; i < P; i += FUSE_THREADS) {
@@ -350,7 +373,8 @@ int rr_launch_fuse(const rr_fusion_params* p, int B, int n_in, int n_shards, int
                    const int32_t* d_count, const float* d_dense,
                    const float* d_bm25, const double* d_n, const double* d_avg, const int64_t* d_grow,
                    const float* d_rerank, const float* d_best, const float* d_gate, int64_t* d_top_row,
-                   float* d_top_final, int32_t* d_top_pos, float* d_components, cudaStream_t stream) {
+                   float* d_top_final, int32_t* d_top_pos, float* d_components, int32_t* d_incomplete,
+                   cudaStream_t stream) {
     if (!p || B < 0 || !d_dense || !d_grow || !d_top_row || !d_top_final)
         return rr_fail(RR_EINVAL, "rr_fuse_topk: null argument");
     if (p->pool <= 0 || p->pool > FUSE_MAX_POOL) return rr_fail(RR_EINVAL, "rr_fuse_topk: pool must be in 1..%d", FUSE_MAX_POOL);
@@ -366,6 +390,7 @@ int rr_launch_fuse(const rr_fusion_params* p, int B, int n_in, int n_shards, int
     a.grow = reinterpret_cast<const long long*>(d_grow); a.rerank = d_rerank; a.best = d_best; a.gate = d_gate;
     a.top_row = reinterpret_cast<long long*>(d_top_row); a.top_final = d_top_final; a.top_pos = d_top_pos;
     a.components = d_components;
+    a.incomplete = d_incomplete;
     const int n_pad_in = next_pow2(n_in), n_pad_pool = next_pow2(p->pool);
     const int n_pad = n_pad_in > n_pad_pool ? n_pad_in : n_pad_pool;
     const size_t smem = (size_t)n_pad * 8 + (size_t)(n_pad + (n_pad & 1)) * 4 + (size_t)p->pool * (8 * 3 + 4 * 3) + 16;

@@ -5,8 +5,9 @@ The reference has no distributed code; the sharding follow
 north_star: the corpus is cut row-wise, every rank holds rows [row_offset, row_offset+n) with the
 postings of those rows and GLOBAL BM25 statistics, and per batch
 
-  1. every rank computes, for ALL B queries, its local exact top-`pool` by dense similarity and the
-     candidate tuples (dense, bm25, n_reviews, avg_stars, global row) -- K2/K3 + K1 candidates;
+  1. every rank computes, for ALL B queries, its local exact top-m by dense similarity (m = pool, or
+     fewer with the two-round proof of `ShardedSearcher`) and the candidate tuples
+     (dense, bm25, n_reviews, avg_stars, global row) -- K2/K3 + K1 candidates;
   2. ONE all-to-all ships, to rank r, the tuples of query slice r from every shard
      (B*pool*32 bytes leave each rank; an all-gather would move G times more);
   3. rank r merges its G*pool tuples per query by (dense desc, global row asc), keeps `pool`
@@ -20,6 +21,7 @@ with gloo (tests/test_dist_cpu.py); the compute calls need the CUDA library.
 """
 from __future__ import annotations
 
+import math
 from typing import Optional, Tuple
 
 import torch
@@ -85,34 +87,78 @@ def unpack_shard(recv: torch.Tensor, shard: int, per_rank_queries: int, pool: in
             take("dense", torch.float32, 4), take("bm25", torch.float32, 4))
 
 
-class ShardedSearcher:
-    """Hybrid search over a row-sharded corpus; call `search` collectively on every rank."""
+def local_pool(pool: int, world: int) -> int:
+    """Tuples each shard sends per query in round 1.  With rows spread evenly, a shard holds
+    Binomial(pool, 1/world) of the global pool: mean + 6 sigma, rounded up to 16, capped at pool."""
+    if world <= 1:
+        return pool
+    mean = pool / world
+    m = int(math.ceil((mean + 6.0 * math.sqrt(mean)) / 16.0) * 16)
+    return min(pool, max(16, m))
 
-    def __init__(self, index, group=None):
+
+class ShardedSearcher:
+    """Hybrid search over a row-sharded corpus; call `search` collectively on every rank.
+
+    Two-round distributed top-pool.  Round 1: every shard sends its local exact top-m (m = local_pool,
+    e.g. 48 of pool 150 on 8 shards), so the per-query work on a shard (shortlist selection, exact
+    rescoring, candidate BM25) shrinks with the shard.  The owner merges G*m tuples and PROVES the
+    result: a shard whose m-th similarity is below the merged pool's cut-off cannot hold another pool
+    member.  Queries that fail the proof (rows clustered on one shard) are repeated with m = pool,
+    which is always exact.  Results are therefore identical to the single-GPU search."""
+
+    def __init__(self, index, group=None, round1_pool: Optional[int] = None):
         self.ix = index
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.round1_pool = round1_pool
+        self.last_repeated = 0
+
+    def _round(self, q, term_ids, n_terms, fusion, mode, m):
+        ix, G = self.ix, self.world
+        B, k = int(q.shape[0]), fusion.k
+        Bg = B // G
+        cand, dense, _cnt = ix.dense_topk(q, m, mode)
+        bm25, n, avg, grow = ix.candidate_tuples(term_ids, n_terms, cand)
+        recv = exchange(pack_tuples(G, grow, n, avg, dense, bm25), self.group)
+        views, stride = field_views(recv, Bg, m)
+        rows, final, flags = ix.fuse_sharded(fusion, G, m, stride, Bg, views["dense"], views["bm25"], views["n"],
+                                             views["avg"], views["grow"])
+        # one collective for all outputs: [Bg, k] rows | [Bg, k] finals | [Bg] flags (as int64 words)
+        mine = torch.cat([rows.view(-1), final.view(-1).view(torch.int32).to(torch.int64), flags.to(torch.int64)])
+        out = torch.empty((G, mine.numel()), dtype=torch.int64, device=mine.device)
+        dist.all_gather_into_tensor(out.view(-1), mine, group=self.group)
+        all_rows = out[:, :Bg * k].reshape(B, k)
+        all_final = out[:, Bg * k:2 * Bg * k].to(torch.int32).view(torch.float32).reshape(B, k)
+        all_flags = out[:, 2 * Bg * k:].reshape(B)
+        return all_rows, all_final, all_flags
 
     def search(self, q: torch.Tensor, term_ids: Optional[torch.Tensor], n_terms: Optional[torch.Tensor], fusion,
                mode: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
         """q float32[B, D] (identical on every rank, B % world == 0) -> (global rows int64[B, k],
         final float32[B, k]) on every rank."""
-        ix, G = self.ix, self.world
-        B, pool, k = int(q.shape[0]), fusion.pool, fusion.k
+        G = self.world
+        B, pool = int(q.shape[0]), fusion.pool
         if B % G:
             raise ValueError("batch size must be a multiple of the world size")
-        Bg = B // G
-        cand, dense, _cnt = ix.dense_topk(q, pool, mode)
-        bm25, n, avg, grow = ix.candidate_tuples(term_ids, n_terms, cand)
-        recv = exchange(pack_tuples(G, grow, n, avg, dense, bm25), self.group)
-        views, stride = field_views(recv, Bg, pool)
-        rows, final = ix.fuse_sharded(fusion, G, pool, stride, Bg, views["dense"], views["bm25"], views["n"],
-                                      views["avg"], views["grow"])
-        # one collective for both outputs: [Bg, k] int64 rows | [Bg, k] float32 finals (as int64 words)
-        mine = torch.cat([rows.view(-1), final.view(-1).view(torch.int32).to(torch.int64)])
-        out = torch.empty((G, mine.numel()), dtype=torch.int64, device=mine.device)
-        dist.all_gather_into_tensor(out.view(-1), mine, group=self.group)
-        all_rows = out[:, :Bg * k].reshape(B, k)
-        all_final = out[:, Bg * k:].to(torch.int32).view(torch.float32).reshape(B, k)
-        return all_rows, all_final
+        m = self.round1_pool or local_pool(pool, G)
+        m = min(m, pool)
+        rows, final, flags = self._round(q, term_ids, n_terms, fusion, mode, m)
+        self.last_repeated = 0
+        if m < pool:
+            idx = torch.nonzero(flags, as_tuple=False).view(-1)        # host sync: how many queries need round 2
+            nf = int(idx.numel())
+            self.last_repeated = nf
+            if nf > 0:
+                pad = (-nf) % G
+                if pad:
+                    idx = torch.cat([idx, idx[:1].expand(pad)])
+                r2, f2, _ = self._round(q[idx].contiguous(),
+                                        None if term_ids is None else term_ids[idx].contiguous(),
+                                        None if n_terms is None else n_terms[idx].contiguous(), fusion, mode, pool)
+                rows = rows.clone()
+                final = final.clone()
+                rows[idx[:nf]] = r2[:nf]
+                final[idx[:nf]] = f2[:nf]
+        return rows, final

@@ -358,10 +358,11 @@ class HybridIndex:
         p = fusion.to_c()
         rows = torch.empty((B, fusion.k), dtype=torch.int64, device=self.device)
         final = torch.empty((B, fusion.k), dtype=torch.float32, device=self.device)
+        flags = torch.zeros((B,), dtype=torch.int32, device=self.device)
         check(self.lib.rr_fuse_topk_sharded(C.byref(p), B, n_shards, per_shard, shard_stride_bytes, _ptr(dense),
                                             _ptr(bm25), _ptr(n), _ptr(avg), _ptr(grow), _ptr(rows), _ptr(final),
-                                            self.device.index or 0, _stream()))
-        return rows, final
+                                            _ptr(flags), self.device.index or 0, _stream()))
+        return rows, final, flags
 
     # ---- one-shot ------------------------------------------------------------------------------
     def hybrid_search(self, q, term_ids, n_terms, fusion: Fusion, mode: int = _lib.RR_DENSE_AUTO):

@@ -41,10 +41,15 @@ WORKER = textwrap.dedent('''
     st.finalize()
     ix = rr.engine.HybridIndex(full.emb[row0:row1], offs, toks, V, full.n_reviews[row0:row1], full.avg_stars[row0:row1],
                                device=dev, row_offset=row0, stats=st)
-    searcher = rr.dist.ShardedSearcher(ix)
-    for mode in (rr._lib.RR_DENSE_EXACT, rr._lib.RR_DENSE_TENSOR):
+    whole_ref = None
+    for mode, r1 in ((rr._lib.RR_DENSE_EXACT, None), (rr._lib.RR_DENSE_TENSOR, None), (rr._lib.RR_DENSE_TENSOR, 16)):
+        # r1=16: far too few tuples per shard in round 1 -> many queries must take the exact second round
+        searcher = rr.dist.ShardedSearcher(ix, round1_pool=r1)
         rows, final = searcher.search(torch.from_numpy(q).to(dev), torch.from_numpy(qt).to(dev),
                                       torch.from_numpy(nt).to(dev), fusion, mode=mode)
+        if r1 == 16:
+            assert searcher.last_repeated > 0
+        print("rank", rank, "mode", mode, "round1", r1 or rr.dist.local_pool(fusion.pool, world), "repeated", searcher.last_repeated)
         if rank == 0:
             whole = rr.engine.HybridIndex(full.emb, full.doc_offsets, full.token_ids, V, full.n_reviews, full.avg_stars,
                                           device=dev)

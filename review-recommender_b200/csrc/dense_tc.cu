@@ -377,8 +377,8 @@ __global__ void __launch_bounds__(256)
 tc_select_kernel(const unsigned long long* __restrict__ cand_keys, unsigned* __restrict__ cand_cnt, int n_sub,
                  int cap_sub, unsigned long long* __restrict__ kept_keys, int* __restrict__ kept_cnt, int KP,
                  float* __restrict__ tau, int* __restrict__ overflow, int final_pass,
-                 long long* __restrict__ rows_out) {
-    extern __shared__ unsigned long long sk[];
+                 long long* __restrict__ rows_out, int sort_cap) {
+    extern __shared__ unsigned long long sk[];      // sort_cap keys
     __shared__ int s_off[TC_MAX_SUB + 1];
     __shared__ unsigned s_hist[256];
     __shared__ unsigned long long s_red[16];
@@ -419,15 +419,15 @@ tc_select_kernel(const unsigned long long* __restrict__ cand_keys, unsigned* __r
     if (tid + 256 < n_sub) s_off[tid + 256] = kc + tot0 + wbase1 + x1 - c1;
     const int total_all = kc + tot0 + tot1;
     if (tid == 0) s_off[n_sub] = total_all;
-    if (over || (tid == 0 && total_all > TC_SORT_MAX)) s_over = 1;
+    if (over || (tid == 0 && total_all > sort_cap)) s_over = 1;
     __syncthreads();
-    const int total = min(total_all, TC_SORT_MAX);
+    const int total = min(total_all, sort_cap);
 
     // gather into shared memory
     for (int i = tid; i < kc; i += 256) sk[i] = kept_keys[(size_t)q * KP + i];
     for (int r = wid; r < n_sub; r += 8) {
         const int lo = s_off[r];
-        const int n = min(s_off[r + 1], TC_SORT_MAX) - lo;
+        const int n = min(s_off[r + 1], sort_cap) - lo;
         const unsigned long long* src = cand_keys + ((size_t)q * n_sub + r) * cap_sub;
         for (int i = lane; i < n; i += 32) {
             const unsigned long long raw = src[i];               // {score bits, doc} as written by the epilogue
@@ -775,7 +775,6 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
     const int seg0_tiles = std::max(1, std::min(reps_min, (TC_SORT_MAX - KP) / TC_BN));
     int n_segments = 0;
     int dt_lo = 0;
-    const size_t sel_smem = (size_t)TC_SORT_MAX * 8;
     while (dt_lo < n_dt) {
         const int dt_hi = dt_lo == 0 ? std::min(n_dt, seg0_tiles)
                                      : (int)std::min<long long>(n_dt, (long long)dt_lo * TC_GROWTH);
@@ -798,13 +797,18 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
         }
         const int final_pass = dt_hi >= n_dt;
         {
+            // keys a query can bring to this selection: everything of the all-pass first segment, else the
+            // kept list plus ~ (growth-1)*k' expected passes (2x head-room; more is flagged as overflow
+            // and that query is redone exactly)
+            const int expect = dt_lo == 0 ? (dt_hi - dt_lo) * TC_BN : KP * (2 * TC_GROWTH);
+            const int sort_cap = std::min(TC_SORT_MAX, std::max(1024, (expect + 255) / 256 * 256));
             RrProfScope prof(RR_PROF_TC_SELECT, s);
-            tc_select_kernel<<<B, 256, sel_smem, s>>>(static_cast<const unsigned long long*>(st->cand_keys.p),
+            tc_select_kernel<<<B, 256, (size_t)sort_cap * 8, s>>>(static_cast<const unsigned long long*>(st->cand_keys.p),
                                                       static_cast<unsigned*>(st->cand_cnt.p), n_sub, cap_sub,
                                                       static_cast<unsigned long long*>(st->kept_keys.p),
                                                       static_cast<int*>(st->kept_cnt.p), KP, static_cast<float*>(st->tau.p),
                                                       static_cast<int*>(st->overflow.p), final_pass,
-                                                      static_cast<long long*>(st->rows.p));
+                                                      static_cast<long long*>(st->rows.p), sort_cap);
         }
         RR_LAUNCH_CHECK();
         dt_lo = dt_hi;
@@ -815,7 +819,9 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
     const float eps_rel = (0.0078125f + 0.000030517578125f + 1e-4f) * d->max_row_norm;
     {
         RrProfScope prof(RR_PROF_TC_FINALIZE, s);
-        tc_finalize_kernel<<<B, 256, sel_smem, s>>>(static_cast<const unsigned long long*>(st->kept_keys.p),
+        int fin_pad = 2;
+        while (fin_pad < KP) fin_pad <<= 1;
+        tc_finalize_kernel<<<B, 256, (size_t)fin_pad * 8, s>>>(static_cast<const unsigned long long*>(st->kept_keys.p),
                                                     static_cast<const int*>(st->kept_cnt.p), KP,
                                                     static_cast<const float*>(st->exact.p),
                                                     static_cast<const int*>(st->overflow.p),

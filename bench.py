@@ -321,15 +321,15 @@ def main():
         return float(t.item())
 
     # ---- device-resident timing ------------------------------------------------------------------
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()          # sampled from the warm-up on: every sample is taken under the same load
     for _ in range(args.warmup):
         step_device()
     sync_all()
     eng.profile_enable(True)
     eng.profile_collect()
     eng.launch_count(reset=True)
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()

@@ -679,7 +679,10 @@ static int shortlist_size(int pool) {
     const char* env = getenv("RR_TC_SHORTLIST_FACTOR");
     double f = env ? atof(env) : 2.6;
     if (!(f >= 1.0)) f = 2.6;
-    int kp = (int)std::ceil(pool * f);
+    // rows within the certification margin of the pool-th score: ~0.9*pool on unit-norm data, plus six
+    // standard deviations and a constant so that small pools (sharded round 1) certify as reliably as big ones
+    const double base = 1.9 * pool;
+    int kp = (int)std::ceil(std::max(pool * f, base + 6.0 * std::sqrt(base) + 16.0));
     kp = (kp + 63) / 64 * 64;
     return std::max(kp, 64);
 }

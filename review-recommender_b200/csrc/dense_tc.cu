@@ -45,7 +45,8 @@ constexpr int TC_BM = 128;      // queries per CTA tile (UMMA M)
 constexpr int TC_BN = 256;      // docs per tile (UMMA N)
 constexpr int TC_BK = 64;       // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int TC_STAGES = 4;
-constexpr int TC_MAX_KB = 6;    // dim_pad <= 384 keeps the query tile resident
+constexpr int TC_MAX_KB = 6;    // dim_pad <= 384 keeps the query tile resident in shared memory ...
+constexpr int TC_MAX_KB_STREAMED = 32;   // ... wider rows (<= 2048) stream the query k-blocks next to the corpus k-blocks
 constexpr int TC_THREADS = 384;     // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue (2 x 4 warps)
 constexpr int TC_EPI_THREADS = 256;
 constexpr int TC_Q_KB_BYTES = TC_BM * TC_BK * 2;    // 16 KB
@@ -56,8 +57,8 @@ constexpr int TC_SMEM_BAR = 256;
 constexpr int TC_SMEM_TOTAL = TC_SMEM_Q + TC_SMEM_B + TC_SMEM_BAR + 1024;   // + alignment slack
 constexpr int TC_CAP_TOTAL = 16384;  // candidate slots per query per segment, split evenly over the CTAs
                                      // that scan for that query (each owns a private sub-list: no atomics)
-constexpr int TC_SORT_MAX = 8192;    // largest per-query sort in tc_select_kernel (64 KB of keys)
-constexpr int TC_GROWTH = 4;         // corpus prefix grows x4 per segment
+constexpr int TC_SORT_MAX = 16384;   // largest per-query selection in tc_select_kernel (128 KB of keys)
+constexpr int TC_GROWTH = 4;         // corpus prefix grows x4 per segment (x2 for very long shortlists)
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -189,6 +190,7 @@ struct TcFilterArgs {
     int qt0, n_qt;     // query tiles handled by this launch
     int reps;          // CTAs per query tile
     int dt_lo, dt_hi;  // doc tiles of this segment
+    int q_resident;    // 1: query tile loaded once (dim_pad <= 384); 0: its k-blocks are streamed with the corpus'
     const float* tau;  // [B]
     int n_sub, cap_sub;              // sub-lists per query (2 per scanning CTA) and slots per sub-list
     unsigned long long* cand_keys;   // [B, n_sub, cap_sub]
@@ -200,8 +202,10 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                  const TcFilterArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // resident: [Q: 6 x 16 KB][B ring: 4 x 32 KB]      streamed: [ring: 4 x (A 16 KB | B 32 KB)]
     uint8_t* sQ = smem;
     uint8_t* sB = smem + TC_SMEM_Q;
+    constexpr int kStreamStage = TC_Q_KB_BYTES + TC_B_KB_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_SMEM_Q + TC_SMEM_B);
     uint64_t* full = bars;                  // [TC_STAGES]  TMA -> MMA
     uint64_t* empty = bars + TC_STAGES;     // [TC_STAGES]  MMA -> TMA
@@ -234,16 +238,25 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (warp == 0) {
         // ===== TMA producer (one thread) =====
         if (lane == 0 && n_tiles > 0) {
-            mbar_expect_tx(qfull, (uint32_t)(a.n_kb * TC_Q_KB_BYTES));
-            for (int kb = 0; kb < a.n_kb; ++kb) tma_load_2d(&tmap_q, qfull, sQ + kb * TC_Q_KB_BYTES, kb * TC_BK, qt * TC_BM);
+            if (a.q_resident) {
+                mbar_expect_tx(qfull, (uint32_t)(a.n_kb * TC_Q_KB_BYTES));
+                for (int kb = 0; kb < a.n_kb; ++kb) tma_load_2d(&tmap_q, qfull, sQ + kb * TC_Q_KB_BYTES, kb * TC_BK, qt * TC_BM);
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int t = 0; t < n_tiles; ++t) {
                 const int dt = a.dt_lo + j0 + t * a.reps;
                 for (int kb = 0; kb < a.n_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
-                    mbar_expect_tx(&full[stage], (uint32_t)TC_B_KB_BYTES);
-                    tma_load_2d(&tmap_c, &full[stage], sB + stage * TC_B_KB_BYTES, kb * TC_BK, dt * TC_BN);
+                    if (a.q_resident) {
+                        mbar_expect_tx(&full[stage], (uint32_t)TC_B_KB_BYTES);
+                        tma_load_2d(&tmap_c, &full[stage], sB + stage * TC_B_KB_BYTES, kb * TC_BK, dt * TC_BN);
+                    } else {
+                        uint8_t* st = smem + stage * kStreamStage;
+                        mbar_expect_tx(&full[stage], (uint32_t)kStreamStage);
+                        tma_load_2d(&tmap_q, &full[stage], st, kb * TC_BK, qt * TC_BM);
+                        tma_load_2d(&tmap_c, &full[stage], st + TC_Q_KB_BYTES, kb * TC_BK, dt * TC_BN);
+                    }
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -251,8 +264,10 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0 && n_tiles > 0) {
-            mbar_wait(qfull, 0u);
-            tc_fence_after();
+            if (a.q_resident) {
+                mbar_wait(qfull, 0u);
+                tc_fence_after();
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int t = 0; t < n_tiles; ++t) {
@@ -264,8 +279,10 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 for (int kb = 0; kb < a.n_kb; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_sw128(sQ + kb * TC_Q_KB_BYTES);
-                    const uint64_t db = umma_desc_sw128(sB + stage * TC_B_KB_BYTES);
+                    const uint8_t* pa = a.q_resident ? sQ + kb * TC_Q_KB_BYTES : smem + stage * kStreamStage;
+                    const uint8_t* pb = a.q_resident ? sB + stage * TC_B_KB_BYTES : smem + stage * kStreamStage + TC_Q_KB_BYTES;
+                    const uint64_t da = umma_desc_sw128(pa);
+                    const uint64_t db = umma_desc_sw128(pb);
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k)       // +32 bytes (>>4 = 2) per K=16 step
                         umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kInstrDesc, (uint32_t)((kb | k) != 0));
@@ -675,6 +692,9 @@ void rr_tc_destroy(rr_tc_state* s) {
     delete s;
 }
 
+// corpus prefix growth per segment: x4, or x2 when 8*k' keys would not fit one selection
+static int KP_growth(int kp) { return kp * 2 * TC_GROWTH <= TC_SORT_MAX ? TC_GROWTH : 2; }
+
 static int shortlist_size(int pool) {
     const char* env = getenv("RR_TC_SHORTLIST_FACTOR");
     double f = env ? atof(env) : 2.6;
@@ -688,14 +708,15 @@ static int shortlist_size(int pool) {
 }
 
 bool rr_tc_can_handle(int dim_pad, int pool) {
-    return dim_pad > 0 && dim_pad <= TC_MAX_KB * TC_BK && shortlist_size(pool) <= TC_SORT_MAX / 4;
+    return dim_pad > 0 && dim_pad <= TC_MAX_KB_STREAMED * TC_BK && shortlist_size(pool) <= TC_SORT_MAX / 4;
 }
 
 int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, const float* d_q, int32_t B,
                      int32_t pool, int64_t* d_idx, float* d_sims, int32_t* d_count, rr_dense_stats* stats,
                      rr_exact_fn exact_fn, void* exact_ctx, cudaStream_t s) {
-    if (d->dim_pad > TC_MAX_KB * TC_BK)
-        return rr_fail(RR_EUNSUPPORTED, "tensor path supports dim <= %d in this build", TC_MAX_KB * TC_BK);
+    if (d->dim_pad > TC_MAX_KB_STREAMED * TC_BK)
+        return rr_fail(RR_EUNSUPPORTED, "tensor path supports dim <= %d in this build", TC_MAX_KB_STREAMED * TC_BK);
+    const int growth = KP_growth(shortlist_size(pool));
     const int KP = shortlist_size(pool);
     if (KP > TC_SORT_MAX / 4) return rr_fail(RR_EUNSUPPORTED, "tensor path supports pool <= %d", (int)(TC_SORT_MAX / 4 / 2.6));
     if (!*state) {
@@ -780,7 +801,7 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
     int dt_lo = 0;
     while (dt_lo < n_dt) {
         const int dt_hi = dt_lo == 0 ? std::min(n_dt, seg0_tiles)
-                                     : (int)std::min<long long>(n_dt, (long long)dt_lo * TC_GROWTH);
+                                     : (int)std::min<long long>(n_dt, (long long)dt_lo * growth);
         int qt0 = 0;
         for (int p = 0; p < best_parts; ++p) {
             const int nq = n_qt / best_parts + (p < n_qt % best_parts ? 1 : 0);
@@ -788,6 +809,7 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
             a.n_docs = d->n_docs; a.n_kb = d->dim_pad / TC_BK; a.B = B; a.qt0 = qt0; a.n_qt = nq;
             a.reps = std::max(1, std::min(sm_count / nq, dt_hi - dt_lo));
             a.dt_lo = dt_lo; a.dt_hi = dt_hi; a.tau = static_cast<const float*>(st->tau.p);
+            a.q_resident = d->dim_pad <= TC_MAX_KB * TC_BK ? 1 : 0;
             a.n_sub = n_sub; a.cap_sub = cap_sub;
             a.cand_keys = static_cast<unsigned long long*>(st->cand_keys.p);
             a.cand_cnt = static_cast<unsigned*>(st->cand_cnt.p);
@@ -803,7 +825,7 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
             // keys a query can bring to this selection: everything of the all-pass first segment, else the
             // kept list plus ~ (growth-1)*k' expected passes (2x head-room; more is flagged as overflow
             // and that query is redone exactly)
-            const int expect = dt_lo == 0 ? (dt_hi - dt_lo) * TC_BN : KP * (2 * TC_GROWTH);
+            const int expect = dt_lo == 0 ? (dt_hi - dt_lo) * TC_BN : KP * (2 * growth);
             const int sort_cap = std::min(TC_SORT_MAX, std::max(1024, (expect + 255) / 256 * 256));
             RrProfScope prof(RR_PROF_TC_SELECT, s);
             tc_select_kernel<<<B, 256, (size_t)sort_cap * 8, s>>>(static_cast<const unsigned long long*>(st->cand_keys.p),

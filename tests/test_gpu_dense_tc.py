@@ -25,7 +25,10 @@ def _both(ix, q, pool):
 
 
 @pytest.mark.parametrize("n,d,b,pool", [(5000, 64, 40, 20), (70_000, 384, 200, 150), (33_333, 100, 130, 150),
-                                         (300_000, 384, 256, 150), (1000, 128, 3, 150)])
+                                         (300_000, 384, 256, 150), (1000, 128, 3, 150),
+                                         (60_000, 768, 130, 150),      # 768-d: query k-blocks streamed (configs[4] shape)
+                                         (120_000, 768, 64, 1000),     # top-1000 shortlist (configs[4]: k = pool = 1000)
+                                         (50_000, 448, 33, 48)])       # small pool of a sharded round 1
 def test_tensor_path_equals_exact_path(n, d, b, pool):
     rr = _rr()
     emb = rr.synth.embeddings(n, d)

@@ -24,6 +24,16 @@ def test_hybrid_matches_oracle(n, d, v, b, l, k, driver):
     assert frac >= 0.9
 
 
+def test_config5_shape_dense_heavy_top1000():
+    """BASELINE configs[4] at reduced N: 768-d, fusion weight 0.8 on dense, top-1000 for the reranker
+    (pool = 1000), through the tensor path (batch >= 32, N >= 65536) and through the exact path."""
+    import review_recommender_b200 as rr
+    for mode in (rr._lib.RR_DENSE_TENSOR, rr._lib.RR_DENSE_EXACT):
+        frac = check_hybrid_against_oracle(70_000, 768, 20_000, 4, 4, 1000, driver="streamlit", mode=mode, rerank_k=0,
+                                           w_dense=0.8, w_bm25=0.1, w_prior=0.1, w_rerank=0.0, w_best=0.0)
+        assert frac >= 0.9
+
+
 def test_golden_cases_from_the_reference(golden_dir):
     """The reference's own run_search / search outputs (tests/golden/search_cases.json) reproduced
     through the C-ABI: same top-k SKUs, fused scores within 1e-5 relative."""

@@ -401,7 +401,7 @@ tc_select_kernel(const unsigned long long* __restrict__ cand_keys, unsigned* __r
     __shared__ unsigned long long s_red[16];
     __shared__ unsigned long long s_prefix, s_minsel;
     __shared__ int s_bits, s_krem, s_done, s_over, s_out;
-    __shared__ int s_wsum[8], s_wsum1[8], s_tail;
+    __shared__ int s_wsum[8], s_wsum1[8];
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int kc = kept_cnt[q];
 
@@ -558,6 +558,161 @@ tc_select_kernel(const unsigned long long* __restrict__ cand_keys, unsigned* __r
         kept_cnt[q] = newk;
         tau[q] = newk == KP ? rr_key_score(s_minsel) : -INFINITY;
         if (s_over) overflow[q] = 1;
+    }
+}
+
+// Warp-per-query variant of the selection (used when a query's keys fit `cap` <= 2048 slots): no block
+// barriers, 4..8 queries per CTA.  Same algorithm as tc_select_kernel: gather kept + candidate sub-lists into
+// shared memory, MSB-first radix select below the common prefix, compact the k' survivors, tau = k'-th score.
+__global__ void __launch_bounds__(256)
+tc_select_warp_kernel(const unsigned long long* __restrict__ cand_keys, unsigned* __restrict__ cand_cnt, int n_sub,
+                      int cap_sub, unsigned long long* __restrict__ kept_keys, int* __restrict__ kept_cnt, int KP,
+                      float* __restrict__ tau, int* __restrict__ overflow, int final_pass,
+                      long long* __restrict__ rows_out, int cap, int warps_per_cta, int B) {
+    extern __shared__ unsigned long long smem_sel[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int q = blockIdx.x * warps_per_cta + wid;
+    if (wid >= warps_per_cta || q >= B) return;
+    // per-warp carve: keys[cap] | hist[256] (u32) | off[TC_MAX_SUB+1] (int)
+    const size_t per_warp_words = (size_t)cap + 128 + (TC_MAX_SUB + 2) / 2 + 1;
+    unsigned long long* sk = smem_sel + (size_t)wid * per_warp_words;
+    unsigned* hist = reinterpret_cast<unsigned*>(sk + cap);
+    int* s_off = reinterpret_cast<int*>(sk + cap + 128);
+    const unsigned FULL = 0xffffffffu;
+
+    const int kc = kept_cnt[q];
+    // ---- sub-list sizes -> offsets ------------------------------------------------------------------
+    int run = kc, over = 0;
+    for (int r0 = 0; r0 < n_sub; r0 += 32) {
+        const int r = r0 + lane;
+        int c = 0;
+        if (r < n_sub) {
+            const unsigned raw = cand_cnt[(size_t)q * n_sub + r];
+            c = (int)min(raw, (unsigned)cap_sub);
+            over |= raw > (unsigned)cap_sub;
+        }
+        int x = c;
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, x, o); if (lane >= o) x += y; }
+        if (r < n_sub) s_off[r] = run + x - c;
+        run += __shfl_sync(FULL, x, 31);
+    }
+    const int total_all = run;
+    if (lane == 0) s_off[n_sub] = total_all;
+    over = __any_sync(FULL, over) || total_all > cap;
+    const int total = min(total_all, cap);
+    __syncwarp();
+
+    // ---- gather ----------------------------------------------------------------------------------
+    for (int i = lane; i < kc; i += 32) sk[i] = kept_keys[(size_t)q * KP + i];
+    for (int r = 0; r < n_sub; ++r) {
+        const int lo = s_off[r];
+        const int n = min(s_off[r + 1], cap) - lo;
+        const unsigned long long* src = cand_keys + ((size_t)q * n_sub + r) * cap_sub;
+        for (int i = lane; i < n; i += 32) {
+            const unsigned long long raw = src[i];
+            const unsigned long long k = rr_make_key(__uint_as_float((uint32_t)raw), (uint32_t)(raw >> 32));
+            sk[lo + i] = k ? k : 1ull;
+        }
+    }
+    __syncwarp();
+
+    int newk = total;
+    unsigned long long thr_prefix = 0ull;
+    int thr_bits = 0;
+    if (total > KP) {
+        unsigned long long kmin = ~0ull, kmax = 0ull;
+        for (int i = lane; i < total; i += 32) { const unsigned long long k = sk[i]; kmin = min(kmin, k); kmax = max(kmax, k); }
+        for (int o = 16; o > 0; o >>= 1) {
+            kmin = min(kmin, __shfl_xor_sync(FULL, kmin, o));
+            kmax = max(kmax, __shfl_xor_sync(FULL, kmax, o));
+        }
+        int bits = kmin == kmax ? 56 : min(__clzll((long long)(kmin ^ kmax)), 56);
+        unsigned long long prefix = bits ? (kmax >> (64 - bits)) : 0ull;
+        int krem = KP;
+        bool done = false;
+        for (int pass = 0; pass < 9 && !done; ++pass) {
+            const int dig = min(8, 64 - bits);
+            if (dig <= 0) break;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0u;
+            __syncwarp();
+            const int shift = 64 - bits - dig;
+            for (int i0 = 0; i0 < total; i0 += 32) {
+                const int i = i0 + lane;
+                bool in = false;
+                unsigned b = 0;
+                if (i < total) {
+                    const unsigned long long k = sk[i];
+                    in = bits == 0 || (k >> (64 - bits)) == prefix;
+                    b = (unsigned)((k >> shift) & ((1u << dig) - 1u));
+                }
+                const unsigned act = __ballot_sync(FULL, in);
+                if (in) {
+                    const unsigned peers = __match_any_sync(act, b);
+                    if ((int)(__ffs(peers) - 1) == lane) atomicAdd(&hist[b], (unsigned)__popc(peers));
+                }
+            }
+            __syncwarp();
+            unsigned loc[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { loc[j] = hist[255 - (lane * 8 + j)]; sum += loc[j]; }
+            unsigned incl = sum;
+            for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
+            const unsigned excl = incl - sum;
+            const bool mine = excl < (unsigned)krem && (unsigned)krem <= incl;
+            int bucket = 0, nk = 0, fin = 0;
+            if (mine) {
+                unsigned above = excl;
+                int j = 0;
+#pragma unroll
+                for (int jj = 0; jj < 7; ++jj) { if (j == jj && above + loc[jj] < (unsigned)krem) { above += loc[jj]; ++j; } }
+                unsigned lj = 0;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) if (jj == j) lj = loc[jj];
+                bucket = 255 - (lane * 8 + j);
+                nk = krem - (int)above;
+                fin = (lj == (unsigned)nk) || (bits + dig >= 64);
+            }
+            const unsigned who = __ballot_sync(FULL, mine);
+            const int src = __ffs(who) - 1;
+            bucket = __shfl_sync(FULL, bucket, src);
+            krem = __shfl_sync(FULL, nk, src);
+            done = __shfl_sync(FULL, fin, src) != 0;
+            prefix = (prefix << dig) | (unsigned long long)bucket;
+            bits += dig;
+            __syncwarp();
+        }
+        thr_prefix = prefix;
+        thr_bits = bits;
+        newk = KP;
+    }
+    // ---- compact survivors --------------------------------------------------------------------------
+    unsigned long long mymin = ~0ull;
+    int out = 0;
+    for (int i0 = 0; i0 < total; i0 += 32) {
+        const int i = i0 + lane;
+        bool sel = false;
+        unsigned long long k = 0ull;
+        if (i < total) { k = sk[i]; sel = thr_bits == 0 || (k >> (64 - thr_bits)) >= thr_prefix; }
+        const unsigned m = __ballot_sync(FULL, sel);
+        if (sel) {
+            const int slot = out + __popc(m & ((1u << lane) - 1u));
+            if (slot < KP) {
+                kept_keys[(size_t)q * KP + slot] = k;
+                if (final_pass) rows_out[(size_t)q * KP + slot] = (long long)rr_key_index(k);
+            }
+            mymin = min(mymin, k);
+        }
+        out += __popc(m);
+    }
+    for (int o = 16; o > 0; o >>= 1) mymin = min(mymin, __shfl_xor_sync(FULL, mymin, o));
+    if (final_pass)
+        for (int i = newk + lane; i < KP; i += 32) rows_out[(size_t)q * KP + i] = -1ll;
+    for (int r = lane; r < n_sub; r += 32) cand_cnt[(size_t)q * n_sub + r] = 0u;
+    if (lane == 0) {
+        kept_cnt[q] = newk;
+        tau[q] = newk == KP ? rr_key_score(mymin) : -INFINITY;
+        if (over) overflow[q] = 1;
     }
 }
 
@@ -730,6 +885,8 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
         RR_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SORT_MAX * 8));
         RR_CUDA(cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SORT_MAX * 8));
         RR_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        RR_CUDA(cudaFuncSetAttribute(tc_select_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        RR_CUDA(cudaFuncSetAttribute(tc_select_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         RR_CUDA(cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         st->attr_set = true;
     }
@@ -825,15 +982,26 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
             // keys a query can bring to this selection: everything of the all-pass first segment, else the
             // kept list plus ~ (growth-1)*k' expected passes (2x head-room; more is flagged as overflow
             // and that query is redone exactly)
-            const int expect = dt_lo == 0 ? (dt_hi - dt_lo) * TC_BN : KP * (2 * growth);
+            // (kept k' + (growth-1) k' expected passes) with 50 % head-room
+            const int expect = dt_lo == 0 ? (dt_hi - dt_lo) * TC_BN + KP : KP * (growth + 2);
             const int sort_cap = std::min(TC_SORT_MAX, std::max(1024, (expect + 255) / 256 * 256));
             RrProfScope prof(RR_PROF_TC_SELECT, s);
-            tc_select_kernel<<<B, 256, (size_t)sort_cap * 8, s>>>(static_cast<const unsigned long long*>(st->cand_keys.p),
-                                                      static_cast<unsigned*>(st->cand_cnt.p), n_sub, cap_sub,
-                                                      static_cast<unsigned long long*>(st->kept_keys.p),
-                                                      static_cast<int*>(st->kept_cnt.p), KP, static_cast<float*>(st->tau.p),
-                                                      static_cast<int*>(st->overflow.p), final_pass,
-                                                      static_cast<long long*>(st->rows.p), sort_cap);
+            if (sort_cap <= 2048) {
+                // warp per query: 4..8 queries per CTA, no block barriers
+                const size_t per_warp_words = (size_t)sort_cap + 128 + (TC_MAX_SUB + 2) / 2 + 1;
+                const int wpc = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(96 * 1024) / (per_warp_words * 8)));
+                tc_select_warp_kernel<<<(B + wpc - 1) / wpc, wpc * 32, per_warp_words * 8 * wpc, s>>>(
+                    static_cast<const unsigned long long*>(st->cand_keys.p), static_cast<unsigned*>(st->cand_cnt.p), n_sub,
+                    cap_sub, static_cast<unsigned long long*>(st->kept_keys.p), static_cast<int*>(st->kept_cnt.p), KP,
+                    static_cast<float*>(st->tau.p), static_cast<int*>(st->overflow.p), final_pass,
+                    static_cast<long long*>(st->rows.p), sort_cap, wpc, B);
+            } else {
+                tc_select_kernel<<<B, 256, (size_t)sort_cap * 8, s>>>(
+                    static_cast<const unsigned long long*>(st->cand_keys.p), static_cast<unsigned*>(st->cand_cnt.p), n_sub,
+                    cap_sub, static_cast<unsigned long long*>(st->kept_keys.p), static_cast<int*>(st->kept_cnt.p), KP,
+                    static_cast<float*>(st->tau.p), static_cast<int*>(st->overflow.p), final_pass,
+                    static_cast<long long*>(st->rows.p), sort_cap);
+            }
         }
         RR_LAUNCH_CHECK();
         dt_lo = dt_hi;

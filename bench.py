@@ -327,8 +327,6 @@ def main():
     for _ in range(args.warmup):
         step_device()
     sync_all()
-    eng.profile_enable(True)
-    eng.profile_collect()
     eng.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
@@ -337,12 +335,24 @@ def main():
         rows, final = step_device()
     e1.record()
     sync_all()
-    clock_info = clocks.stop() if rank == 0 else {}
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.launch_count(reset=True)
+    ms_per_step = ms_total / args.steps
+    # the same K steps again with every kernel launch bracketed by CUDA events on its stream (per-class
+    # device time for the roofline); kept out of the loop above because ~80 event records per step cost
+    # 0.1-0.2 ms of host time, which is visible when a step is only a few ms long (multi-GPU)
+    eng.profile_enable(True)
+    eng.profile_collect()
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    sync_all()
+    profiled_ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     prof = eng.profile_collect()
     eng.profile_enable(False)
-    ms_per_step = ms_total / args.steps
+    clock_info = clocks.stop() if rank == 0 else {}
     value = B / (ms_per_step / 1000.0)
     dstats = ix.dense_stats()
 
@@ -454,7 +464,8 @@ def main():
                    "query_terms": L, "k": K, "pool": fusion.pool, "parallelism": f"row-sharded x{world}",
                    "l2": "inputs larger than L2 (bf16 corpus shard read every step)",
                    "dense_path": dstats, "setup_s": setup_s},
-        "roofline": roofline, "kernels": kernels, "sparse": sparse, "cpu_baseline": cpu_base,
+        "roofline": roofline, "kernels": kernels, "profiled_ms_per_step": profiled_ms_per_step, "sparse": sparse,
+        "cpu_baseline": cpu_base,
         "clocks": {"sm_mhz": clock_info.get("sm_mhz"), "sm_max_mhz": clock_info.get("sm_max_mhz"),
                    "reasons": clock_info.get("reasons", []), "samples": clock_info.get("samples", 0)},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,

@@ -442,15 +442,14 @@ tc_select_kernel(const unsigned long long* __restrict__ cand_keys, unsigned* __r
 
     // gather into shared memory
     for (int i = tid; i < kc; i += 256) sk[i] = kept_keys[(size_t)q * KP + i];
-    for (int r = wid; r < n_sub; r += 8) {
-        const int lo = s_off[r];
-        const int n = min(s_off[r + 1], sort_cap) - lo;
-        const unsigned long long* src = cand_keys + ((size_t)q * n_sub + r) * cap_sub;
-        for (int i = lane; i < n; i += 32) {
-            const unsigned long long raw = src[i];               // {score bits, doc} as written by the epilogue
-            unsigned long long k = rr_make_key(__uint_as_float((uint32_t)raw), (uint32_t)(raw >> 32));
-            sk[lo + i] = k ? k : 1ull;
-        }
+    // flat gather: position p -> (sub-list r by binary search over the offsets, entry p - off[r]); every load
+    // is independent, so a thread keeps several in flight instead of walking the sub-lists one by one
+    for (int p = kc + tid; p < total; p += 256) {
+        int lo_r = 0, hi_r = n_sub;                 // largest r with s_off[r] <= p
+        while (hi_r - lo_r > 1) { const int mid = (lo_r + hi_r) >> 1; if (s_off[mid] <= p) lo_r = mid; else hi_r = mid; }
+        const unsigned long long raw = cand_keys[((size_t)q * n_sub + lo_r) * cap_sub + (p - s_off[lo_r])];
+        unsigned long long k = rr_make_key(__uint_as_float((uint32_t)raw), (uint32_t)(raw >> 32));   // {score bits, doc}
+        sk[p] = k ? k : 1ull;
     }
     __syncthreads();
 
@@ -604,15 +603,12 @@ tc_select_warp_kernel(const unsigned long long* __restrict__ cand_keys, unsigned
 
     // ---- gather ----------------------------------------------------------------------------------
     for (int i = lane; i < kc; i += 32) sk[i] = kept_keys[(size_t)q * KP + i];
-    for (int r = 0; r < n_sub; ++r) {
-        const int lo = s_off[r];
-        const int n = min(s_off[r + 1], cap) - lo;
-        const unsigned long long* src = cand_keys + ((size_t)q * n_sub + r) * cap_sub;
-        for (int i = lane; i < n; i += 32) {
-            const unsigned long long raw = src[i];
-            const unsigned long long k = rr_make_key(__uint_as_float((uint32_t)raw), (uint32_t)(raw >> 32));
-            sk[lo + i] = k ? k : 1ull;
-        }
+    for (int p = kc + lane; p < total; p += 32) {      // flat gather, independent loads (see tc_select_kernel)
+        int lo_r = 0, hi_r = n_sub;
+        while (hi_r - lo_r > 1) { const int mid = (lo_r + hi_r) >> 1; if (s_off[mid] <= p) lo_r = mid; else hi_r = mid; }
+        const unsigned long long raw = cand_keys[((size_t)q * n_sub + lo_r) * cap_sub + (p - s_off[lo_r])];
+        const unsigned long long k = rr_make_key(__uint_as_float((uint32_t)raw), (uint32_t)(raw >> 32));
+        sk[p] = k ? k : 1ull;
     }
     __syncwarp();
 

@@ -154,7 +154,7 @@ int rr_candidate_tuples(rr_index*, const int32_t* d_term_ids, const int32_t* d_n
  * order -- only meaningful when n_in == pool), d_best, d_gate.
  * Outputs: d_top_row int64[B, k] global rows (-1 padding), d_top_final float[B, k],
  * d_top_pos int32[B, k] pool positions; d_components float[B, pool, 8] or NULL:
- * {dense_mm, bm25_mm, prior, trust, final, dense_raw, bm25_raw, volume}. */
+ * {dense_mm, bm25_mm, prior, trust, final, dense_raw, bm25_raw, best_mm}. */
 typedef struct rr_fusion_params {
     double w_dense, w_bm25, w_rerank, w_prior, w_best;
     double prior_C;
@@ -165,6 +165,8 @@ typedef struct rr_fusion_params {
     int32_t bm25_is_f64_zero;/* 1 = CLI without BM25 (`cand["_bm25"] = 0.0`, app/test.py:252) */
     int32_t k;
     int32_t pool;
+    int32_t best_is_raw;     /* 1 = d_best holds raw best-review similarities; K4 min-max normalises them
+                                (`best_contrib = _minmax(best_contrib)`, :294); 0 = already normalised */
 } rr_fusion_params;
 
 int rr_fuse_topk(const rr_fusion_params*, int32_t B, int32_t n_in, const int32_t* d_count,
@@ -198,6 +200,46 @@ int rr_hybrid_search(rr_index*, const float* d_q, const int32_t* d_term_ids, con
 int rr_hybrid_search_host(rr_index*, const float* h_q, const int32_t* h_term_ids, const int32_t* h_n_terms,
                           int32_t B, int32_t l_max, const rr_fusion_params*, int32_t dense_mode,
                           int64_t* h_top_row, float* h_top_final, rr_stream);
+
+/* Best-review scoring: the dense contraction of _best_snippets (app/app_product_search.py:320-370) and
+ * best_review_snippets (app/test.py:181-215).  d_rev_emb float[n_slots, dim] holds the review embeddings
+ * grouped by product, file order inside a product, already L2-normalised (the reference normalises the
+ * selected rows on every call, :349).  d_rev_range int64[n_products, 2] = {first slot, end slot} of the
+ * reviews of product row r (rows with the same SKU share a range; no reviews: lo == hi).
+ * For every (query, candidate row) the maximum similarity over the product's reviews and the slot of the
+ * FIRST review attaining it (np.argmax, :356); products without reviews and invalid candidates give
+ * score 0 and slot -1 (run_search leaves best_contrib at 0 for them, :290-293).
+ * Optional `max_rows` cap (:343-346): d_slot_file int64[n_slots] = file position of every slot and
+ * d_limit int64[B] = first file position dropped for the query (INT64_MAX = no cap); both or neither.
+ * d_cand int64[B, pool] product rows; outputs are [B, pool]. */
+int rr_best_review_scores(const float* d_rev_emb, const int64_t* d_rev_range, int64_t n_products, int32_t dim,
+                          const float* d_q, int32_t B, const int64_t* d_cand, int32_t pool,
+                          const int64_t* d_slot_file, const int64_t* d_limit,
+                          float* d_best_score, int64_t* d_best_slot, int device, rr_stream);
+
+/* Attribute gates: calculate_gate_factor utils.py:88-101 (= _gate_factor app/app_product_search.py:228-236)
+ * over `agg_text[:6000]` of every pool member (app/app_product_search.py:297-302, app/test.py:291-297).
+ * Text store: d_text = UTF-8 bytes of str(agg_text)[:6000].lower() of every product row, each text starting
+ * on a 16-byte boundary (blob length a multiple of 16); d_text_off int64[n_docs] start offsets,
+ * d_text_len int32[n_docs] byte lengths.
+ * Patterns (lower-case group members): d_pat bytes, d_pat_off int32[n_pat+1]; group g owns patterns
+ * d_group_pat_off[g] .. d_group_pat_off[g+1]; query b owns groups d_query_group_off[b] ..
+ * d_query_group_off[b+1] (at most 32; the reference keeps 6, utils.py:86).
+ * d_group_fixed int32[n_groups] (optional) = bit of d_fixed_bits uint32[n_docs] that already answers the
+ * group (the fixed COLORS / SYNONYMS sets, utils.py:15-38, precomputed by rr_gate_fixed_bitmaps) or -1.
+ * Output d_gate float[B, pool] = (float32) penalty^(groups without a match), 1.0 for invalid candidates;
+ * d_hits int32[B, pool] (optional) = groups with a match. */
+int rr_gate_factors(const uint8_t* d_text, const int64_t* d_text_off, const int32_t* d_text_len, int64_t n_docs,
+                    const uint32_t* d_fixed_bits, const uint8_t* d_pat, const int32_t* d_pat_off,
+                    const int32_t* d_group_pat_off, const int32_t* d_group_fixed,
+                    const int32_t* d_query_group_off, int32_t B, const int64_t* d_cand, int32_t pool,
+                    double penalty, float* d_gate, int32_t* d_hits, int device, rr_stream);
+
+/* Per-row bitmap of up to 32 query-independent groups (bit g = some member of group g occurs in the row's
+ * text), computed once at load. */
+int rr_gate_fixed_bitmaps(const uint8_t* d_text, const int64_t* d_text_off, const int32_t* d_text_len,
+                          int64_t n_docs, const uint8_t* d_pat, const int32_t* d_pat_off,
+                          const int32_t* d_group_pat_off, int32_t n_groups, uint32_t* d_bits, int device, rr_stream);
 
 /* Counters for bench.py: number of kernels this library launched since the last reset, and
  * diagnostics of the last rr_dense_topk on this handle. */

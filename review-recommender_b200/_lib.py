@@ -37,7 +37,7 @@ class FusionParams(C.Structure):
         ("w_dense", C.c_double), ("w_bm25", C.c_double), ("w_rerank", C.c_double), ("w_prior", C.c_double),
         ("w_best", C.c_double), ("prior_C", C.c_double), ("min_reviews", C.c_int32), ("saturation", C.c_int32),
         ("use_trust", C.c_int32), ("rerank_is_f32", C.c_int32), ("bm25_is_f64_zero", C.c_int32),
-        ("k", C.c_int32), ("pool", C.c_int32),
+        ("k", C.c_int32), ("pool", C.c_int32), ("best_is_raw", C.c_int32),
     ]
 
 
@@ -75,6 +75,11 @@ SIGNATURES = {
                                        _P, _P, _P, _P, _P, C.c_int, _P]),
     "rr_profile_enable": (C.c_int, [C.c_int]),
     "rr_profile_collect": (C.c_int, [_P, _P, C.c_int32]),
+    "rr_best_review_scores": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P,
+                                        C.c_int, _P]),
+    "rr_gate_factors": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_double,
+                                  _P, _P, C.c_int, _P]),
+    "rr_gate_fixed_bitmaps": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, C.c_int32, _P, C.c_int, _P]),
     "rr_hybrid_search": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(FusionParams), C.c_int32,
                                    _P, _P, _P]),
     "rr_hybrid_search_host": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(FusionParams), C.c_int32,

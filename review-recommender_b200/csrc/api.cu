@@ -314,6 +314,47 @@ extern "C" int rr_fuse_topk_sharded(const rr_fusion_params* p, int32_t B, int32_
                           nullptr, nullptr, d_incomplete, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int rr_best_review_scores(const float* d_rev_emb, const int64_t* d_rev_range, int64_t n_products, int32_t dim,
+                                     const float* d_q, int32_t B, const int64_t* d_cand, int32_t pool,
+                                     const int64_t* d_slot_file, const int64_t* d_limit,
+                                     float* d_best_score, int64_t* d_best_slot, int device, rr_stream stream) {
+    if (!d_rev_emb || !d_rev_range || !d_q || !d_cand || !d_best_score || !d_best_slot || dim <= 0 || B < 0 || pool <= 0)
+        return rr_fail(RR_EINVAL, "rr_best_review_scores: bad argument");
+    if ((d_slot_file == nullptr) != (d_limit == nullptr))
+        return rr_fail(RR_EINVAL, "rr_best_review_scores: d_slot_file and d_limit go together");
+    RR_CUDA(cudaSetDevice(device));
+    return rr_launch_best_review(d_rev_emb, d_rev_range, n_products, dim, d_q, B, d_cand, pool, d_slot_file, d_limit,
+                                 d_best_score, d_best_slot, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rr_gate_factors(const uint8_t* d_text, const int64_t* d_text_off, const int32_t* d_text_len, int64_t n_docs,
+                               const uint32_t* d_fixed_bits, const uint8_t* d_pat, const int32_t* d_pat_off,
+                               const int32_t* d_group_pat_off, const int32_t* d_group_fixed,
+                               const int32_t* d_query_group_off, int32_t B, const int64_t* d_cand, int32_t pool,
+                               double penalty, float* d_gate, int32_t* d_hits, int device, rr_stream stream) {
+    if (!d_text || !d_text_off || !d_text_len || !d_pat_off || !d_group_pat_off || !d_query_group_off || !d_cand ||
+        !d_gate || B < 0 || pool <= 0)
+        return rr_fail(RR_EINVAL, "rr_gate_factors: bad argument");
+    if (d_fixed_bits != nullptr && d_group_fixed == nullptr)
+        return rr_fail(RR_EINVAL, "rr_gate_factors: d_fixed_bits needs d_group_fixed");
+    RR_CUDA(cudaSetDevice(device));
+    return rr_launch_gate_query(d_text, d_text_off, d_text_len, n_docs, d_fixed_bits, d_pat, d_pat_off, d_group_pat_off,
+                                d_group_fixed, d_query_group_off, B, d_cand, pool, penalty, d_gate, d_hits,
+                                static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rr_gate_fixed_bitmaps(const uint8_t* d_text, const int64_t* d_text_off, const int32_t* d_text_len,
+                                     int64_t n_docs, const uint8_t* d_pat, const int32_t* d_pat_off,
+                                     const int32_t* d_group_pat_off, int32_t n_groups, uint32_t* d_bits, int device,
+                                     rr_stream stream) {
+    if (!d_text || !d_text_off || !d_text_len || !d_pat || !d_pat_off || !d_group_pat_off || !d_bits || n_groups < 0 ||
+        n_groups > 32)
+        return rr_fail(RR_EINVAL, "rr_gate_fixed_bitmaps: bad argument (at most 32 groups)");
+    RR_CUDA(cudaSetDevice(device));
+    return rr_launch_gate_bitmaps(d_text, d_text_off, d_text_len, n_docs, d_pat, d_pat_off, d_group_pat_off, n_groups,
+                                  d_bits, static_cast<cudaStream_t>(stream));
+}
+
 // ---------------------------------------------------------------------------------------------
 // one-shot hybrid search
 // ---------------------------------------------------------------------------------------------

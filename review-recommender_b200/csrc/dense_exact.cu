@@ -166,6 +166,44 @@ rescore_kernel(const float* __restrict__ emb, long long n_rows, int D, const flo
 }
 
 // ---------------------------------------------------------------------------------------------
+// Best review per (query, candidate product): segmented arg-max of canonical dot products.
+// One warp per (query, candidate).  rev_range[r] = {lo, hi}: the review slots of product row r
+// (slots of one product are contiguous and in file order; rows that share a SKU share a range).
+// slot_file (optional) = file position of every slot and limit[q] = first file position that the
+// reference's `max_rows` cap drops for query q (app/app_product_search.py:343-346).
+// ---------------------------------------------------------------------------------------------
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+best_review_kernel(const float* __restrict__ rev, const long long* __restrict__ rev_range, long long n_products, int D,
+                   const float* __restrict__ queries, const long long* __restrict__ cand, int pool, int B,
+                   const long long* __restrict__ slot_file, const long long* __restrict__ limit,
+                   float* __restrict__ out_score, long long* __restrict__ out_slot) {
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= (long long)B * pool) return;
+    const int q = (int)(gw / pool);
+    const long long r = cand[gw];
+    float best = 0.f;
+    long long best_i = -1;
+    if (r >= 0 && r < n_products) {
+        const long long lo = rev_range[2 * r], hi = rev_range[2 * r + 1];
+        const long long lim = (slot_file != nullptr && limit != nullptr) ? limit[q] : 0x7fffffffffffffffLL;
+        for (long long i = lo; i < hi; ++i) {
+            if (slot_file != nullptr && slot_file[i] >= lim) break;       // file order inside a product
+            float s;
+            if constexpr (VEC4)
+                s = warp_xor_sum(lane_partial_v4(reinterpret_cast<const float4*>(rev + i * D),
+                                                 reinterpret_cast<const float4*>(queries + (long long)q * D), D >> 2, lane));
+            else
+                s = warp_xor_sum(lane_partial_scalar(rev + i * D, queries + (long long)q * D, D, lane));
+            // first maximum, NaN counts as the maximum: np.argmax (:356)
+            if (best_i < 0 || s > best || (s != s && best == best)) { best = s; best_i = i; }
+        }
+    }
+    if (lane == 0) { out_score[gw] = best; out_slot[gw] = best_i; }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Radix select of the top-k composite keys of every row of a score matrix.
 // ---------------------------------------------------------------------------------------------
 constexpr int RS_BINS = 2048;
@@ -341,6 +379,28 @@ int rr_launch_rescore(const float* d_emb, int64_t n_rows, int D, const float* d_
         rescore_kernel<true><<<blocks, 256, 0, stream>>>(d_emb, n_rows, D, d_q, reinterpret_cast<const long long*>(d_rows), n_slots, B, d_out);
     else
         rescore_kernel<false><<<blocks, 256, 0, stream>>>(d_emb, n_rows, D, d_q, reinterpret_cast<const long long*>(d_rows), n_slots, B, d_out);
+    RR_LAUNCH_CHECK();
+    return RR_OK;
+}
+
+int rr_launch_best_review(const float* d_rev_emb, const int64_t* d_rev_range, int64_t n_products, int D,
+                          const float* d_q, int B, const int64_t* d_cand, int pool, const int64_t* d_slot_file,
+                          const int64_t* d_limit, float* d_score, int64_t* d_slot, cudaStream_t stream) {
+    const long long warps = (long long)B * pool;
+    if (warps <= 0) return RR_OK;
+    const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rev_emb) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(d_q) & 15) == 0);
+    const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+    RrProfScope prof(RR_PROF_MISC, stream);
+    auto ll = [](const int64_t* p) { return reinterpret_cast<const long long*>(p); };
+    if (vec4)
+        best_review_kernel<true><<<blocks, 256, 0, stream>>>(d_rev_emb, ll(d_rev_range), n_products, D, d_q, ll(d_cand),
+                                                             pool, B, ll(d_slot_file), ll(d_limit), d_score,
+                                                             reinterpret_cast<long long*>(d_slot));
+    else
+        best_review_kernel<false><<<blocks, 256, 0, stream>>>(d_rev_emb, ll(d_rev_range), n_products, D, d_q, ll(d_cand),
+                                                              pool, B, ll(d_slot_file), ll(d_limit), d_score,
+                                                              reinterpret_cast<long long*>(d_slot));
     RR_LAUNCH_CHECK();
     return RR_OK;
 }

@@ -213,6 +213,22 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
         bmm_lo = lo; bmm_div = (float)(dh - dl + 1e-12);
     }
 
+    // raw best-review similarities (pool order) get the same float32 min-max (:294, app/test.py:288)
+    float emm_lo = 0.f, emm_div = 1.f;
+    bool e_zero = false;
+    const bool best_raw = a.best != nullptr && a.p.best_is_raw;
+    if (best_raw) {
+        const long long e0 = (long long)b * a.p.pool;
+        float lo = INFINITY, hi = -INFINITY; int bad = 0;
+        for (int i = tid; i < P; i += FUSE_THREADS) { const float x = a.best[e0 + i]; if (x != x) bad = 1; lo = fminf(lo, x); hi = fmaxf(hi, x); }
+        lo = block_reduce<float>(lo, [](float x, float y) { return fminf(x, y); }, red_f);
+        hi = block_reduce<float>(hi, [](float x, float y) { return fmaxf(x, y); }, red_f);
+        bad = block_reduce<int>(bad, [](int x, int y) { return x | y; }, red_i);
+        const double dl = (double)lo, dh = (double)hi;
+        e_zero = bad || isinf(lo) || isinf(hi) || (dh - dl < 1e-12) || P == 0;
+        emm_lo = lo; emm_div = (float)(dh - dl + 1e-12);
+    }
+
     // ---- 4. g = nanmean(avg) over the pool, NumPy pairwise order -----------------------------------
     if (tid == 0) { int c = 0; pw_leaves(0, P, s_leaf_lo, s_leaf_n, c); s_nleaf = c; }
     __syncthreads();
@@ -311,8 +327,10 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
         if (!is64) { acc64 = (double)acc32; is64 = true; }
         acc64 = __dadd_rn(acc64, __dmul_rn(a.p.w_prior, prior));
         // best-review term (float32 column)
+        float be;
         {
-            const float be = a.best ? a.best[ex0 + i] : 0.f;
+            be = a.best ? a.best[ex0 + i] : 0.f;
+            if (best_raw) be = e_zero ? 0.f : __fdiv_rn(__fsub_rn(be, emm_lo), emm_div);
             acc64 = __dadd_rn(acc64, (double)__fmul_rn(wbest32, be));
         }
         float fin = (float)acc64;
@@ -326,7 +344,7 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
         if (a.components) {
             float* c = a.components + ((long long)b * a.p.pool + i) * 8;
             c[0] = dm; c[1] = bm; c[2] = (float)prior; c[3] = trust; c[4] = fin;
-            c[5] = s_dense[i]; c[6] = s_bm25[i]; c[7] = (float)vol;
+            c[5] = s_dense[i]; c[6] = s_bm25[i]; c[7] = be;
         }
     }
     if (a.components) {

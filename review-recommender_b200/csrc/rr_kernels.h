@@ -27,6 +27,20 @@ int rr_launch_topk_rows(const float* d_scores, int64_t ld, int64_t n, int rows, 
                         int64_t* d_idx, float* d_score, int32_t* d_count, int out_ld, int sm_count,
                         cudaStream_t stream);
 
+int rr_launch_best_review(const float* d_rev_emb, const int64_t* d_rev_range, int64_t n_products, int D,
+                          const float* d_q, int B, const int64_t* d_cand, int pool, const int64_t* d_slot_file,
+                          const int64_t* d_limit, float* d_score, int64_t* d_slot, cudaStream_t stream);
+
+// gate.cu
+int rr_launch_gate_query(const uint8_t* d_text, const int64_t* d_text_off, const int32_t* d_text_len, int64_t n_docs,
+                         const uint32_t* d_fixed_bits, const uint8_t* d_pat, const int32_t* d_pat_off,
+                         const int32_t* d_group_pat_off, const int32_t* d_group_fixed, const int32_t* d_query_group_off,
+                         int B, const int64_t* d_cand, int pool, double penalty, float* d_gate, int32_t* d_hits,
+                         cudaStream_t stream);
+int rr_launch_gate_bitmaps(const uint8_t* d_text, const int64_t* d_text_off, const int32_t* d_text_len, int64_t n_docs,
+                           const uint8_t* d_pat, const int32_t* d_pat_off, const int32_t* d_group_pat_off, int n_groups,
+                           uint32_t* d_bits, cudaStream_t stream);
+
 // fuse.cu
 int rr_launch_fuse(const rr_fusion_params* p, int B, int n_in, int n_shards, int64_t shard_stride_bytes,
                    const int32_t* d_count, const float* d_dense,

@@ -15,6 +15,8 @@ the reference caches its own loads (st.cache_resource / st.cache_data).
     run_search(query, k, rerank_k, w_*, prior_C, use_snips,
                max_scan, min_reviews, gate_penalty)       :245       SearchEngine.run_search
     search(args)                                app/test.py:228      SearchEngine.search
+    _best_snippets(qvec, cand_skus, max_rows)             :320       SearchEngine._best_snippets
+    best_review_snippets(qvec, cand_skus, max_rows)  app/test.py:181 SearchEngine.best_review_snippets
 
 There is no CPU fallback: without the CUDA library or a GPU these raise RRError.
 """
@@ -37,6 +39,41 @@ STOP_WORDS = {"a", "an", "the", "and", "or", "of", "for", "to", "in", "on", "wit
 def tokenize_query(query: str) -> List[str]:
     """utils.py:57-60."""
     return [t for t in TOKEN_RE.findall(query.lower()) if t not in STOP_WORDS]
+
+
+# Gate vocabularies: the data tables of utils.py:15-38 (= SYN / COLORS in app/app_product_search.py and
+# app/test.py).  Keys are what a query token must equal (synonym sets) / any member must occur in the
+# query (colour sets); insertion order matters because the first 6 distinct groups are kept.
+GATE_COLORS: Dict[str, frozenset] = {name: frozenset(words.split("|")) for name, words in (
+    ("yellow", "yellow|mustard|lemon|gold|golden"), ("red", "red|scarlet|crimson|maroon"),
+    ("blue", "blue|navy|cobalt|azure"), ("green", "green|emerald|olive"), ("black", "black"),
+    ("white", "white|ivory"), ("pink", "pink|rose"), ("purple", "purple|violet|lavender"),
+    ("orange", "orange|amber"), ("brown", "brown|tan|beige|khaki"), ("gray", "gray|grey|charcoal|slate"))}
+GATE_SYNONYMS: Dict[str, frozenset] = {name: frozenset(words.split("|")) for name, words in (
+    ("sock", "sock|socks"), ("headphone", "headphone|headphones|earphone|earphones|earbud|earbuds|headset"),
+    ("keyboard", "keyboard|keyboards"), ("wireless", "wireless|bluetooth"),
+    ("noise", "noise cancelling|noise-canceling|noise canceling|anc"), ("cat", "cat|cats|kitten|kittens|kitty"),
+    ("dog", "dog|dogs|puppy|puppies"), ("design", "design|pattern|print|graphic|artwork|motif|theme"))}
+GATE_FIXED_GROUPS: List[frozenset] = list(GATE_COLORS.values()) + list(GATE_SYNONYMS.values())
+GATE_MAX_GROUPS = 6
+
+
+def build_gate_groups(query: str) -> List[frozenset]:
+    """utils.py:62-86 (= _build_gate_groups app/app_product_search.py:211-226, app/test.py:62-78): colour sets
+    with a member occurring in the lower-cased query (substring test), then per query token its synonym
+    set or, for other tokens of >= 4 characters, the token itself; duplicates dropped, first 6 kept."""
+    lowered = query.lower()
+    picked: List[frozenset] = [words for words in GATE_COLORS.values() if any(w in lowered for w in words)]
+    for tok in tokenize_query(query):
+        if tok in GATE_SYNONYMS:
+            picked.append(GATE_SYNONYMS[tok])
+        elif len(tok) >= 4:
+            picked.append(frozenset((tok,)))
+    distinct: List[frozenset] = []
+    for g in picked:
+        if g not in distinct:
+            distinct.append(g)
+    return distinct[:GATE_MAX_GROUPS]
 
 
 # --------------------------------------------------------------------------------------------
@@ -186,10 +223,23 @@ class SearchEngine:
 
     def __init__(self, meta, Vn: np.ndarray, bm25_corpus: Optional[Sequence[Sequence[str]]] = None,
                  bm25_skus: Optional[Sequence[str]] = None, encode: Optional[Callable] = None,
-                 rerank: Optional[Callable] = None, gate: Optional[Callable] = None, device: str = "cuda:0"):
+                 rerank: Optional[Callable] = None, gate: Optional[Callable] = None, device: str = "cuda:0",
+                 reviews=None):
+        """`reviews`: the reviews_with_embeddings.parquet frame (columns sku, text, stars, embedding) or
+        None when the file does not exist (snippets are then skipped, like `REV_EMB.exists()` :285)."""
         import pandas as pd
         self.meta = meta.reset_index(drop=True)
         self.encode, self.rerank, self.gate = encode, rerank, gate
+        self.reviews = None
+        self.review_ix = None
+        self.gate_ix = None
+        if gate is None and "agg_text" in self.meta.columns:
+            self.gate_ix = engine.GateIndex(self.meta["agg_text"].astype(str).tolist(), GATE_FIXED_GROUPS, device=device)
+        if reviews is not None and "sku" in reviews.columns and len(reviews):
+            self.reviews = reviews.reset_index(drop=True)
+            E = np.stack(self.reviews["embedding"].values).astype(np.float32)
+            self.review_ix = engine.ReviewIndex(E, self.reviews["sku"].astype(str).tolist(),
+                                                self.meta["sku"].astype(str).tolist(), device=device)
         n = len(self.meta)
         if n != Vn.shape[0]:
             raise SystemExit(f"[ERR] length mismatch: meta={n} vs emb_rows={Vn.shape[0]}")     # app/test.py:142
@@ -233,7 +283,52 @@ class SearchEngine:
         ids = [self.vocab.get(t, -1) for t in toks]
         return toks, engine.HybridIndex.pack_terms([ids])
 
-    def _search(self, query: str, fusion: "engine.Fusion", gate_penalty: float):
+    # ---- best-review snippets ---------------------------------------------------------------------
+    def _snippets_for_rows(self, qvec: np.ndarray, rows: np.ndarray, max_rows: int, text_cap: int):
+        """(raw best similarity float32[len(rows)], {sku: {"score", "text", "stars"}}) for product rows."""
+        score, file_pos = self.review_ix.best(qvec[None, :], rows[None, :].astype(np.int64), max_rows=max_rows)
+        score, file_pos = score[0], file_pos[0]
+        snips: Dict[str, Dict] = {}
+        skus = self.meta["sku"].astype(str).values
+        has_stars = "stars" in self.reviews.columns
+        for i, r in enumerate(rows):
+            f = int(file_pos[i])
+            if f < 0:
+                continue
+            rev = self.reviews.iloc[f]
+            snips[str(skus[r])] = {"score": float(score[i]), "text": str(rev["text"])[:text_cap],
+                                   "stars": float(rev["stars"]) if has_stars else float("nan")}
+        return score, snips
+
+    def _rows_of_skus(self, cand_skus: Sequence[str]) -> np.ndarray:
+        lut = getattr(self, "_sku_row", None)
+        if lut is None:
+            lut = {}
+            for r, s in enumerate(self.meta["sku"].astype(str).tolist()):
+                lut.setdefault(s, r)
+            self._sku_row = lut
+        return np.asarray([lut.get(str(s), -1) for s in cand_skus], dtype=np.int64)
+
+    def _best_snippets(self, qvec: np.ndarray, cand_skus: List[str], max_rows: int = 300_000) -> Dict[str, Dict]:
+        """app/app_product_search.py:320-370 (any failure -> {}, like its try/except)."""
+        if self.review_ix is None:
+            return {}
+        if max_rows <= 0:
+            return {}            # the reference's np.stack of zero rows raises and is swallowed (:348, :366)
+        rows = self._rows_of_skus(cand_skus)
+        return self._snippets_for_rows(np.asarray(qvec, dtype=np.float32), rows, max_rows, 600)[1]
+
+    def best_review_snippets(self, qvec: np.ndarray, cand_skus: List[str], max_rows: int = 1_000_000) -> Dict[str, Dict]:
+        """app/test.py:181-215."""
+        if self.review_ix is None:
+            return {}
+        rows = self._rows_of_skus(cand_skus)
+        if max_rows <= 0 and self.review_ix.cap_limits(rows[None, :], 0) is not None:
+            raise ValueError("need at least one array to stack")       # np.stack([]) at app/test.py:206
+        return self._snippets_for_rows(np.asarray(qvec, dtype=np.float32), rows, max_rows, 400)[1]
+
+    def _search(self, query: str, fusion: "engine.Fusion", gate_penalty: float, use_snips: bool = False,
+                max_scan: int = 300_000):
         import torch
         qvec = np.asarray(self.encode(query), dtype=np.float32)
         toks, (tid, nt) = self._terms(query)
@@ -257,13 +352,29 @@ class SearchEngine:
                 if np.isfinite(lo) and np.isfinite(hi) and hi - lo >= 1e-12:
                     z[:rr_k] = ((rr - lo) / (hi - lo + 1e-12)).astype(np.float32)      # _minmax, :182-187
             rerank = z[None, :]
-        if self.gate is not None and "agg_text" in frame:
+        if self.gate_ix is not None:
+            # calculate_gate_factor over agg_text[:6000] of the pool on the GPU (:297-302, app/test.py:291-297)
+            gate = self.gate_ix.factors([build_gate_groups(query)], cand, gate_penalty)
+        elif self.gate is not None and "agg_text" in frame:
             g = np.ones(pool, dtype=np.float32)
             texts = frame["agg_text"].astype(str).str.slice(0, 6000).tolist()
             g[:P] = np.array([self.gate(t, query, gate_penalty) for t in texts], dtype=np.float32)
             gate = g[None, :]
+        snips: Dict[str, Dict] = {}
+        best = None
+        if use_snips and self.review_ix is not None:
+            text_cap = 600 if fusion.driver == "streamlit" else 400
+            if max_scan <= 0 and fusion.driver != "streamlit":
+                self.best_review_snippets(qvec, frame["sku"].astype(str).tolist(), max_scan)    # raises like the CLI
+            if max_scan > 0:
+                raw, snips = self._snippets_for_rows(qvec, rows, max_scan, text_cap)
+                if snips:
+                    b_ = np.zeros(pool, dtype=np.float32)
+                    b_[:P] = raw
+                    best = b_[None, :]
+                    fusion.best_is_raw = True
         top_rows, final, pos, comp = self.ix.fuse(fusion, dense, bm25, n, avg, grow, count=cnt, rerank=rerank,
-                                                  gate=gate, want_components=True)
+                                                  best=best, gate=gate, want_components=True)
         pos = pos[0].cpu().numpy()
         pos = pos[pos >= 0]
         comp = comp[0].cpu().numpy()
@@ -271,9 +382,13 @@ class SearchEngine:
         out["_dense"], out["_bm25"], out["_prior"] = comp[pos, 0], comp[pos, 1], comp[pos, 2]
         out["_trust"], out["_final"] = comp[pos, 3], comp[pos, 4]
         out["_rerank"] = rerank[0][pos] if rerank is not None else 0.0
-        out["_best"] = np.zeros(len(pos), dtype=np.float32)
-        out["_gate"] = gate[0][pos] if gate is not None else np.ones(len(pos), dtype=np.float32)
-        return out, toks
+        out["_best"] = comp[pos, 7]
+        if gate is not None:
+            g0 = gate[0].cpu().numpy() if hasattr(gate, "cpu") else gate[0]
+            out["_gate"] = g0[pos]
+        else:
+            out["_gate"] = np.ones(len(pos), dtype=np.float32)
+        return out, toks, snips
 
     def run_search(self, query: str, k: int, rerank_k: int, w_dense: float, w_bm25: float, w_rerank: float,
                    w_prior: float, w_best: float, prior_C: float, use_snips: bool, max_scan: int,
@@ -283,13 +398,18 @@ class SearchEngine:
         fusion = engine.Fusion(k=k, rerank_k=rerank_k, w_dense=w_dense, w_bm25=w_bm25, w_rerank=w_rerank,
                                w_prior=w_prior, w_best=w_best, prior_C=prior_C, min_reviews=min_reviews,
                                driver="streamlit", bm25_absent=not self.bm25_active)
-        out, toks = self._search(query, fusion, gate_penalty)
-        return out, {}, {"bm25_active": self.bm25_active, "tokens": toks, "groups": [], "pool": fusion.pool}
+        out, toks, snips = self._search(query, fusion, gate_penalty, use_snips=use_snips, max_scan=max_scan)
+        return out, snips, {"bm25_active": self.bm25_active, "tokens": toks,
+                             "groups": [list(g) for g in build_gate_groups(query)], "pool": fusion.pool}
 
     def search(self, args):
         """The numeric core of search(args) (app/test.py:228-309); returns the top-k DataFrame."""
         fusion = engine.Fusion(k=args.k, rerank_k=args.rerank_k, w_dense=args.w_dense, w_bm25=args.w_bm25,
                                w_rerank=args.w_rerank, w_prior=args.w_prior, w_best=args.w_best,
                                prior_C=args.prior_C, driver="cli", bm25_absent=not self.bm25_active)
-        out, _ = self._search(args.query, fusion, getattr(args, "gate_penalty", 0.5))
+        out, _, snips = self._search(args.query, fusion, getattr(args, "gate_penalty", 0.5),
+                                     use_snips=not getattr(args, "no_snippets", True),
+                                     max_scan=getattr(args, "max_reviews_scan", 1_000_000))
+        out = out.rename(columns={"_best": "_bestrev"})
+        self.last_snippets = snips
         return out

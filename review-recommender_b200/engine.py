@@ -149,6 +149,7 @@ class Fusion:
     saturation: int = 80
     driver: str = "streamlit"
     bm25_absent: bool = False
+    best_is_raw: bool = False       # `best` handed to fuse() holds raw similarities, K4 min-max normalises them
 
     @property
     def pool(self) -> int:
@@ -159,7 +160,7 @@ class Fusion:
                             int(self.min_reviews), int(self.saturation), 1 if self.driver == "streamlit" else 0,
                             1 if self.rerank_k > 0 else 0,
                             1 if (self.bm25_absent and self.driver != "streamlit") else 0,
-                            int(self.k), int(self.pool))
+                            int(self.k), int(self.pool), 1 if self.best_is_raw else 0)
 
 
 # --------------------------------------------------------------------------------------------
@@ -399,6 +400,174 @@ class HybridIndex:
         check(self.lib.rr_hybrid_search_host(self._h, _ptr(q), _ptr(term_ids), _ptr(n_terms), B, lmax, C.byref(p),
                                              mode, _ptr(rows), _ptr(final), _stream()))
         return rows, final
+
+
+class ReviewIndex:
+    """Review embeddings grouped by product, resident in HBM, for best-review scoring (_best_snippets
+    app/app_product_search.py:320-370, best_review_snippets app/test.py:181-215).
+
+    `rev_emb` float32[M, D] and `rev_skus` (M strings) are the `embedding` / `sku` columns of
+    reviews_with_embeddings.parquet in file order; `product_skus` are the `sku` column of
+    product_emb_meta in row order.  Reviews are regrouped so that the reviews of one SKU are contiguous
+    slots in file order (the order `groupby("sku")` + `argmax` sees, :355-356); rows are L2-normalised
+    here once (the reference does it per call on the selected subset, :349) in float32 like _l2norm."""
+
+    def __init__(self, rev_emb: np.ndarray, rev_skus: Sequence[str], product_skus: Sequence[str],
+                 device: str | torch.device = "cuda:0"):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RRError("ReviewIndex needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device)
+        rev_emb = np.asarray(rev_emb, dtype=np.float32)
+        if rev_emb.ndim != 2 or rev_emb.shape[0] != len(rev_skus):
+            raise RRError("rev_emb must be [M, D] with one row per review")
+        group_of_sku: Dict[str, int] = {}
+        row_group = np.empty(len(product_skus), dtype=np.int64)
+        for r, sku in enumerate(product_skus):
+            row_group[r] = group_of_sku.setdefault(str(sku), len(group_of_sku))
+        n_groups = len(group_of_sku)
+        rev_group = np.fromiter((group_of_sku.get(str(x), -1) for x in rev_skus), dtype=np.int64, count=len(rev_skus))
+        keep = np.nonzero(rev_group >= 0)[0]
+        order = keep[np.argsort(rev_group[keep], kind="stable")]          # file order inside a SKU
+        counts = np.bincount(rev_group[order], minlength=n_groups).astype(np.int64)
+        off = np.zeros(n_groups + 1, dtype=np.int64)
+        np.cumsum(counts, out=off[1:])
+        self.slot_file = np.ascontiguousarray(order, dtype=np.int64)      # slot -> file position
+        self.group_count = counts
+        self.group_off = off
+        self.row_group = row_group
+        rng = np.stack([off[row_group], off[row_group + 1]], axis=1) if len(row_group) else np.zeros((0, 2), np.int64)
+        e = rev_emb[order]
+        nrm = np.maximum(np.linalg.norm(e, axis=1, keepdims=True), 1e-12)  # _l2norm, :179-180 (float32 throughout)
+        e = np.ascontiguousarray(e / nrm, dtype=np.float32)
+        self.n_products, self.dim, self.n_slots = len(row_group), int(rev_emb.shape[1]), int(len(order))
+        self.emb = (torch.from_numpy(e) if self.n_slots else torch.zeros((1, max(self.dim, 1)))).to(self.device)
+        self.range = torch.from_numpy(np.ascontiguousarray(rng)).to(self.device)
+        self.slot_file_dev = torch.from_numpy(self.slot_file if self.n_slots else np.zeros(1, np.int64)).to(self.device)
+
+    def cap_limits(self, cand: np.ndarray, max_rows: Optional[int]) -> Optional[np.ndarray]:
+        """int64[B]: first file position the `max_rows` cap drops (`sub_meta.iloc[:max_rows]`, :343-346), or
+        None when no query selects more than max_rows reviews.  The selection is `sku.isin(set(cand_skus))`."""
+        if max_rows is None:
+            return None
+        lim = np.full(cand.shape[0], INT64_MAX, dtype=np.int64)
+        hit = False
+        for b in range(cand.shape[0]):
+            rows = cand[b][(cand[b] >= 0) & (cand[b] < self.n_products)]
+            groups = np.unique(self.row_group[rows])
+            total = int(self.group_count[groups].sum())
+            if total > max_rows:
+                hit = True
+                files = np.concatenate([self.slot_file[self.group_off[g]:self.group_off[g + 1]] for g in groups])
+                lim[b] = np.sort(files)[max_rows] if max_rows > 0 else -1
+        return lim if hit else None
+
+    def best(self, q, cand, max_rows: Optional[int] = None, as_numpy: bool = True):
+        """(best similarity float32[B, pool], file position of that review int64[B, pool]; 0 / -1 when the
+        product has no review).  `cand` int64[B, pool] product rows."""
+        q = q if isinstance(q, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32))
+        q = q.to(self.device, dtype=torch.float32).contiguous()
+        if q.dim() == 1:
+            q = q[None, :]
+        if int(q.shape[1]) != self.dim:
+            raise RRError(f"query dim {int(q.shape[1])} != review embedding dim {self.dim}")
+        cand_t = cand if isinstance(cand, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cand, dtype=np.int64))
+        cand_t = cand_t.to(self.device, dtype=torch.int64).contiguous()
+        B, pool = int(cand_t.shape[0]), int(cand_t.shape[1])
+        limit = self.cap_limits(cand_t.cpu().numpy(), max_rows) if max_rows is not None else None
+        limit_t = torch.from_numpy(limit).to(self.device) if limit is not None else None
+        score = torch.empty((B, pool), dtype=torch.float32, device=self.device)
+        slot = torch.empty((B, pool), dtype=torch.int64, device=self.device)
+        check(self.lib.rr_best_review_scores(_ptr(self.emb), _ptr(self.range), self.n_products, self.dim, _ptr(q), B,
+                                             _ptr(cand_t), pool,
+                                             _ptr(self.slot_file_dev) if limit_t is not None else _ptr(None),
+                                             _ptr(limit_t), _ptr(score), _ptr(slot), self.device.index or 0, _stream()))
+        file_pos = torch.where(slot >= 0, self.slot_file_dev[slot.clamp_min(0)], slot) if self.n_slots else slot
+        if as_numpy:
+            return score.cpu().numpy(), file_pos.cpu().numpy()
+        return score, file_pos
+
+
+class GateIndex:
+    """Product text resident in HBM for the attribute gates (calculate_gate_factor utils.py:88-101 over
+    `agg_text[:6000]`, app/app_product_search.py:297-302).  `texts` is the agg_text column in row order
+    (anything; `str()` is applied like `.astype(str)`).  `fixed_groups` are query-independent groups (the
+    COLORS / SYNONYMS sets) whose per-row answers are precomputed into a bitmap at load."""
+
+    def __init__(self, texts: Sequence, fixed_groups: Sequence[Sequence[str]] = (), device: str | torch.device = "cuda:0",
+                 max_chars: int = 6000):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RRError("GateIndex needs a CUDA device (no CPU fallback)")
+        if len(fixed_groups) > 32:
+            raise RRError("at most 32 fixed gate groups")
+        self.device = torch.device(device)
+        enc = [str(t)[:max_chars].lower().encode("utf-8") for t in texts]
+        n = len(enc)
+        lens = np.fromiter((len(b) for b in enc), dtype=np.int64, count=n)
+        if n and int(lens.max()) > np.iinfo(np.int32).max:
+            raise RRError("text too long")
+        padded = (lens + 15) // 16 * 16
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(padded, out=off[1:])
+        blob = np.zeros(int(off[-1]) + 16, dtype=np.uint8)
+        for i, b in enumerate(enc):
+            if b:
+                blob[off[i]:off[i] + len(b)] = np.frombuffer(b, dtype=np.uint8)
+        self.n_docs = n
+        self.text = torch.from_numpy(blob).to(self.device)
+        self.text_off = torch.from_numpy(off[:-1].copy() if n else np.zeros(1, np.int64)).to(self.device)
+        self.text_len = torch.from_numpy(lens.astype(np.int32) if n else np.zeros(1, np.int32)).to(self.device)
+        self.fixed_groups = [frozenset(g) for g in fixed_groups]
+        self.fixed_bits = None
+        if self.fixed_groups and n:
+            pat, pat_off, gp_off, _ = self._encode([[g for g in self.fixed_groups]])
+            bits = torch.zeros(n, dtype=torch.int32, device=self.device)
+            check(self.lib.rr_gate_fixed_bitmaps(_ptr(self.text), _ptr(self.text_off), _ptr(self.text_len), n,
+                                                 _ptr(pat), _ptr(pat_off), _ptr(gp_off), len(self.fixed_groups),
+                                                 _ptr(bits), self.device.index or 0, _stream()))
+            self.fixed_bits = bits
+
+    def _encode(self, groups_per_query: Sequence[Sequence[Sequence[str]]]):
+        """-> device tensors (pattern bytes, pat_off, group_pat_off, query_group_off) + host group_fixed list."""
+        pat = bytearray()
+        pat_off, gp_off, qg_off, fixed = [0], [0], [0], []
+        lut = {g: i for i, g in enumerate(self.fixed_groups)}
+        for groups in groups_per_query:
+            for g in groups:
+                fixed.append(lut.get(frozenset(g), -1))
+                for syn in sorted(g):
+                    pat += str(syn).lower().encode("utf-8")
+                    pat_off.append(len(pat))
+                gp_off.append(len(pat_off) - 1)
+            qg_off.append(len(gp_off) - 1)
+        pat_arr = np.frombuffer(bytes(pat) + b"\0" * 16, dtype=np.uint8).copy()
+
+        def dev(a, dt):
+            return torch.from_numpy(np.asarray(a, dtype=dt)).to(self.device)
+        self._qg_off = dev(qg_off, np.int32)
+        return dev(pat_arr, np.uint8), dev(pat_off, np.int32), dev(gp_off, np.int32), fixed
+
+    def factors(self, groups_per_query: Sequence[Sequence[Sequence[str]]], cand, penalty: float,
+                want_hits: bool = False, use_bitmaps: bool = True):
+        """gate float32[B, pool] (device) for candidate product rows int64[B, pool]."""
+        cand = cand if isinstance(cand, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cand, dtype=np.int64))
+        cand = cand.to(self.device, dtype=torch.int64).contiguous()
+        B, pool = int(cand.shape[0]), int(cand.shape[1])
+        if len(groups_per_query) != B:
+            raise RRError("one group list per query")
+        if any(len(g) > 32 for g in groups_per_query):
+            raise RRError("at most 32 gate groups per query")
+        pat, pat_off, gp_off, fixed = self._encode(groups_per_query)
+        gate = torch.empty((B, pool), dtype=torch.float32, device=self.device)
+        hits = torch.empty((B, pool), dtype=torch.int32, device=self.device) if want_hits else None
+        bits = self.fixed_bits if use_bitmaps else None
+        gfix = torch.from_numpy(np.asarray(fixed if fixed else [-1], dtype=np.int32)).to(self.device) if bits is not None else None
+        check(self.lib.rr_gate_factors(_ptr(self.text), _ptr(self.text_off), _ptr(self.text_len), self.n_docs,
+                                       _ptr(bits), _ptr(pat), _ptr(pat_off), _ptr(gp_off), _ptr(gfix),
+                                       _ptr(self._qg_off), B, _ptr(cand), pool, float(penalty), _ptr(gate), _ptr(hits),
+                                       self.device.index or 0, _stream()))
+        return (gate, hits) if want_hits else gate
 
 
 def profile_enable(on: bool) -> None:

@@ -182,12 +182,23 @@ int rr_fuse_topk(const rr_fusion_params*, int32_t B, int32_t n_in, const int32_t
  * per_shard may be SMALLER than pool (each shard sends only its local top-m): d_incomplete[b]
  * (optional) is then set to 1 when some shard sent all m of its tuples and its weakest one still
  * reaches the merged pool's cut-off, i.e. that shard may hold further pool members and the query has
- * to be repeated with per_shard = pool; 0 means the merged pool is provably the exact global pool. */
+ * to be repeated with per_shard = pool; 0 means the merged pool is provably the exact global pool.
+ * A shard block whose first global row is -2 (rr_shard_tuples: dense result not certified) also sets it. */
 int rr_fuse_topk_sharded(const rr_fusion_params*, int32_t B, int32_t n_shards, int32_t per_shard,
                          int64_t shard_stride_bytes,
                          const float* d_dense, const float* d_bm25, const double* d_n_reviews,
                          const double* d_avg_stars, const int64_t* d_global_row,
                          int64_t* d_top_row, float* d_top_final, int32_t* d_incomplete, int device, rr_stream);
+
+/* Row-shard half of a distributed search with NO host synchronisation: the shard's exact top-m by dense
+ * similarity for all B queries and the candidate tuples, written straight into the all-to-all send buffer.
+ * d_send: n_ranks blocks of (B/n_ranks)*m*32 bytes; block g holds, for the queries g*B/n_ranks .. owned by rank
+ * g, the five fields back to back: global row int64 | n_reviews f64 | avg_stars f64 | dense f32 | bm25 f32, each
+ * [B/n_ranks, m].  A query whose dense result could not be certified by the tensor path (rr_dense_topk would
+ * redo it exactly, which needs a read-back) gets global row -2 in all its m tuples: rr_fuse_topk_sharded then
+ * reports it in d_incomplete and the caller repeats it through the synchronous entry points. */
+int rr_shard_tuples(rr_index*, const float* d_q, const int32_t* d_term_ids, const int32_t* d_n_terms,
+                    int32_t B, int32_t l_max, int32_t m, int32_t dense_mode, int32_t n_ranks, void* d_send, rr_stream);
 
 /* One-shot single-shard search (rerank/best/gate absent): dense top-pool -> tuples -> fuse. */
 int rr_hybrid_search(rr_index*, const float* d_q, const int32_t* d_term_ids, const int32_t* d_n_terms,

@@ -80,6 +80,7 @@ SIGNATURES = {
     "rr_gate_factors": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_double,
                                   _P, _P, C.c_int, _P]),
     "rr_gate_fixed_bitmaps": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, C.c_int32, _P, C.c_int, _P]),
+    "rr_shard_tuples": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "rr_hybrid_search": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(FusionParams), C.c_int32,
                                    _P, _P, _P]),
     "rr_hybrid_search_host": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(FusionParams), C.c_int32,

@@ -254,7 +254,8 @@ static int dense_exact_locked(rr_index* ix, const float* d_q, int32_t B, int32_t
 }
 
 static int dense_topk_locked(rr_index* ix, const float* d_q, int32_t B, int32_t pool, int32_t mode,
-                             int64_t* d_idx, float* d_sims, int32_t* d_count, cudaStream_t s) {
+                             int64_t* d_idx, float* d_sims, int32_t* d_count, cudaStream_t s,
+                             int32_t* d_uncertified = nullptr) {
     if (mode == RR_DENSE_AUTO) {
         const bool tc_ok = rr_tc_supported(ix->cc_major, ix->cc_minor) && ix->d.d_emb_bf16 != nullptr &&
                            rr_tc_can_handle(ix->d.dim_pad, pool);
@@ -269,11 +270,12 @@ static int dense_topk_locked(rr_index* ix, const float* d_q, int32_t B, int32_t 
                                    cudaStream_t st) {
                                     return dense_exact_locked(static_cast<rr_index*>(ctx), q, b, p, idx, sims, cnt, st);
                                 },
-                                ix, s);
+                                ix, d_uncertified, s);
     }
     if (mode != RR_DENSE_EXACT) return rr_fail(RR_EINVAL, "rr_dense_topk: unknown mode %d", mode);
     ix->stats = rr_dense_stats{};
     ix->stats.path = 1;
+    if (d_uncertified) RR_CUDA(cudaMemsetAsync(d_uncertified, 0, sizeof(int32_t) * (size_t)B, s));   // exact path: all proven
     return dense_exact_locked(ix, d_q, B, pool, d_idx, d_sims, d_count, s);
 }
 
@@ -312,6 +314,37 @@ extern "C" int rr_fuse_topk_sharded(const rr_fusion_params* p, int32_t B, int32_
     return rr_launch_fuse(p, B, n_shards * per_shard, n_shards, shard_stride_bytes, nullptr, d_dense, d_bm25,
                           d_n_reviews, d_avg_stars, d_global_row, nullptr, nullptr, nullptr, d_top_row, d_top_final,
                           nullptr, nullptr, d_incomplete, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rr_shard_tuples(rr_index* ix, const float* d_q, const int32_t* d_term_ids, const int32_t* d_n_terms,
+                               int32_t B, int32_t l_max, int32_t m, int32_t dense_mode, int32_t n_ranks, void* d_send,
+                               rr_stream stream) {
+    if (!ix || !d_q || !d_send || B <= 0 || m <= 0 || n_ranks <= 0 || B % n_ranks)
+        return rr_fail(RR_EINVAL, "rr_shard_tuples: bad argument (B must be a multiple of n_ranks)");
+    if (m > 8192) return rr_fail(RR_EINVAL, "rr_shard_tuples: m larger than 8192 is not supported");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    RR_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t bm = (size_t)B * m;
+    RR_TRY(ix->tuples.ensure(align_up(bm * 8, 256) + align_up(bm * 4, 256) + 2 * align_up((size_t)B * 4, 256)));
+    Carver c{static_cast<char*>(ix->tuples.p)};
+    int64_t* idx = c.take<int64_t>(bm);
+    float* sims = c.take<float>(bm);
+    int32_t* cnt = c.take<int32_t>(B);
+    int32_t* uncert = c.take<int32_t>(B);
+    RR_TRY(dense_topk_locked(ix, d_q, B, m, dense_mode, idx, sims, cnt, s, uncert));
+    // packed exchange layout: per destination rank [rows i64 | n f64 | avg f64 | dense f32 | bm25 f32] x (B/n_ranks * m)
+    const int bg = B / n_ranks;
+    const size_t bp = (size_t)bg * m;
+    char* base = static_cast<char*>(d_send);
+    const bool have = ix->d.vocab_size > 0 && l_max > 0 && d_term_ids && d_n_terms;
+    return rr_launch_bm25_candidates(ix->d.d_postings, ix->d.d_tile_base, ix->d.d_blk_off, ix->d.d_fwd_off, ix->d.d_fwd_data,
+                                     have ? ix->d.vocab_size : 0, std::max(ix->d.tile_docs, 1), ix->d.n_docs,
+                                     have ? d_term_ids : nullptr, d_n_terms, B, l_max, idx, m, ix->d.d_n_reviews,
+                                     ix->d.d_avg_stars, ix->d.row_offset, reinterpret_cast<float*>(base + bp * 28),
+                                     reinterpret_cast<double*>(base + bp * 8), reinterpret_cast<double*>(base + bp * 16),
+                                     reinterpret_cast<int64_t*>(base), s, bg, (int64_t)(bp * 32), sims,
+                                     reinterpret_cast<float*>(base + bp * 24), uncert);
 }
 
 extern "C" int rr_best_review_scores(const float* d_rev_emb, const int64_t* d_rev_range, int64_t n_products, int32_t dim,

@@ -22,6 +22,8 @@
 //      candidate's doc id inside each term segment of the doc's tile; same impacts, same
 //      order => bit-identical to the tile kernel at those docs.  Also gathers n_reviews /
 //      avg_stars / global row so that the fusion kernel gets complete tuples.
+#include <type_traits>
+
 #include "rr_internal.h"
 
 namespace {
@@ -161,10 +163,25 @@ bm25_candidates_kernel(const uint2* __restrict__ postings, const uint64_t* __res
                        const long long* __restrict__ cand, int pool, int B,
                        const double* __restrict__ n_reviews, const double* __restrict__ avg_stars, long long row_offset,
                        float* __restrict__ bm25_out, double* __restrict__ n_out, double* __restrict__ avg_out,
-                       long long* __restrict__ grow_out) {
+                       long long* __restrict__ grow_out, int pack_bg, long long pack_stride,
+                       const float* __restrict__ dense_in, float* __restrict__ dense_out,
+                       const int* __restrict__ uncertified) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)B * pool) return;
     const int q = (int)(gid / pool);
+    // exchange layout (pack_bg > 0): the outputs are the field bases of destination rank 0's block; query q goes
+    // to rank q / pack_bg, whose block of every field starts pack_stride bytes after the previous rank's
+    long long oid = gid;
+    long long shift = 0;
+    if (pack_bg > 0) {
+        const int g = q / pack_bg;
+        oid = (long long)(q - g * pack_bg) * pool + (gid - (long long)q * pool);
+        shift = (long long)g * pack_stride;
+    }
+    auto at = [shift](auto* base, long long i) {
+        using T = std::remove_pointer_t<decltype(base)>;
+        return reinterpret_cast<T*>(reinterpret_cast<char*>(base) + shift) + i;
+    };
     const long long doc = cand[gid];
     const bool valid = doc >= 0 && doc < n_docs;
     float sum = 0.f;
@@ -209,10 +226,13 @@ bm25_candidates_kernel(const uint2* __restrict__ postings, const uint64_t* __res
             }
         }
     }
-    if (bm25_out) bm25_out[gid] = sum;
-    if (n_out) n_out[gid] = (valid && n_reviews) ? n_reviews[doc] : 0.0;
-    if (avg_out) avg_out[gid] = (valid && avg_stars) ? avg_stars[doc] : __longlong_as_double(0x7FF8000000000000ll);
-    if (grow_out) grow_out[gid] = valid ? row_offset + doc : -1;
+    if (bm25_out) *at(bm25_out, oid) = sum;
+    if (n_out) *at(n_out, oid) = (valid && n_reviews) ? n_reviews[doc] : 0.0;
+    if (avg_out) *at(avg_out, oid) = (valid && avg_stars) ? avg_stars[doc] : __longlong_as_double(0x7FF8000000000000ll);
+    // -2 = "this shard could not certify its dense result for the query": the merging rank repeats the query
+    const bool poisoned = uncertified != nullptr && uncertified[q] != 0;
+    if (grow_out) *at(grow_out, oid) = poisoned ? -2 : (valid ? row_offset + doc : -1);
+    if (dense_out) *at(dense_out, oid) = dense_in[gid];
 }
 
 }  // namespace
@@ -246,7 +266,9 @@ int rr_launch_bm25_candidates(const uint64_t* d_postings, const uint64_t* d_tile
                               const uint64_t* d_fwd_off, const uint64_t* d_fwd_data, int V, int T, int64_t n_docs, const int32_t* d_terms, const int32_t* d_nterms,
                               int B, int l_max, const int64_t* d_cand, int pool, const double* d_nrev,
                               const double* d_avg, int64_t row_offset, float* d_bm25, double* d_n_out,
-                              double* d_avg_out, int64_t* d_grow_out, cudaStream_t stream) {
+                              double* d_avg_out, int64_t* d_grow_out, cudaStream_t stream, int pack_bg,
+                              int64_t pack_stride, const float* d_dense_in, float* d_dense_out,
+                              const int32_t* d_uncertified) {
     const int64_t total = (int64_t)B * pool;
     if (total <= 0) return RR_OK;
     const int threads = 256;
@@ -257,7 +279,8 @@ int rr_launch_bm25_candidates(const uint64_t* d_postings, const uint64_t* d_tile
         reinterpret_cast<const unsigned long long*>(d_fwd_off), reinterpret_cast<const uint2*>(d_fwd_data), V, T,
         (long long)n_docs, d_terms, d_nterms,
         l_max, reinterpret_cast<const long long*>(d_cand), pool, B, d_nrev, d_avg, (long long)row_offset, d_bm25,
-        d_n_out, d_avg_out, reinterpret_cast<long long*>(d_grow_out));
+        d_n_out, d_avg_out, reinterpret_cast<long long*>(d_grow_out), pack_bg, (long long)pack_stride, d_dense_in,
+        d_dense_out, d_uncertified);
     RR_LAUNCH_CHECK();
     return RR_OK;
 }

@@ -716,7 +716,8 @@ __global__ void __launch_bounds__(256)
 tc_finalize_kernel(const unsigned long long* __restrict__ kept_keys, const int* __restrict__ kept_cnt, int KP,
                    const float* __restrict__ exact, const int* __restrict__ overflow, const float* __restrict__ qnorm,
                    const float* __restrict__ tau, float eps_rel, int pool, long long* __restrict__ out_idx, float* __restrict__ out_sims,
-                   int32_t* __restrict__ out_count, int* __restrict__ n_flagged, int* __restrict__ flagged) {
+                   int32_t* __restrict__ out_count, int* __restrict__ n_flagged, int* __restrict__ flagged,
+                   int* __restrict__ uncertified) {
     extern __shared__ unsigned long long sk[];
     const int q = blockIdx.x;
     const int kc = kept_cnt[q];
@@ -748,6 +749,7 @@ tc_finalize_kernel(const unsigned long long* __restrict__ kept_keys, const int* 
             ok = pth > c + eps;
         }
         if (!ok) flagged[atomicAdd(n_flagged, 1)] = q;
+        if (uncertified) uncertified[q] = ok ? 0 : 1;
     }
 }
 
@@ -864,7 +866,7 @@ bool rr_tc_can_handle(int dim_pad, int pool) {
 
 int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, const float* d_q, int32_t B,
                      int32_t pool, int64_t* d_idx, float* d_sims, int32_t* d_count, rr_dense_stats* stats,
-                     rr_exact_fn exact_fn, void* exact_ctx, cudaStream_t s) {
+                     rr_exact_fn exact_fn, void* exact_ctx, int32_t* d_uncertified, cudaStream_t s) {
     if (d->dim_pad > TC_MAX_KB_STREAMED * TC_BK)
         return rr_fail(RR_EUNSUPPORTED, "tensor path supports dim <= %d in this build", TC_MAX_KB_STREAMED * TC_BK);
     const int growth = KP_growth(shortlist_size(pool));
@@ -1016,9 +1018,19 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
                                                     static_cast<const int*>(st->overflow.p),
                                                     static_cast<const float*>(st->qnorm.p),
                                                     static_cast<const float*>(st->tau.p), eps_rel, pool,
-                                                    reinterpret_cast<long long*>(d_idx), d_sims, d_count, n_flagged, flagged);
+                                                    reinterpret_cast<long long*>(d_idx), d_sims, d_count, n_flagged, flagged,
+                                                    d_uncertified);
     }
     RR_LAUNCH_CHECK();
+    if (d_uncertified != nullptr) {
+        // deferred mode: nothing is read back; the caller acts on the per-query mask (uncertified results
+        // are best-effort and must be redone by a synchronous call)
+        if (stats) {
+            stats->path = 2; stats->n_uncertified = -1; stats->n_overflow = 0; stats->shortlist = KP;
+            stats->n_segments = n_segments; stats->eps = eps_rel;
+        }
+        return RR_OK;
+    }
     RR_CUDA(cudaMemcpyAsync(st->h_nflag, n_flagged, sizeof(int), cudaMemcpyDeviceToHost, s));
     RR_CUDA(cudaStreamSynchronize(s));
     const int nf = *st->h_nflag;

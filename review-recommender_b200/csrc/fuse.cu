@@ -158,7 +158,10 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
         __shared__ int s_incomplete;
         if (tid == 0) s_incomplete = 0;
         __syncthreads();
-        if (a.n_shards > 1 && per_shard < a.p.pool) {
+        // a shard that could not certify its dense result marks its tuples with global row -2
+        for (int s = tid; s < a.n_shards; s += FUSE_THREADS)
+            if (a.grow[at(s * per_shard, 8)] == -2) s_incomplete = 1;
+        if (per_shard < a.p.pool) {
             const float cut = n_valid >= a.p.pool ? rr_key_score(key[P - 1]) : -INFINITY;
             for (int s = tid; s < a.n_shards; s += FUSE_THREADS) {
                 int cnt = 0;

@@ -15,7 +15,9 @@ int rr_launch_bm25_candidates(const uint64_t* d_postings, const uint64_t* d_tile
                               const uint64_t* d_fwd_off, const uint64_t* d_fwd_data, int V, int T, int64_t n_docs, const int32_t* d_terms, const int32_t* d_nterms,
                               int B, int l_max, const int64_t* d_cand, int pool, const double* d_nrev,
                               const double* d_avg, int64_t row_offset, float* d_bm25, double* d_n_out,
-                              double* d_avg_out, int64_t* d_grow_out, cudaStream_t stream);
+                              double* d_avg_out, int64_t* d_grow_out, cudaStream_t stream, int pack_bg = 0,
+                              int64_t pack_stride = 0, const float* d_dense_in = nullptr, float* d_dense_out = nullptr,
+                              const int32_t* d_uncertified = nullptr);
 
 // dense_exact.cu
 size_t rr_exact_scratch_bytes(int rows, int k);

@@ -16,6 +16,9 @@ postings of those rows and GLOBAL BM25 statistics, and per batch
      the merge;
   4. one small all-gather returns the [B, k] results to every rank.
 
+Round 1 runs without any host synchronisation (`rr_shard_tuples` writes the packed send buffer, K4 writes into
+the all-gather buffer); the only read-back of a search is the list of queries that need the second round.
+
 The pack / exchange / unpack helpers are device-agnostic so that the plumbing is tested on CPU
 with gloo (tests/test_dist_cpu.py); the compute calls need the CUDA library.
 """
@@ -115,24 +118,39 @@ class ShardedSearcher:
         self.round1_pool = round1_pool
         self.last_repeated = 0
 
-    def _round(self, q, term_ids, n_terms, fusion, mode, m):
+    def _merge(self, recv: torch.Tensor, fusion, m: int, B: int):
+        """Owner side of a round: K4 over the G*m received tuples of this rank's B/G queries, then ONE all-gather
+        of a byte buffer [rows int64[Bg,k] | final f32[Bg,k] | flags int32[Bg]] (the kernel writes into views of it)."""
         ix, G = self.ix, self.world
-        B, k = int(q.shape[0]), fusion.k
-        Bg = B // G
-        cand, dense, _cnt = ix.dense_topk(q, m, mode)
-        bm25, n, avg, grow = ix.candidate_tuples(term_ids, n_terms, cand)
-        recv = exchange(pack_tuples(G, grow, n, avg, dense, bm25), self.group)
+        k, Bg = fusion.k, B // G
         views, stride = field_views(recv, Bg, m)
-        rows, final, flags = ix.fuse_sharded(fusion, G, m, stride, Bg, views["dense"], views["bm25"], views["n"],
-                                             views["avg"], views["grow"])
-        # one collective for all outputs: [Bg, k] rows | [Bg, k] finals | [Bg] flags (as int64 words)
-        mine = torch.cat([rows.view(-1), final.view(-1).view(torch.int32).to(torch.int64), flags.to(torch.int64)])
-        out = torch.empty((G, mine.numel()), dtype=torch.int64, device=mine.device)
+        o_final, o_flags = Bg * k * 8, Bg * k * 12
+        nbytes = (Bg * k * 12 + Bg * 4 + 7) // 8 * 8                       # rows of the gathered buffer stay 8-byte aligned
+        mine = torch.empty(nbytes, dtype=torch.uint8, device=recv.device)
+        rows = mine[:o_final].view(torch.int64).view(Bg, k)
+        final = mine[o_final:o_flags].view(torch.float32).view(Bg, k)
+        flags = mine[o_flags:o_flags + Bg * 4].view(torch.int32)
+        ix.fuse_sharded(fusion, G, m, stride, Bg, views["dense"], views["bm25"], views["n"], views["avg"], views["grow"],
+                        out=(rows, final, flags))
+        out = torch.empty((G, mine.numel()), dtype=torch.uint8, device=mine.device)
         dist.all_gather_into_tensor(out.view(-1), mine, group=self.group)
-        all_rows = out[:, :Bg * k].reshape(B, k)
-        all_final = out[:, Bg * k:2 * Bg * k].to(torch.int32).view(torch.float32).reshape(B, k)
-        all_flags = out[:, 2 * Bg * k:].reshape(B)
+        all_rows = out[:, :o_final].view(torch.int64).reshape(B, k)
+        all_final = out[:, o_final:o_flags].view(torch.float32).reshape(B, k)
+        all_flags = out[:, o_flags:o_flags + Bg * 4].view(torch.int32).reshape(B)
         return all_rows, all_final, all_flags
+
+    def _round(self, q, term_ids, n_terms, fusion, mode, m, deferred: bool):
+        """deferred=True: no host synchronisation anywhere (queries the tensor path cannot certify come back
+        flagged); deferred=False: rr_dense_topk redoes uncertified queries exactly before the exchange."""
+        ix, G = self.ix, self.world
+        B = int(q.shape[0])
+        if deferred:
+            send = ix.shard_tuples(q, term_ids, n_terms, m, G, mode)
+        else:
+            cand, dense, _cnt = ix.dense_topk(q, m, mode)
+            bm25, n, avg, grow = ix.candidate_tuples(term_ids, n_terms, cand)
+            send = pack_tuples(G, grow, n, avg, dense, bm25)
+        return self._merge(exchange(send, self.group), fusion, m, B)
 
     def search(self, q: torch.Tensor, term_ids: Optional[torch.Tensor], n_terms: Optional[torch.Tensor], fusion,
                mode: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -144,21 +162,22 @@ class ShardedSearcher:
             raise ValueError("batch size must be a multiple of the world size")
         m = self.round1_pool or local_pool(pool, G)
         m = min(m, pool)
-        rows, final, flags = self._round(q, term_ids, n_terms, fusion, mode, m)
-        self.last_repeated = 0
-        if m < pool:
-            idx = torch.nonzero(flags, as_tuple=False).view(-1)        # host sync: how many queries need round 2
-            nf = int(idx.numel())
-            self.last_repeated = nf
-            if nf > 0:
-                pad = (-nf) % G
-                if pad:
-                    idx = torch.cat([idx, idx[:1].expand(pad)])
-                r2, f2, _ = self._round(q[idx].contiguous(),
-                                        None if term_ids is None else term_ids[idx].contiguous(),
-                                        None if n_terms is None else n_terms[idx].contiguous(), fusion, mode, pool)
-                rows = rows.clone()
-                final = final.clone()
-                rows[idx[:nf]] = r2[:nf]
-                final[idx[:nf]] = f2[:nf]
+        rows, final, flags = self._round(q, term_ids, n_terms, fusion, mode, m, deferred=True)
+        # the ONE host synchronisation of a search: which queries need the second round (a shard may hold more
+        # pool members than it sent, or could not certify its tensor-path result)
+        idx = torch.nonzero(flags, as_tuple=False).view(-1)
+        nf = int(idx.numel())
+        self.last_repeated = nf
+        if nf > 0:
+            pad = (-nf) % G
+            if pad:
+                idx = torch.cat([idx, idx[:1].expand(pad)])
+            r2, f2, _ = self._round(q[idx].contiguous(),
+                                    None if term_ids is None else term_ids[idx].contiguous(),
+                                    None if n_terms is None else n_terms[idx].contiguous(), fusion, mode, pool,
+                                    deferred=False)
+            rows = rows.clone()
+            final = final.clone()
+            rows[idx[:nf]] = r2[:nf]
+            final[idx[:nf]] = f2[:nf]
         return rows, final

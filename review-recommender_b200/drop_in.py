@@ -212,6 +212,37 @@ def _bm25_for_candidates(bm25_blob, query: str, cand_skus: List[str]) -> np.ndar
 
 
 # --------------------------------------------------------------------------------------------
+# artifact loaders
+# --------------------------------------------------------------------------------------------
+def load_product_index(emb_path, meta_path):
+    """load_product_index app/test.py:134-146 (= _product_index app/app_product_search.py:87-117): the meta frame
+    and the row-normalised float32 embeddings; the same SystemExit messages for missing / inconsistent files."""
+    import os
+    import pandas as pd
+    if not os.path.exists(str(emb_path)) or not os.path.exists(str(meta_path)):
+        raise SystemExit("[ERR] product_emb.npy and/or product_emb_meta.parquet missing in data/processed/")
+    meta = pd.read_parquet(meta_path)
+    if "sku" not in meta.columns or "agg_text" not in meta.columns:
+        raise SystemExit("[ERR] product_emb_meta.parquet must have 'sku' and 'agg_text'")
+    V = np.load(emb_path, mmap_mode="r").astype(np.float32)
+    if len(meta) != V.shape[0]:
+        raise SystemExit(f"[ERR] length mismatch: meta={len(meta)} vs emb_rows={V.shape[0]}")
+    x = np.array(V)
+    Vn = x / np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-12)          # l2_normalize utils.py:40-44
+    return meta.reset_index(drop=True), Vn
+
+
+def load_bm25_blob(bm25_pkl):
+    """The pickle half of load_bm25 (app/test.py:148-157): None if the file does not exist."""
+    import os
+    import pickle
+    if not os.path.exists(str(bm25_pkl)):
+        return None
+    with open(bm25_pkl, "rb") as f:
+        return pickle.load(f)
+
+
+# --------------------------------------------------------------------------------------------
 # the two search drivers
 # --------------------------------------------------------------------------------------------
 class SearchEngine:
@@ -329,66 +360,90 @@ class SearchEngine:
 
     def _search(self, query: str, fusion: "engine.Fusion", gate_penalty: float, use_snips: bool = False,
                 max_scan: int = 300_000):
-        import torch
-        qvec = np.asarray(self.encode(query), dtype=np.float32)
-        toks, (tid, nt) = self._terms(query)
+        return self._search_batch([query], fusion, gate_penalty, use_snips, max_scan)[0]
+
+    def _search_batch(self, queries: Sequence[str], fusion: "engine.Fusion", gate_penalty: float,
+                      use_snips: bool = False, max_scan: int = 300_000):
+        """The numeric core of run_search / search for a batch of queries in ONE pass over the GPU kernels
+        (dense top-pool, candidate BM25, gates, best reviews, fusion); per query the result is what the
+        single-query call returns.  -> list of (top-k DataFrame, tokens, snippets)."""
+        B = len(queries)
+        if B == 0:
+            return []
+        qmat = np.stack([np.asarray(self.encode(q), dtype=np.float32) for q in queries])
+        toks = [tokenize_query(q) for q in queries]
         pool = fusion.pool
-        cand, dense, cnt = self.ix.dense_topk(qvec[None, :], pool)
-        if self.bm25_active and toks:
+        cand, dense, cnt = self.ix.dense_topk(qmat, pool)
+        if self.bm25_active and any(toks):
+            # a query without tokens scores zeros (:203-204) -- an empty term list does exactly that
+            tid, nt = engine.HybridIndex.pack_terms([[self.vocab.get(t, -1) for t in tk] for tk in toks])
             bm25, n, avg, grow = self.ix.candidate_tuples(tid, nt, cand)
         else:
             bm25, n, avg, grow = self.ix.candidate_tuples(None, None, cand)
-        P = int(cnt[0].item())
-        rows = cand[0, :P].cpu().numpy()
-        frame = self.meta.iloc[rows].reset_index(drop=True)
-        rerank = gate = None
+        counts = cnt.cpu().numpy()
+        cand_h = cand.cpu().numpy()
+        frames = [self.meta.iloc[cand_h[b, :counts[b]]].reset_index(drop=True) for b in range(B)]
+
+        rerank = gate = best = None
         if fusion.rerank_k > 0:
-            rr_k = min(fusion.rerank_k, P)
-            z = np.zeros(pool, dtype=np.float32)
+            z = np.zeros((B, pool), dtype=np.float32)
             if self.rerank is not None:
-                texts = frame["agg_text"].astype(str).str.slice(0, 2000).tolist()[:rr_k]
-                rr = np.array(self.rerank(query, texts), dtype=np.float32)
-                lo, hi = float(np.min(rr)), float(np.max(rr))
-                if np.isfinite(lo) and np.isfinite(hi) and hi - lo >= 1e-12:
-                    z[:rr_k] = ((rr - lo) / (hi - lo + 1e-12)).astype(np.float32)      # _minmax, :182-187
-            rerank = z[None, :]
+                for b in range(B):
+                    rr_k = min(fusion.rerank_k, int(counts[b]))
+                    texts = frames[b]["agg_text"].astype(str).str.slice(0, 2000).tolist()[:rr_k]
+                    rr = np.array(self.rerank(queries[b], texts), dtype=np.float32)
+                    lo, hi = float(np.min(rr)), float(np.max(rr))
+                    if np.isfinite(lo) and np.isfinite(hi) and hi - lo >= 1e-12:
+                        z[b, :rr_k] = ((rr - lo) / (hi - lo + 1e-12)).astype(np.float32)      # _minmax, :182-187
+            rerank = z
         if self.gate_ix is not None:
             # calculate_gate_factor over agg_text[:6000] of the pool on the GPU (:297-302, app/test.py:291-297)
-            gate = self.gate_ix.factors([build_gate_groups(query)], cand, gate_penalty)
-        elif self.gate is not None and "agg_text" in frame:
-            g = np.ones(pool, dtype=np.float32)
-            texts = frame["agg_text"].astype(str).str.slice(0, 6000).tolist()
-            g[:P] = np.array([self.gate(t, query, gate_penalty) for t in texts], dtype=np.float32)
-            gate = g[None, :]
-        snips: Dict[str, Dict] = {}
-        best = None
+            gate = self.gate_ix.factors([build_gate_groups(q) for q in queries], cand, gate_penalty)
+        elif self.gate is not None and "agg_text" in self.meta.columns:
+            g = np.ones((B, pool), dtype=np.float32)
+            for b in range(B):
+                texts = frames[b]["agg_text"].astype(str).str.slice(0, 6000).tolist()
+                g[b, :counts[b]] = np.array([self.gate(t, queries[b], gate_penalty) for t in texts], dtype=np.float32)
+            gate = g
+        snips_all: List[Dict[str, Dict]] = [{} for _ in range(B)]
         if use_snips and self.review_ix is not None:
             text_cap = 600 if fusion.driver == "streamlit" else 400
             if max_scan <= 0 and fusion.driver != "streamlit":
-                self.best_review_snippets(qvec, frame["sku"].astype(str).tolist(), max_scan)    # raises like the CLI
+                for b in range(B):      # raises like the CLI when some candidate has reviews
+                    self.best_review_snippets(qmat[b], frames[b]["sku"].astype(str).tolist(), max_scan)
             if max_scan > 0:
-                raw, snips = self._snippets_for_rows(qvec, rows, max_scan, text_cap)
-                if snips:
-                    b_ = np.zeros(pool, dtype=np.float32)
-                    b_[:P] = raw
-                    best = b_[None, :]
+                raw, file_pos = self.review_ix.best(qmat, cand, max_rows=max_scan)
+                skus = self.meta["sku"].astype(str).values
+                has_stars = "stars" in self.reviews.columns
+                for b in range(B):
+                    for i in range(int(counts[b])):
+                        f = int(file_pos[b, i])
+                        if f >= 0:
+                            rev = self.reviews.iloc[f]
+                            snips_all[b][str(skus[cand_h[b, i]])] = {
+                                "score": float(raw[b, i]), "text": str(rev["text"])[:text_cap],
+                                "stars": float(rev["stars"]) if has_stars else float("nan")}
+                if any(snips_all):
+                    # queries without any snippet keep an all-zero column, whose min-max is zeros as well (:288-294)
+                    best = raw
                     fusion.best_is_raw = True
         top_rows, final, pos, comp = self.ix.fuse(fusion, dense, bm25, n, avg, grow, count=cnt, rerank=rerank,
                                                   best=best, gate=gate, want_components=True)
-        pos = pos[0].cpu().numpy()
-        pos = pos[pos >= 0]
-        comp = comp[0].cpu().numpy()
-        out = frame.iloc[pos].reset_index(drop=True).copy()
-        out["_dense"], out["_bm25"], out["_prior"] = comp[pos, 0], comp[pos, 1], comp[pos, 2]
-        out["_trust"], out["_final"] = comp[pos, 3], comp[pos, 4]
-        out["_rerank"] = rerank[0][pos] if rerank is not None else 0.0
-        out["_best"] = comp[pos, 7]
-        if gate is not None:
-            g0 = gate[0].cpu().numpy() if hasattr(gate, "cpu") else gate[0]
-            out["_gate"] = g0[pos]
-        else:
-            out["_gate"] = np.ones(len(pos), dtype=np.float32)
-        return out, toks, snips
+        pos_h, comp_h = pos.cpu().numpy(), comp.cpu().numpy()
+        gate_h = None if gate is None else (gate.cpu().numpy() if hasattr(gate, "cpu") else gate)
+        results = []
+        for b in range(B):
+            p_ = pos_h[b]
+            p_ = p_[p_ >= 0]
+            c = comp_h[b]
+            out = frames[b].iloc[p_].reset_index(drop=True).copy()
+            out["_dense"], out["_bm25"], out["_prior"] = c[p_, 0], c[p_, 1], c[p_, 2]
+            out["_trust"], out["_final"] = c[p_, 3], c[p_, 4]
+            out["_rerank"] = rerank[b][p_] if rerank is not None else 0.0
+            out["_best"] = c[p_, 7]
+            out["_gate"] = gate_h[b][p_] if gate_h is not None else np.ones(len(p_), dtype=np.float32)
+            results.append((out, toks[b], snips_all[b]))
+        return results
 
     def run_search(self, query: str, k: int, rerank_k: int, w_dense: float, w_bm25: float, w_rerank: float,
                    w_prior: float, w_best: float, prior_C: float, use_snips: bool, max_scan: int,
@@ -401,6 +456,52 @@ class SearchEngine:
         out, toks, snips = self._search(query, fusion, gate_penalty, use_snips=use_snips, max_scan=max_scan)
         return out, snips, {"bm25_active": self.bm25_active, "tokens": toks,
                              "groups": [list(g) for g in build_gate_groups(query)], "pool": fusion.pool}
+
+    def run_search_batch(self, queries: Sequence[str], k: int = 10, rerank_k: int = 0, w_dense: float = 0.55,
+                         w_bm25: float = 0.20, w_rerank: float = 0.20, w_prior: float = 0.20, w_best: float = 0.10,
+                         prior_C: float = 20.0, use_snips: bool = False, max_scan: int = 300_000, min_reviews: int = 8,
+                         gate_penalty: float = 0.5):
+        """run_search for a list of queries as one GPU batch: [(DataFrame, snippets, debug)] in query order,
+        each element equal to run_search(query, ...).  This is what a batched eval driver calls instead of one
+        run_search per (method, query) (evaluate_ranking_methods evals/performance_metrics.py:238-281)."""
+        fusion = engine.Fusion(k=k, rerank_k=rerank_k, w_dense=w_dense, w_bm25=w_bm25, w_rerank=w_rerank,
+                               w_prior=w_prior, w_best=w_best, prior_C=prior_C, min_reviews=min_reviews,
+                               driver="streamlit", bm25_absent=not self.bm25_active)
+        res = self._search_batch(list(queries), fusion, gate_penalty, use_snips=use_snips, max_scan=max_scan)
+        return [(out, snips, {"bm25_active": self.bm25_active, "tokens": toks,
+                              "groups": [list(g) for g in build_gate_groups(q)], "pool": fusion.pool})
+                for q, (out, toks, snips) in zip(queries, res)]
+
+    def batched_search_function(self, queries: Sequence[str]):
+        """A `search_function(query, **config)` for the reference's evaluate_ranking_methods
+        (evals/performance_metrics.py:238-281) that answers every query of `queries` from ONE GPU batch per
+        distinct config instead of one run_search call per (method, query)."""
+        cache: Dict[Tuple, Dict[str, Tuple]] = {}
+        qlist = list(dict.fromkeys(queries))
+
+        def search_function(query, **config):
+            key = tuple(sorted(config.items()))
+            if key not in cache:
+                cache[key] = dict(zip(qlist, self.run_search_batch(qlist, **config)))
+            hit = cache[key].get(query)
+            return hit if hit is not None else self.run_search_batch([query], **config)[0]
+        return search_function
+
+    @classmethod
+    def from_artifacts(cls, emb_path, meta_path, bm25_pkl=None, reviews_path=None, **kw) -> "SearchEngine":
+        """Builds the engine from the reference's artifact files: product_emb.npy, product_emb_meta.parquet,
+        product_bm25.pkl ({"skus", "corpus", "tokenizer"}, nlp/12_product_prep.py:85-88) and, optionally,
+        reviews_with_embeddings.parquet -- load_product_index + load_bm25 (app/test.py:134-157)."""
+        meta, Vn = load_product_index(emb_path, meta_path)
+        blob = load_bm25_blob(bm25_pkl) if bm25_pkl is not None else None
+        reviews = None
+        if reviews_path is not None:
+            import os
+            import pandas as pd
+            if os.path.exists(str(reviews_path)):
+                reviews = pd.read_parquet(reviews_path)
+        return cls(meta, Vn, blob["corpus"] if blob else None, [str(x) for x in blob["skus"]] if blob else None,
+                   reviews=reviews, **kw)
 
     def search(self, args):
         """The numeric core of search(args) (app/test.py:228-309); returns the top-k DataFrame."""

@@ -351,15 +351,36 @@ class HybridIndex:
                                     _ptr(pos), _ptr(comp), self.device.index or 0, _stream()))
         return rows, final, pos, comp
 
+    def shard_tuples(self, q, term_ids, n_terms, m: int, n_ranks: int, mode: int = _lib.RR_DENSE_AUTO,
+                     send: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The shard's exact top-m + candidate tuples for all B queries, packed for the all-to-all
+        (uint8 [n_ranks, (B/n_ranks)*m*32], layout of dist.pack_tuples); no host synchronisation."""
+        q = self._dev(q, torch.float32)
+        B = int(q.shape[0])
+        lmax = 0
+        if term_ids is not None:
+            term_ids = self._dev(term_ids, torch.int32)
+            n_terms = self._dev(n_terms, torch.int32)
+            lmax = int(term_ids.shape[1])
+        nbytes = (B // n_ranks) * m * 32
+        if send is None or send.numel() != n_ranks * nbytes:
+            send = torch.empty((n_ranks, nbytes), dtype=torch.uint8, device=self.device)
+        check(self.lib.rr_shard_tuples(self._h, _ptr(q), _ptr(term_ids), _ptr(n_terms), B, lmax, m, mode, n_ranks,
+                                       _ptr(send), _stream()))
+        return send
+
     def fuse_sharded(self, fusion: Fusion, n_shards: int, per_shard: int, shard_stride_bytes: int, B: int,
-                     dense, bm25, n, avg, grow):
+                     dense, bm25, n, avg, grow, out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
         """K4 over tuples received from `n_shards` row shards (cross-shard merge + fusion).  The field
         tensors are views into one exchange buffer; shard s's [B, per_shard] block of a field starts
         s*shard_stride_bytes after the field's base."""
         p = fusion.to_c()
-        rows = torch.empty((B, fusion.k), dtype=torch.int64, device=self.device)
-        final = torch.empty((B, fusion.k), dtype=torch.float32, device=self.device)
-        flags = torch.zeros((B,), dtype=torch.int32, device=self.device)
+        if out is not None:
+            rows, final, flags = out
+        else:
+            rows = torch.empty((B, fusion.k), dtype=torch.int64, device=self.device)
+            final = torch.empty((B, fusion.k), dtype=torch.float32, device=self.device)
+            flags = torch.zeros((B,), dtype=torch.int32, device=self.device)
         check(self.lib.rr_fuse_topk_sharded(C.byref(p), B, n_shards, per_shard, shard_stride_bytes, _ptr(dense),
                                             _ptr(bm25), _ptr(n), _ptr(avg), _ptr(grow), _ptr(rows), _ptr(final),
                                             _ptr(flags), self.device.index or 0, _stream()))

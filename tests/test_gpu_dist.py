@@ -28,6 +28,14 @@ WORKER = textwrap.dedent('''
     syn = rr.synth
     full = syn.make_corpus(N, D, V)
     q = syn.queries(B, D)
+    # 600 rows within 1e-4 of row 17 and a query equal to it: the tensor path cannot certify that query, so the
+    # shard marks its tuples (global row -2) and the query must take the synchronous second round
+    rng = np.random.default_rng(3)
+    base = full.emb[17].copy()
+    for r in range(1000, 1600):
+        v = base + 1e-4 * rng.standard_normal(D).astype(np.float32)
+        full.emb[r] = v / np.linalg.norm(v)
+    q[0] = base
     qt = syn.query_terms(B, L, full.doc_offsets, full.token_ids, V).astype(np.int32)
     nt = np.full(B, L, dtype=np.int32)
     fusion = rr.engine.Fusion(k=K, rerank_k=0, w_rerank=0.0, w_best=0.0)
@@ -48,7 +56,11 @@ WORKER = textwrap.dedent('''
         rows, final = searcher.search(torch.from_numpy(q).to(dev), torch.from_numpy(qt).to(dev),
                                       torch.from_numpy(nt).to(dev), fusion, mode=mode)
         if r1 == 16:
-            assert searcher.last_repeated > 0
+            assert searcher.last_repeated > 1
+        if mode == rr._lib.RR_DENSE_TENSOR:
+            assert searcher.last_repeated >= 1, "the near-duplicate query must be repeated"
+        if mode == rr._lib.RR_DENSE_EXACT and world == 1:
+            assert searcher.last_repeated == 0
         print("rank", rank, "mode", mode, "round1", r1 or rr.dist.local_pool(fusion.pool, world), "repeated", searcher.last_repeated)
         if rank == 0:
             whole = rr.engine.HybridIndex(full.emb, full.doc_offsets, full.token_ids, V, full.n_reviews, full.avg_stars,
@@ -68,7 +80,16 @@ def test_sharded_equals_single_gpu(tmp_path):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    world = 2 if n < 4 else 4
+    _run_world(tmp_path, 2 if n < 4 else 4)
+
+
+def test_world_of_one_runs_the_same_protocol(tmp_path):
+    """One rank over NCCL: rr_shard_tuples (no host synchronisation), the poisoned-tuple path for uncertified
+    queries and the single all-gather buffer, on a single-GPU box."""
+    _run_world(tmp_path, 1)
+
+
+def _run_world(tmp_path, world):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     import socket

@@ -91,3 +91,47 @@ def test_search_engine_reproduces_reference_golden_cases(golden_dir):
         np.testing.assert_allclose(top["_final"].values, ref_final, rtol=1e-5, atol=1e-7)
         assert_ids_match_modulo_ties(got_rows, top["_final"].values, ref_rows, ref_final, 2e-6,
                                      f"{c['driver']} q{c['query_index']}")
+
+
+def test_batched_search_equals_single_queries_and_artifact_loader(golden_dir, tmp_path):
+    """run_search_batch (one GPU batch) == run_search per query, with gates and snippets on; the engine is built
+    from artifact files in the reference's formats (product_emb.npy / product_emb_meta.parquet / product_bm25.pkl /
+    reviews_with_embeddings.parquet); the reference's evaluate_ranking_methods loop shape is served from the batch."""
+    import pickle
+    from tests import snippet_world
+    from tests.golden_worlds import GATE_QUERIES, make_gate_texts
+    rr = _rr()
+    w = snippet_world.load(golden_dir)
+    z = w["z"]
+    meta = w["meta"].copy()
+    meta["agg_text"] = make_gate_texts(len(meta), z["doc_offsets"], z["token_ids"])
+    np.save(tmp_path / "product_emb.npy", np.array(z["emb"]))                  # un-normalised rows on purpose
+    meta.to_parquet(tmp_path / "product_emb_meta.parquet")
+    with open(tmp_path / "product_bm25.pkl", "wb") as f:
+        pickle.dump({"skus": w["bm25_skus"], "corpus": w["bm25_corpus"], "tokenizer": "simple_en_v1"}, f, protocol=4)
+    w["reviews"].to_parquet(tmp_path / "reviews_with_embeddings.parquet")
+    queries = list(w["cases"]["query_strs"]) + GATE_QUERIES[:5]
+    table = dict(w["table"])
+    table.update({q: z["queries"][i % len(z["queries"])] for i, q in enumerate(GATE_QUERIES)})
+    eng = rr.drop_in.SearchEngine.from_artifacts(tmp_path / "product_emb.npy", tmp_path / "product_emb_meta.parquet",
+                                                 tmp_path / "product_bm25.pkl", tmp_path / "reviews_with_embeddings.parquet",
+                                                 encode=lambda q: table[q])
+    assert eng.gate_ix is not None and eng.review_ix is not None and eng.bm25_active
+    cfg = dict(k=20, rerank_k=0, w_dense=0.45, w_bm25=0.15, w_rerank=0.0, w_prior=0.10, w_best=0.30, prior_C=20.0,
+               use_snips=True, max_scan=300_000, min_reviews=8, gate_penalty=0.5)
+    batch = eng.run_search_batch(queries, **cfg)
+    assert len(batch) == len(queries)
+    for q, (top_b, snips_b, dbg_b) in zip(queries, batch):
+        top_1, snips_1, dbg_1 = eng.run_search(q, *[cfg[k] for k in ("k", "rerank_k", "w_dense", "w_bm25", "w_rerank",
+                                                                      "w_prior", "w_best", "prior_C", "use_snips",
+                                                                      "max_scan", "min_reviews", "gate_penalty")])
+        assert top_b["sku"].tolist() == top_1["sku"].tolist(), q
+        for col in ("_final", "_dense", "_bm25", "_prior", "_best", "_gate", "_trust"):
+            np.testing.assert_array_equal(top_b[col].values, top_1[col].values, err_msg=f"{q} {col}")
+        assert snips_b == snips_1 and dbg_b == dbg_1
+    fn = eng.batched_search_function(queries)
+    for q in queries[:3]:
+        res, _, _ = fn(q, **cfg)
+        assert res["sku"].tolist() == batch[queries.index(q)][0]["sku"].tolist()
+    with pytest.raises(SystemExit):
+        rr.drop_in.load_product_index(tmp_path / "missing.npy", tmp_path / "product_emb_meta.parquet")

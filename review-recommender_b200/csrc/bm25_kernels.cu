@@ -22,6 +22,7 @@
 //      candidate's doc id inside each term segment of the doc's tile; same impacts, same
 //      order => bit-identical to the tile kernel at those docs.  Also gathers n_reviews /
 //      avg_stars / global row so that the fusion kernel gets complete tuples.
+#include <cstdlib>
 #include <type_traits>
 
 #include "rr_internal.h"
@@ -41,8 +42,8 @@ __device__ __forceinline__ uint4 ldg_stream16(const uint4* p) {
     return r;
 }
 
-// One CTA per (doc tile, query).  Latency is hidden by residency (>= 4 CTAs of 256 threads per SM, each
-// with 4 x 16 B loads in flight per thread = 64 KB in flight per SM), not by register double-buffering:
+// One CTA per (doc tile, query).  Latency is hidden by residency (4 CTAs of 256 threads per SM with 12288-doc
+// tiles = 48 KB of accumulators each; every thread keeps 4 x 16 B loads in flight), not by register double-buffering:
 // the r01 profile showed the double-buffered 512-thread version at 92 registers -> 1 CTA/SM -> 31 % of HBM.
 __global__ void __launch_bounds__(BM25_THREADS, BM25_MIN_CTAS)
 bm25_tile_scores_kernel(const uint4* __restrict__ postings, const uint64_t* __restrict__ tile_base,
@@ -102,10 +103,8 @@ bm25_tile_scores_kernel(const uint4* __restrict__ postings, const uint64_t* __re
         int phase_first = 0;     // block-uniform, monotone
         int prev_seg = -1;       // block-uniform: last term accumulated
 
-        for (int r = 0; r < n_rounds; ++r) {
-            uint4 p[BM25_U];
-            uint32_t unit_of[BM25_U];
-            int seg[BM25_U];
+        // issue this thread's BM25_U 16-byte loads of round r (no wait)
+        auto load_round = [&](int r, uint4 (&p)[BM25_U], uint32_t (&unit_of)[BM25_U], int (&seg)[BM25_U]) {
 #pragma unroll
             for (int u = 0; u < BM25_U; ++u) {
                 const uint32_t v = (uint32_t)(r * R + u * BM25_THREADS + tid);
@@ -118,7 +117,9 @@ bm25_tile_scores_kernel(const uint4* __restrict__ postings, const uint64_t* __re
                     seg[u] = load_cursor;
                 }
             }
-            // terms covered by this round (block-uniform)
+        };
+        // add round r's impacts, term by term in query order (a barrier separates consecutive terms)
+        auto add_round = [&](int r, const uint4 (&p)[BM25_U], const uint32_t (&unit_of)[BM25_U], const int (&seg)[BM25_U]) {
             const uint32_t v_first = (uint32_t)r * R;
             const uint32_t v_last = min(total, v_first + (uint32_t)R) - 1u;
             while (v_first >= s_ustart[phase_first + 1]) ++phase_first;
@@ -146,6 +147,17 @@ bm25_tile_scores_kernel(const uint4* __restrict__ postings, const uint64_t* __re
                     }
                 }
             }
+        };
+
+        // one round of loads in flight per thread.  Issuing round r+1 before accumulating round r (two rounds in
+        // flight, 80 registers, 3 CTAs/SM) was measured SLOWER on B200 (r02: 49 % vs 62 % of HBM peak at 8 M docs),
+        // as was the 512-thread register double buffer of r01: latency is hidden by residency instead.
+        uint4 pa[BM25_U];
+        uint32_t ua[BM25_U];
+        int sa[BM25_U];
+        for (int r = 0; r < n_rounds; ++r) {
+            load_round(r, pa, ua, sa);
+            add_round(r, pa, ua, sa);
         }
     }
     __syncthreads();
@@ -272,8 +284,8 @@ int rr_launch_bm25_candidates(const uint64_t* d_postings, const uint64_t* d_tile
     const int64_t total = (int64_t)B * pool;
     if (total <= 0) return RR_OK;
     const int threads = 256;
-    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
     RrProfScope prof(RR_PROF_BM25_CAND, stream);
+    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
     bm25_candidates_kernel<<<blocks, threads, 0, stream>>>(
         reinterpret_cast<const uint2*>(d_postings), d_tile_base, d_blk_off,
         reinterpret_cast<const unsigned long long*>(d_fwd_off), reinterpret_cast<const uint2*>(d_fwd_data), V, T,

@@ -3,7 +3,7 @@
 get_scores mode (every doc scored), B in {1, 64, 256}.  Reports achieved HBM GB/s against the
 algorithmic bytes of SURVEY.md section 8d:  8 B per posting of the query's terms + 4 B per doc per query.
 
-    python tools/bench_bm25.py [--docs 20000000] [--vocab 200000] [--terms 16] [--tile-docs 16384]
+    python tools/bench_bm25.py [--docs 20000000] [--vocab 200000] [--terms 16] [--tile-docs 12288]
 """
 import argparse
 import json
@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--docs", type=int, default=20_000_000)
     ap.add_argument("--vocab", type=int, default=200_000)
     ap.add_argument("--terms", type=int, default=16)
-    ap.add_argument("--tile-docs", type=int, default=16384)
+    ap.add_argument("--tile-docs", type=int, default=12288)
     ap.add_argument("--batches", default="1,64,256")
     ap.add_argument("--reps", type=int, default=5)
     args = ap.parse_args()

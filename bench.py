@@ -56,6 +56,18 @@ def parse_args():
     return ap.parse_args()
 
 
+def load_traffic(kernel: str):
+    """DRAM bytes of one profiled launch of `kernel` from the committed ncu --set full capture (or None)."""
+    p = REPO / "profiles" / "r01_traffic.json"
+    try:
+        d = json.loads(p.read_text())
+        rec = dict(d[kernel])
+        rec["source"] = d.get("source")
+        return rec
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = REPO / "MEASURED_PEAKS.json"
     if p.exists():
@@ -428,11 +440,19 @@ def main():
         flops = 2.0 * B * n_local * D
         t = kernels[dom]["ms_per_step"] / 1000.0
         ach = flops / t / 1e12
+        tr = load_traffic("tc_filter_kernel")
+        n_l = kernels[dom]["launches_per_step"]
         roofline = {"kernel": "tc_filter_kernel (tcgen05 bf16 GEMM + threshold filter)", "bound": "tensor",
                     "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
-                    "peak_source": f"{peaks['source']} bf16_tflops_sustained", "algorithmic_flops_per_step": flops,
-                    "launches_per_step": kernels[dom]["launches_per_step"]}
+                    "frac": ach / peaks["bf16_tflops_sustained"],
+                    "traffic": tr["dram_bytes"] if tr else None,
+                    "traffic_note": (f"DRAM read+write bytes of ONE profiled launch ({tr['launch']}; its bf16 corpus segment is "
+                                     f"{tr['corpus_bytes_of_segment']:.3e} B, read once) -- {tr['source']}") if tr else None,
+                    "peak_source": f"{peaks['source']} bf16_tflops_sustained (cuBLAS back to back); burst "
+                                   f"{peaks['bf16_tflops']:.1f} -> frac {ach / peaks['bf16_tflops']:.3f}",
+                    "algorithmic_flops_per_step": flops, "launches_per_step": n_l,
+                    "algorithmic_flops_per_launch_avg": flops / max(n_l, 1.0),
+                    "avg_launch_ms": kernels[dom]["ms_per_step"] / max(n_l, 1.0)}
     elif dom == "dense_gemv":
         groups = (B + 7) // 8
         nbytes = 4.0 * D * n_local * groups
@@ -459,7 +479,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16 tensor-core shortlist, f32 exact rescoring + f32/f64 fusion", "data": "synthetic",
+        "dtype": "bf16", "data": "synthetic",
+        "dtype_note": "bf16 tensor-core shortlist (fp32 accumulate), exact f32 rescoring, f32/f64 fusion as the reference",
         "config": {"workload": cfg["workload"], "docs": N, "docs_per_gpu": n_local, "dim": D, "vocab": V, "batch": B,
                    "query_terms": L, "k": K, "pool": fusion.pool, "parallelism": f"row-sharded x{world}",
                    "l2": "inputs larger than L2 (bf16 corpus shard read every step)",

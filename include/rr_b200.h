@@ -228,6 +228,19 @@ int rr_best_review_scores(const float* d_rev_emb, const int64_t* d_rev_range, in
                           const int64_t* d_slot_file, const int64_t* d_limit,
                           float* d_best_score, int64_t* d_best_slot, int device, rr_stream);
 
+/* Index preparation: l2_normalize utils.py:40-44 (= _l2norm app/app_product_search.py:179-180) over the rows of
+ * product_emb.npy as done once at load (app/app_product_search.py:110, app/test.py:145), bit-identical to NumPy
+ * (float32 pairwise sum of squares, sqrt, max(., 1e-12), divide), fused with the round-to-nearest bf16 copy the
+ * tensor path reads.  d_in float[n_rows, dim]; d_out_f32 float[n_rows, dim] (may alias d_in) or NULL;
+ * d_out_bf16 [n_rows, dim_pad] (dim_pad a multiple of 64, padding zero-filled) or NULL; d_norms float[n_rows]
+ * (the norms before normalisation) or NULL. */
+int rr_normalize_rows(const float* d_in, int64_t n_rows, int32_t dim, float* d_out_f32, uint16_t* d_out_bf16,
+                      int32_t dim_pad, float* d_norms, int device, rr_stream);
+
+/* The bf16 copy alone (rows already normalised by the caller): round-to-nearest-even, zero padding. */
+int rr_bf16_rows(const float* d_in, int64_t n_rows, int32_t dim, uint16_t* d_out_bf16, int32_t dim_pad,
+                 int device, rr_stream);
+
 /* Attribute gates: calculate_gate_factor utils.py:88-101 (= _gate_factor app/app_product_search.py:228-236)
  * over `agg_text[:6000]` of every pool member (app/app_product_search.py:297-302, app/test.py:291-297).
  * Text store: d_text = UTF-8 bytes of str(agg_text)[:6000].lower() of every product row, each text starting

@@ -77,6 +77,8 @@ SIGNATURES = {
     "rr_profile_collect": (C.c_int, [_P, _P, C.c_int32]),
     "rr_best_review_scores": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P,
                                         C.c_int, _P]),
+    "rr_normalize_rows": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, C.c_int32, _P, C.c_int, _P]),
+    "rr_bf16_rows": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int, _P]),
     "rr_gate_factors": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_double,
                                   _P, _P, C.c_int, _P]),
     "rr_gate_fixed_bitmaps": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, C.c_int32, _P, C.c_int, _P]),

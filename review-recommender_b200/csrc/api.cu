@@ -360,6 +360,27 @@ extern "C" int rr_best_review_scores(const float* d_rev_emb, const int64_t* d_re
                                  d_best_score, d_best_slot, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int rr_normalize_rows(const float* d_in, int64_t n_rows, int32_t dim, float* d_out_f32, uint16_t* d_out_bf16,
+                                 int32_t dim_pad, float* d_norms, int device, rr_stream stream) {
+    if (!d_in || n_rows < 0 || dim <= 0 || (!d_out_f32 && !d_out_bf16 && !d_norms))
+        return rr_fail(RR_EINVAL, "rr_normalize_rows: bad argument");
+    if (d_out_bf16 && (dim_pad < dim || dim_pad % 64))
+        return rr_fail(RR_EINVAL, "rr_normalize_rows: dim_pad must be a multiple of 64 and >= dim");
+    RR_CUDA(cudaSetDevice(device));
+    return rr_launch_normalize_rows(d_in, n_rows, dim, d_out_f32, d_out_bf16, dim_pad, d_norms,
+                                    static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rr_bf16_rows(const float* d_in, int64_t n_rows, int32_t dim, uint16_t* d_out_bf16, int32_t dim_pad,
+                            int device, rr_stream stream) {
+    if (!d_in || !d_out_bf16 || n_rows < 0 || dim <= 0 || dim_pad < dim || dim_pad % 64)
+        return rr_fail(RR_EINVAL, "rr_bf16_rows: bad argument");
+    RR_CUDA(cudaSetDevice(device));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    return rr_launch_bf16_rows(d_in, n_rows, dim, d_out_bf16, dim_pad, sms, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int rr_gate_factors(const uint8_t* d_text, const int64_t* d_text_off, const int32_t* d_text_len, int64_t n_docs,
                                const uint32_t* d_fixed_bits, const uint8_t* d_pat, const int32_t* d_pat_off,
                                const int32_t* d_group_pat_off, const int32_t* d_group_fixed,

@@ -33,6 +33,13 @@ int rr_launch_best_review(const float* d_rev_emb, const int64_t* d_rev_range, in
                           const float* d_q, int B, const int64_t* d_cand, int pool, const int64_t* d_slot_file,
                           const int64_t* d_limit, float* d_score, int64_t* d_slot, cudaStream_t stream);
 
+// prep.cu
+int rr_launch_normalize_rows(const float* d_in, int64_t n_rows, int D, float* d_out_f32, uint16_t* d_out_bf16,
+                             int dim_pad, float* d_norms, cudaStream_t stream);
+
+int rr_launch_bf16_rows(const float* d_in, int64_t n_rows, int D, uint16_t* d_out, int dim_pad, int sm_count,
+                        cudaStream_t stream);
+
 // gate.cu
 int rr_launch_gate_query(const uint8_t* d_text, const int64_t* d_text_off, const int32_t* d_text_len, int64_t n_docs,
                          const uint32_t* d_fixed_bits, const uint8_t* d_pat, const int32_t* d_pat_off,

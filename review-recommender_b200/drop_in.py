@@ -214,7 +214,7 @@ def _bm25_for_candidates(bm25_blob, query: str, cand_skus: List[str]) -> np.ndar
 # --------------------------------------------------------------------------------------------
 # artifact loaders
 # --------------------------------------------------------------------------------------------
-def load_product_index(emb_path, meta_path):
+def load_product_index(emb_path, meta_path, normalize: bool = True):
     """load_product_index app/test.py:134-146 (= _product_index app/app_product_search.py:87-117): the meta frame
     and the row-normalised float32 embeddings; the same SystemExit messages for missing / inconsistent files."""
     import os
@@ -228,6 +228,8 @@ def load_product_index(emb_path, meta_path):
     if len(meta) != V.shape[0]:
         raise SystemExit(f"[ERR] length mismatch: meta={len(meta)} vs emb_rows={V.shape[0]}")
     x = np.array(V)
+    if not normalize:
+        return meta.reset_index(drop=True), x
     Vn = x / np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-12)          # l2_normalize utils.py:40-44
     return meta.reset_index(drop=True), Vn
 
@@ -255,8 +257,9 @@ class SearchEngine:
     def __init__(self, meta, Vn: np.ndarray, bm25_corpus: Optional[Sequence[Sequence[str]]] = None,
                  bm25_skus: Optional[Sequence[str]] = None, encode: Optional[Callable] = None,
                  rerank: Optional[Callable] = None, gate: Optional[Callable] = None, device: str = "cuda:0",
-                 reviews=None):
-        """`reviews`: the reviews_with_embeddings.parquet frame (columns sku, text, stars, embedding) or
+                 reviews=None, normalize: bool = False):
+        """`normalize=True`: `Vn` holds the raw rows of product_emb.npy and is L2-normalised on the device
+        (bit-identical to l2_normalize, engine.HybridIndex).  `reviews`: the reviews_with_embeddings.parquet frame (columns sku, text, stars, embedding) or
         None when the file does not exist (snippets are then skipped, like `REV_EMB.exists()` :285)."""
         import pandas as pd
         self.meta = meta.reset_index(drop=True)
@@ -305,9 +308,9 @@ class SearchEngine:
             # document lengths / statistics are those of the blob; rows without a BM25 doc get no postings
             offs, toks = np.asarray(o, dtype=np.int64), np.asarray(ids, dtype=np.int32)
             self._stats = stats
-            self.ix = engine.HybridIndex(Vn, offs, toks, v, nrev, avg, device=device, stats=stats)
+            self.ix = engine.HybridIndex(Vn, offs, toks, v, nrev, avg, device=device, stats=stats, normalize=normalize)
         else:
-            self.ix = engine.HybridIndex(Vn, n_reviews=nrev, avg_stars=avg, device=device)
+            self.ix = engine.HybridIndex(Vn, n_reviews=nrev, avg_stars=avg, device=device, normalize=normalize)
 
     def _terms(self, query: str):
         toks = tokenize_query(query)
@@ -492,7 +495,7 @@ class SearchEngine:
         """Builds the engine from the reference's artifact files: product_emb.npy, product_emb_meta.parquet,
         product_bm25.pkl ({"skus", "corpus", "tokenizer"}, nlp/12_product_prep.py:85-88) and, optionally,
         reviews_with_embeddings.parquet -- load_product_index + load_bm25 (app/test.py:134-157)."""
-        meta, Vn = load_product_index(emb_path, meta_path)
+        meta, V = load_product_index(emb_path, meta_path, normalize=False)     # rows are normalised on the device
         blob = load_bm25_blob(bm25_pkl) if bm25_pkl is not None else None
         reviews = None
         if reviews_path is not None:
@@ -500,8 +503,8 @@ class SearchEngine:
             import pandas as pd
             if os.path.exists(str(reviews_path)):
                 reviews = pd.read_parquet(reviews_path)
-        return cls(meta, Vn, blob["corpus"] if blob else None, [str(x) for x in blob["skus"]] if blob else None,
-                   reviews=reviews, **kw)
+        return cls(meta, V, blob["corpus"] if blob else None, [str(x) for x in blob["skus"]] if blob else None,
+                   reviews=reviews, normalize=True, **kw)
 
     def search(self, args):
         """The numeric core of search(args) (app/test.py:228-309); returns the top-k DataFrame."""

@@ -176,7 +176,10 @@ class HybridIndex:
                  vocab_size: int = 0, n_reviews=None, avg_stars=None, device: str | torch.device = "cuda:0",
                  row_offset: int = 0, stats: Optional[BM25Stats] = None, k1: float = K1_DEFAULT,
                  b: float = B_DEFAULT, epsilon: float = EPSILON_DEFAULT, tile_docs: int = DEFAULT_TILE_DOCS,
-                 make_bf16: bool = True, postings: Optional[HostPostings] = None, forward_index: bool = True):
+                 make_bf16: bool = True, postings: Optional[HostPostings] = None, forward_index: bool = True,
+                 normalize: bool = False):
+        """`normalize=True`: `emb` holds the raw rows of product_emb.npy; they are L2-normalised on the device
+        exactly like the reference does at load (rr_normalize_rows), fused with the bf16 copy."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RRError("HybridIndex needs a CUDA device (no CPU fallback)")
@@ -189,13 +192,24 @@ class HybridIndex:
         self.row_offset = int(row_offset)
         self.dim_pad = 0
         self.emb_bf16 = None
+        if normalize and self.n_docs:
+            if self.emb.data_ptr() == (emb.data_ptr() if isinstance(emb, torch.Tensor) else 0):
+                self.emb = self.emb.clone()                      # never normalise the caller's tensor in place
+            bf = None
+            if make_bf16:
+                self.dim_pad = (self.dim + 63) // 64 * 64
+                bf = torch.empty((self.n_docs, self.dim_pad), dtype=torch.bfloat16, device=self.device)
+            check(self.lib.rr_normalize_rows(_ptr(self.emb), self.n_docs, self.dim, _ptr(self.emb), _ptr(bf), self.dim_pad,
+                                             _ptr(None), self.device.index or 0, _stream()))
+            self.emb_bf16 = bf
         self.max_row_norm = float(torch.linalg.vector_norm(self.emb, dim=1).max().item()) if self.n_docs else 0.0
-        if make_bf16:
+        if make_bf16 and self.emb_bf16 is None:
             self.dim_pad = (self.dim + 63) // 64 * 64
-            bf = torch.zeros((self.n_docs, self.dim_pad), dtype=torch.bfloat16, device=self.device)
-            step = 1 << 20
-            for r in range(0, self.n_docs, step):
-                bf[r:r + step, :self.dim] = self.emb[r:r + step].to(torch.bfloat16)   # round-to-nearest-even
+            bf = torch.empty((self.n_docs, self.dim_pad), dtype=torch.bfloat16, device=self.device)
+            if self.n_docs:
+                # bf16 copy only (rows already normalised by the caller): same kernel, norms not applied
+                check(self.lib.rr_bf16_rows(_ptr(self.emb), self.n_docs, self.dim, _ptr(bf), self.dim_pad,
+                                            self.device.index or 0, _stream()))
             self.emb_bf16 = bf
 
         self.vocab_size = 0

@@ -68,7 +68,7 @@ WORKER = textwrap.dedent('''
         assert np.allclose(scores[order], ref_sims, atol=1e-6)
     dist.barrier()
     dist.destroy_process_group()
-    print("rank", rank, "ok")
+    print(f"rank {rank} ok", flush=True)
 ''')
 
 

@@ -71,7 +71,7 @@ WORKER = textwrap.dedent('''
             whole.close()
     dist.barrier()
     dist.destroy_process_group()
-    print("rank", rank, "ok")
+    print(f"rank {rank} ok", flush=True)
 ''')
 
 

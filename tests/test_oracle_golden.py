@@ -97,3 +97,8 @@ def test_search_drivers_match_reference(cases, world):
         np.testing.assert_array_equal(pool["_prior"].values, np.float64(c["pool_prior"]))
         assert top["sku"].tolist() == c["top_skus"]
     assert n_cli == 18 and n_st == 24
+
+
+@pytest.mark.parametrize("D", [7, 100, 130, 384, 768])
+def test_l2_normalize_long_rows(prim, D):
+    np.testing.assert_array_equal(P.l2_normalize(prim[f"l2big_in_{D}"]), prim[f"l2big_out_{D}"])

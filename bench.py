@@ -33,6 +33,12 @@ CONFIGS = {
                workload="configs[2]: 10M products x 384-d, 50k-vocab BM25, batch 4096, hybrid top-100, row-sharded"),
     "c2": dict(docs=1_000_000, dim=384, vocab=50_000, batch=1024, terms=4, k=100,
                workload="configs[1]: 1M products x 384-d, 50k-vocab BM25, batch 1024, hybrid top-100"),
+    # BASELINE.json configs[4]: dense-heavy, top-1000 for the reranker (pool = 1000); needs 8 GPUs at full size
+    # (use --docs 6250000 --gpus 1 to time one of its eight row shards)
+    "c5": dict(docs=50_000_000, dim=768, vocab=50_000, batch=8192, terms=4, k=1000,
+               weights=dict(w_dense=0.8, w_bm25=0.1, w_prior=0.1),
+               metric="hybrid top-1000 queries/sec at 50M x 768 docs",
+               workload="configs[4]: 50M products x 768-d dense-heavy (w_dense 0.8), batch 8192, top-1000, row-sharded"),
 }
 METRIC = "hybrid top-100 queries/sec at 10M x 384 docs"
 UNIT = "queries/s"
@@ -53,6 +59,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-queries", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sparse-queries", type=int, default=32, help="queries of the BM25 get_scores sweep")
+    ap.add_argument("--query-groups", type=int, default=1,
+                    help="Q query groups x (gpus/Q) row shards (dist.GridSearcher); 1 = plain row sharding")
     return ap.parse_args()
 
 
@@ -275,21 +283,26 @@ def main():
     N, D, V, B, L, K = cfg["docs"], cfg["dim"], cfg["vocab"], cfg["batch"], cfg["terms"], cfg["k"]
     if B % world:
         raise SystemExit("batch must be a multiple of the number of GPUs")
-    row0 = N * rank // world
-    n_local = N * (rank + 1) // world - row0
+    Q = args.query_groups
+    if Q < 1 or world % Q:
+        raise SystemExit("--query-groups must divide the number of GPUs")
+    searcher = rr.dist.GridSearcher(None, Q) if world > 1 else None      # creates the process sub-groups (collective)
+    qg, shard, R = rr.dist.GridSearcher.layout(rank, world, Q)
+    row0 = N * shard // R
+    n_local = N * (shard + 1) // R - row0
     t_setup = time.perf_counter()
     emb, offs, toks, nrev, avg = device_shard(cfg, row0, n_local, dev)
-    # global BM25 statistics
+    # global BM25 statistics (every query group holds the whole corpus: reduce inside the row group)
     tok_counts = torch.tensor([int(offs[-1])], dtype=torch.int64, device=dev)
     pos0 = 0
-    if world > 1:
-        allc = [torch.zeros_like(tok_counts) for _ in range(world)]
-        dist.all_gather(allc, tok_counts)
-        pos0 = int(sum(int(c.item()) for c in allc[:rank]))
+    if R > 1:
+        allc = [torch.zeros_like(tok_counts) for _ in range(R)]
+        dist.all_gather(allc, tok_counts, group=searcher.row_group)
+        pos0 = int(sum(int(c.item()) for c in allc[:shard]))
     stats = eng.BM25Stats.local(offs, toks, V, token_pos0=pos0)
     local_df = stats.df.copy()
-    if world > 1:
-        rr.dist.all_reduce_stats(stats, device=dev)
+    if R > 1:
+        rr.dist.all_reduce_stats(stats, group=searcher.row_group, device=dev)
     stats.finalize()
     ix = eng.HybridIndex(emb, offs, toks, V, nrev, avg, device=dev, row_offset=row0, stats=stats)
     del emb
@@ -307,12 +320,15 @@ def main():
     del toks
     setup_s = time.perf_counter() - t_setup
 
-    fusion = eng.Fusion(k=K, rerank_k=0, w_dense=0.55, w_bm25=0.20, w_rerank=0.0, w_prior=0.20, w_best=0.0,
-                        prior_C=20.0, min_reviews=8, driver="streamlit")
+    wts = dict(w_dense=0.55, w_bm25=0.20, w_prior=0.20) | cfg.get("weights", {})
+    fusion = eng.Fusion(k=K, rerank_k=0, w_rerank=0.0, w_best=0.0, prior_C=20.0, min_reviews=8, driver="streamlit", **wts)
     q_dev = torch.from_numpy(q_np).to(dev)
     qt_dev = torch.from_numpy(qt_np).to(dev)
     nt_dev = torch.from_numpy(nt_np).to(dev)
-    searcher = rr.dist.ShardedSearcher(ix) if world > 1 else None
+    if searcher is not None:
+        searcher.ix = ix
+        if searcher.inner is not None:
+            searcher.inner.ix = ix
 
     def step_device():
         if searcher is None:
@@ -437,7 +453,7 @@ def main():
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
     roofline = None
     if dom == "tc_filter":
-        flops = 2.0 * B * n_local * D
+        flops = 2.0 * (B // Q) * n_local * D            # this GPU: its query group's slice x its row shard
         t = kernels[dom]["ms_per_step"] / 1000.0
         ach = flops / t / 1e12
         tr = load_traffic("tc_filter_kernel")
@@ -454,7 +470,7 @@ def main():
                     "algorithmic_flops_per_launch_avg": flops / max(n_l, 1.0),
                     "avg_launch_ms": kernels[dom]["ms_per_step"] / max(n_l, 1.0)}
     elif dom == "dense_gemv":
-        groups = (B + 7) // 8
+        groups = (B // Q + 7) // 8
         nbytes = 4.0 * D * n_local * groups
         t = kernels[dom]["ms_per_step"] / 1000.0
         ach = nbytes / t / 1e9
@@ -477,12 +493,12 @@ def main():
         cpu_base = cpu_baseline_obj(cfg, args, times[1:])
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": cfg.get("metric", METRIC), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "dtype_note": "bf16 tensor-core shortlist (fp32 accumulate), exact f32 rescoring, f32/f64 fusion as the reference",
         "config": {"workload": cfg["workload"], "docs": N, "docs_per_gpu": n_local, "dim": D, "vocab": V, "batch": B,
-                   "query_terms": L, "k": K, "pool": fusion.pool, "parallelism": f"row-sharded x{world}",
+                   "query_terms": L, "k": K, "pool": fusion.pool, "weights": wts, "parallelism": f"row-sharded x{R}" + (f", query groups x{Q}" if Q > 1 else ""),
                    "l2": "inputs larger than L2 (bf16 corpus shard read every step)",
                    "dense_path": dstats, "setup_s": setup_s},
         "roofline": roofline, "kernels": kernels, "profiled_ms_per_step": profiled_ms_per_step, "sparse": sparse,

@@ -181,3 +181,66 @@ class ShardedSearcher:
             rows[idx[:nf]] = r2[:nf]
             final[idx[:nf]] = f2[:nf]
         return rows, final
+
+
+class GridSearcher:
+    """Row shards x query groups.  The `world` ranks form Q query groups of R = world/Q ranks (rank = g*R + s);
+    every query group holds the WHOLE corpus cut into R row shards and answers its own slice of the batch with the
+    ShardedSearcher protocol inside the group, so the per-query work a shard does (shortlist selection, exact
+    rescoring, candidate BM25 -- proportional to the batch, not to the shard) is divided by Q as well.  Q = 1 is
+    the plain row-sharded search; Q = world is pure query sharding (corpus replicated, no exchange).  Results are
+    identical for every (R, Q) because each query is answered by an exact search over the whole corpus.
+
+    Collective construction: every rank of `dist.group.WORLD` must create the searcher (it creates the sub-groups)."""
+
+    def __init__(self, index, query_groups: int = 1, round1_pool: Optional[int] = None):
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+        self.Q = int(query_groups)
+        if self.Q < 1 or self.world % self.Q:
+            raise ValueError("query_groups must divide the world size")
+        self.R = self.world // self.Q
+        self.g, self.s = divmod(self.rank, self.R)
+        self.row_group = self.col_group = None
+        for g in range(self.Q):                         # new_group is collective: every rank creates every group
+            grp = dist.new_group([g * self.R + s for s in range(self.R)]) if self.R > 1 else None
+            if g == self.g:
+                self.row_group = grp
+        for s in range(self.R):
+            grp = dist.new_group([g * self.R + s for g in range(self.Q)]) if self.Q > 1 else None
+            if s == self.s:
+                self.col_group = grp
+        self.ix = index
+        self.inner = ShardedSearcher(index, group=self.row_group, round1_pool=round1_pool) if self.R > 1 else None
+        self.last_repeated = 0
+
+    @staticmethod
+    def layout(rank: int, world: int, query_groups: int) -> Tuple[int, int, int]:
+        """(query group, row shard, rows shards per group) of a rank."""
+        R = world // query_groups
+        g, s = divmod(rank, R)
+        return g, s, R
+
+    def search(self, q: torch.Tensor, term_ids: Optional[torch.Tensor], n_terms: Optional[torch.Tensor], fusion,
+               mode: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        B, k = int(q.shape[0]), fusion.k
+        if B % self.world:
+            raise ValueError("batch size must be a multiple of the world size")
+        Bq = B // self.Q
+        lo = self.g * Bq
+        qs = q[lo:lo + Bq]
+        ts = None if term_ids is None else term_ids[lo:lo + Bq]
+        ns = None if n_terms is None else n_terms[lo:lo + Bq]
+        if self.inner is not None:
+            rows, final = self.inner.search(qs, ts, ns, fusion, mode)
+            self.last_repeated = self.inner.last_repeated
+        else:
+            rows, final = self.ix.hybrid_search(qs, ts, ns, fusion, mode=mode)
+        if self.Q == 1:
+            return rows, final
+        mine = torch.cat([rows.reshape(-1).view(torch.uint8), final.reshape(-1).view(torch.uint8)])
+        out = torch.empty((self.Q, mine.numel()), dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(out.view(-1), mine, group=self.col_group)
+        all_rows = out[:, :Bq * k * 8].view(torch.int64).reshape(B, k)
+        all_final = out[:, Bq * k * 8:].view(torch.float32).reshape(B, k)
+        return all_rows, all_final

@@ -69,6 +69,29 @@ WORKER = textwrap.dedent('''
             assert torch.equal(rows, r1), (mode, int((rows != r1).sum()))
             assert torch.equal(final, f1), mode
             whole.close()
+    # ---- row shards x query groups: same answers for every layout ------------------------------------------
+    qd, qtd, ntd = torch.from_numpy(q).to(dev), torch.from_numpy(qt).to(dev), torch.from_numpy(nt).to(dev)
+    plain = rr.dist.ShardedSearcher(ix)
+    ref_rows, ref_final = plain.search(qd, qtd, ntd, fusion, mode=rr._lib.RR_DENSE_TENSOR)
+    for Q in [x for x in (2, 4) if world % x == 0]:
+        grid = rr.dist.GridSearcher(None, Q)
+        g, s, R = rr.dist.GridSearcher.layout(rank, world, Q)
+        r0, r1 = N * s // R, N * (s + 1) // R
+        o2 = full.doc_offsets[r0:r1 + 1] - full.doc_offsets[r0]
+        t2 = full.token_ids[full.doc_offsets[r0]:full.doc_offsets[r1]]
+        st2 = rr.engine.BM25Stats.local(o2, t2, V, token_pos0=int(full.doc_offsets[r0]))
+        if R > 1:
+            rr.dist.all_reduce_stats(st2, group=grid.row_group, device=dev)
+        st2.finalize()
+        ix2 = rr.engine.HybridIndex(full.emb[r0:r1], o2, t2, V, full.n_reviews[r0:r1], full.avg_stars[r0:r1],
+                                    device=dev, row_offset=r0, stats=st2)
+        grid.ix = ix2
+        if grid.inner is not None:
+            grid.inner.ix = ix2
+        rows, final = grid.search(qd, qtd, ntd, fusion, mode=rr._lib.RR_DENSE_TENSOR)
+        assert torch.equal(rows, ref_rows) and torch.equal(final, ref_final), ("grid", Q)
+        print(f"rank {rank} grid Q={Q} R={R} ok", flush=True)
+        ix2.close()
     dist.barrier()
     dist.destroy_process_group()
     print(f"rank {rank} ok", flush=True)

@@ -117,7 +117,26 @@ struct rr_index {
     DeviceBuf staging;    // *_host entry points
     rr_tc_state* tc = nullptr;
     rr_dense_stats stats{};
+    // the scratch buffers above are shared by all callers of the handle: a call that uses them on another stream
+    // than the previous one first waits for the previous call's work (the mutex only serialises the host side)
+    cudaEvent_t fence = nullptr;
+    cudaStream_t fence_stream = nullptr;
+    bool fence_armed = false;
 };
+
+namespace {
+struct ScratchFence {
+    rr_index* ix;
+    cudaStream_t s;
+    ScratchFence(rr_index* ix_, cudaStream_t s_) : ix(ix_), s(s_) {
+        if (!ix->fence) cudaEventCreateWithFlags(&ix->fence, cudaEventDisableTiming);
+        if (ix->fence && ix->fence_armed && ix->fence_stream != s) cudaStreamWaitEvent(s, ix->fence, 0);
+    }
+    ~ScratchFence() {
+        if (ix->fence && cudaEventRecord(ix->fence, s) == cudaSuccess) { ix->fence_stream = s; ix->fence_armed = true; }
+    }
+};
+}  // namespace
 
 namespace {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -169,6 +188,7 @@ extern "C" void rr_index_destroy(rr_index* ix) {
     ix->tuples.release();
     ix->staging.release();
     rr_tc_destroy(ix->tc);
+    if (ix->fence) cudaEventDestroy(ix->fence);
     delete ix;
 }
 
@@ -183,7 +203,9 @@ extern "C" int rr_dense_last_stats(rr_index* ix, rr_dense_stats* out) {
 // ---------------------------------------------------------------------------------------------
 extern "C" int rr_bm25_get_scores(rr_index* ix, const int32_t* d_term_ids, const int32_t* d_n_terms, int32_t B,
                                   int32_t l_max, float* d_out, int64_t ld_out, rr_stream stream) {
-    if (!ix || !d_out || B < 0 || l_max < 0) return rr_fail(RR_EINVAL, "rr_bm25_get_scores: bad argument");
+    if (!ix || B < 0 || l_max < 0) return rr_fail(RR_EINVAL, "rr_bm25_get_scores: bad argument");
+    if (B == 0) return RR_OK;                           // an empty batch has no output buffer to check
+    if (!d_out) return rr_fail(RR_EINVAL, "rr_bm25_get_scores: bad argument");
     if (ld_out < ix->d.n_docs || (ld_out & 3) || (reinterpret_cast<uintptr_t>(d_out) & 15))
         return rr_fail(RR_EINVAL, "rr_bm25_get_scores: ld_out must be >= n_docs and a multiple of 4, d_out 16-byte aligned");
     if (B == 0) return RR_OK;
@@ -286,6 +308,7 @@ extern "C" int rr_dense_topk(rr_index* ix, const float* d_q, int32_t B, int32_t 
     if (B == 0) return RR_OK;
     std::lock_guard<std::mutex> lock(ix->mu);
     RR_CUDA(cudaSetDevice(ix->device));
+    ScratchFence fence(ix, static_cast<cudaStream_t>(stream));
     return dense_topk_locked(ix, d_q, B, pool, mode, d_idx, d_sims, d_count, static_cast<cudaStream_t>(stream));
 }
 
@@ -324,6 +347,7 @@ extern "C" int rr_shard_tuples(rr_index* ix, const float* d_q, const int32_t* d_
     if (m > 8192) return rr_fail(RR_EINVAL, "rr_shard_tuples: m larger than 8192 is not supported");
     std::lock_guard<std::mutex> lock(ix->mu);
     RR_CUDA(cudaSetDevice(ix->device));
+    ScratchFence fence(ix, static_cast<cudaStream_t>(stream));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t bm = (size_t)B * m;
     RR_TRY(ix->tuples.ensure(align_up(bm * 8, 256) + align_up(bm * 4, 256) + 2 * align_up((size_t)B * 4, 256)));
@@ -451,6 +475,7 @@ extern "C" int rr_hybrid_search(rr_index* ix, const float* d_q, const int32_t* d
     if (B == 0) return RR_OK;
     std::lock_guard<std::mutex> lock(ix->mu);
     RR_CUDA(cudaSetDevice(ix->device));
+    ScratchFence fence(ix, static_cast<cudaStream_t>(stream));
     return hybrid_locked(ix, d_q, d_term_ids, d_n_terms, B, l_max, fp, dense_mode, d_top_row, d_top_final,
                          static_cast<cudaStream_t>(stream));
 }
@@ -462,6 +487,7 @@ extern "C" int rr_hybrid_search_host(rr_index* ix, const float* h_q, const int32
     if (B == 0) return RR_OK;
     std::lock_guard<std::mutex> lock(ix->mu);
     RR_CUDA(cudaSetDevice(ix->device));
+    ScratchFence fence(ix, static_cast<cudaStream_t>(stream));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t q_bytes = sizeof(float) * (size_t)B * ix->d.dim;
     const bool have_terms = h_term_ids && h_n_terms && l_max > 0;

@@ -1,0 +1,100 @@
+"""Error behaviour and re-entrancy of the C-ABI: every call returns a code and a thread-local message
+(the Python layer raises RRError), nothing aborts or falls back; one index handle is called concurrently from
+several Python threads the way Streamlit sessions share a cached resource (app/app_product_search.py:53,71,119)."""
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rr():
+    import review_recommender_b200 as rr
+    return rr
+
+
+def test_bad_arguments_raise_with_a_message():
+    import torch
+    rr = _rr()
+    c = rr.synth.make_corpus(3000, 64, 400)
+    ix = rr.engine.HybridIndex(c.emb, c.doc_offsets, c.token_ids, 400, c.n_reviews, c.avg_stars, make_bf16=False)
+    q = rr.synth.queries(4, 64)
+    with pytest.raises(rr._lib.RRError, match="dim"):
+        ix.dense_topk(rr.synth.queries(2, 32), 10)
+    with pytest.raises(rr._lib.RRError, match="8192"):
+        ix.dense_topk(q, 9000)
+    with pytest.raises(rr._lib.RRError, match="bf16"):
+        ix.dense_topk(q, 10, rr._lib.RR_DENSE_TENSOR)              # tensor path asked for, no bf16 copy uploaded
+    with pytest.raises(rr._lib.RRError):
+        rr.engine.GateIndex(["a"], [["x"]] * 33)                    # more than 32 fixed groups
+    # the handle is still usable after errors
+    idx, sims, cnt = ix.dense_topk(q, 10)
+    assert int(cnt.min()) == 10 and torch.isfinite(sims).all()
+    # unknown / out-of-range term ids contribute nothing; an empty batch is a no-op
+    ids = np.array([[-1, 400, 10**6, 5]], dtype=np.int32)
+    s = ix.bm25_get_scores(ids, np.array([4], dtype=np.int32))
+    s5 = ix.bm25_get_scores(np.array([[5]], dtype=np.int32), np.array([1], dtype=np.int32))
+    assert torch.equal(s, s5)
+    assert ix.bm25_get_scores(np.zeros((0, 1), np.int32), np.zeros(0, np.int32)).shape[0] == 0
+    ix.close()
+
+
+def test_concurrent_calls_on_one_handle():
+    import torch
+    rr = _rr()
+    n, d, v = 80_000, 128, 3000
+    c = rr.synth.make_corpus(n, d, v)
+    ix = rr.engine.HybridIndex(c.emb, c.doc_offsets, c.token_ids, v, c.n_reviews, c.avg_stars)
+    fusion = rr.engine.Fusion(k=20, rerank_k=0, w_rerank=0.0, w_best=0.0)
+    batches = []
+    for t in range(6):
+        b = 40 + 8 * t
+        q = np.roll(rr.synth.queries(b, d), t, axis=0)
+        qt = rr.synth.query_terms(b, 4, c.doc_offsets, c.token_ids, v).astype(np.int32)
+        batches.append((q, qt, np.full(b, 4, dtype=np.int32)))
+    serial = [ix.hybrid_search_host(*bt, fusion) for bt in batches]
+    out, errs = [None] * len(batches), []
+
+    def work(i):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for _ in range(3):
+                    out[i] = ix.hybrid_search_host(*batches[i], fusion)
+        except Exception as e:                                       # pragma: no cover
+            errs.append(e)
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(batches))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errs, errs
+    for (r0, f0), (r1, f1) in zip(serial, out):
+        np.testing.assert_array_equal(r0, r1)
+        np.testing.assert_array_equal(f0, f1)
+
+    # device-pointer entry point (no stream sync inside): calls from different threads on different streams share the
+    # handle's scratch buffers and must still not interfere (cross-stream fence inside the library)
+    dev_out = [None] * len(batches)
+
+    def work_dev(i):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                q, qt, nt = (torch.from_numpy(x).cuda() for x in batches[i])
+                for _ in range(5):
+                    r, f = ix.hybrid_search(q, qt, nt, fusion, mode=rr._lib.RR_DENSE_EXACT if i % 2 else rr._lib.RR_DENSE_TENSOR)
+                st.synchronize()
+                dev_out[i] = (r.cpu().numpy(), f.cpu().numpy())
+        except Exception as e:                                       # pragma: no cover
+            errs.append(e)
+    threads = [threading.Thread(target=work_dev, args=(i,)) for i in range(len(batches))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errs, errs
+    for (r0, f0), (r1, f1) in zip(serial, dev_out):
+        np.testing.assert_array_equal(r0, r1)
+        np.testing.assert_array_equal(f0, f1)
+    ix.close()

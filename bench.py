@@ -31,6 +31,11 @@ CONFIGS = {
     # BASELINE.json configs[2]: the configuration the metric is quoted on (fits one B200: 23 GB)
     "c3": dict(docs=10_000_000, dim=384, vocab=50_000, batch=4096, terms=4, k=100,
                workload="configs[2]: 10M products x 384-d, 50k-vocab BM25, batch 4096, hybrid top-100, row-sharded"),
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case (single query, top-10); here mainly for
+    # `--impl reference --config c1`, which then times the WHOLE workload instead of a scaled sample
+    "c1": dict(docs=10_000, dim=384, vocab=20_000, batch=1, terms=4, k=10,
+               metric="hybrid top-10 queries/sec at 10k x 384 docs",
+               workload="configs[0]: 10k products x 384-d, 20k-vocab BM25, single-query hybrid top-10"),
     "c2": dict(docs=1_000_000, dim=384, vocab=50_000, batch=1024, terms=4, k=100,
                workload="configs[1]: 1M products x 384-d, 50k-vocab BM25, batch 1024, hybrid top-100"),
     # BASELINE.json configs[4]: dense-heavy, top-1000 for the reranker (pool = 1000); needs 8 GPUs at full size
@@ -59,6 +64,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-queries", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sparse-queries", type=int, default=32, help="queries of the BM25 get_scores sweep")
+    ap.add_argument("--in-flight", type=int, default=1,
+                    help="batches in flight in the device-resident loop (2 = consecutive steps alternate between two "
+                         "handles / CUDA streams over the same index, so one step's tail overlaps the next step's GEMM)")
     ap.add_argument("--query-groups", type=int, default=1,
                     help="Q query groups x (gpus/Q) row shards (dist.GridSearcher); 1 = plain row sharding")
     return ap.parse_args()
@@ -149,7 +157,7 @@ def run_reference(args, cfg):
     base = cpu_baseline_obj(cfg, args, timed)
     ms = 1000.0 * statistics.mean(timed)
     line = {
-        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": cfg.get("metric", METRIC), "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["workload"], "docs": cfg["docs"], "dim": cfg["dim"], "vocab": cfg["vocab"],
@@ -252,6 +260,7 @@ class ClockSampler:
 def main():
     args = parse_args()
     cfg = dict(CONFIGS[args.config])
+    args.cpu_sample_docs = min(args.cpu_sample_docs, args.docs or cfg["docs"])
     if args.docs:
         cfg["docs"] = args.docs
         cfg["workload"] += f" [debug override: docs={args.docs}]"
@@ -330,10 +339,35 @@ def main():
         if searcher.inner is not None:
             searcher.inner.ix = ix
 
+    # single GPU: every step is enqueued without a host synchronisation (hybrid_search_begin) and completed by
+    # token.result(); with --in-flight 2 consecutive steps alternate between two handles / streams over the same index
+    # tensors, so the tail of step i (rescoring, candidate BM25, fusion) overlaps the GEMM of step i+1
+    import collections
+    lanes = [(ix, torch.cuda.current_stream())]
+    if args.in_flight > 1 and searcher is None:
+        lanes += [(ix.view(), torch.cuda.Stream()) for _ in range(args.in_flight - 1)]
+    step_no = [0]
+    pending = collections.deque()
+    last = [None]
+
     def step_device():
-        if searcher is None:
-            return ix.hybrid_search(q_dev, qt_dev, nt_dev, fusion, mode=args.dense_mode)
-        return searcher.search(q_dev, qt_dev, nt_dev, fusion, mode=args.dense_mode)
+        if searcher is not None:
+            last[0] = searcher.search(q_dev, qt_dev, nt_dev, fusion, mode=args.dense_mode)
+            return last[0]
+        h, st = lanes[step_no[0] % len(lanes)]
+        step_no[0] += 1
+        with torch.cuda.stream(st):
+            pending.append(h.hybrid_search_begin(q_dev, qt_dev, nt_dev, fusion, mode=args.dense_mode))
+        if len(pending) >= len(lanes):
+            last[0] = pending.popleft().result()
+        return last[0]
+
+    def drain():
+        while pending:
+            last[0] = pending.popleft().result()
+        for _, st in lanes[1:]:
+            torch.cuda.current_stream().wait_stream(st)
+        return last[0]
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -348,19 +382,46 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- sparse get_scores sweep (K1, HBM-bound): bytes = 8 per posting + 4 per doc ------------------
+    sparse = None
+    nsq = min(args.sparse_queries, B)
+    if nsq > 0 and rank == 0:
+        ids = qt_dev[:nsq].contiguous()
+        nts = nt_dev[:nsq].contiguous()
+        for _ in range(2):
+            ix.bm25_get_scores(ids, nts)
+        torch.cuda.synchronize(dev)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            ix.bm25_get_scores(ids, nts)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        sp_ms = e0.elapsed_time(e1) / reps
+        postings = int(local_df[qt_np[:nsq]].sum())
+        sp_bytes = 8 * postings + 4 * n_local * nsq
+        sparse = {"kernel": "bm25_tile_scores_kernel (get_scores mode)", "queries": nsq, "docs": n_local,
+                  "postings_per_query": postings / nsq, "ms": sp_ms, "achieved": sp_bytes / sp_ms / 1e6,
+                  "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": sp_bytes / sp_ms / 1e6 / peaks["hbm_gbs"],
+                  "queries_per_s": nsq / (sp_ms / 1000.0)}
+    sync_all()
+
     # ---- device-resident timing ------------------------------------------------------------------
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()          # sampled from the warm-up on: every sample is taken under the same load
     for _ in range(args.warmup):
         step_device()
+    drain()
     sync_all()
     eng.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
     for _ in range(args.steps):
-        rows, final = step_device()
+        step_device()
+    rows, final = drain()
     e1.record()
     sync_all()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -375,6 +436,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step_device()
+    drain()
     e1.record()
     sync_all()
     profiled_ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
@@ -421,31 +483,6 @@ def main():
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e_value = B / (e2e_ms / 1000.0)
     same = bool(np.array_equal(rows_pin.numpy(), rows.cpu().numpy())) if rank == 0 else True
-
-    # ---- sparse get_scores sweep (K1, HBM-bound): bytes = 8 per posting + 4 per doc ------------------
-    sparse = None
-    nsq = min(args.sparse_queries, B)
-    if nsq > 0 and rank == 0:
-        ids = qt_dev[:nsq].contiguous()
-        nts = nt_dev[:nsq].contiguous()
-        for _ in range(2):
-            ix.bm25_get_scores(ids, nts)
-        torch.cuda.synchronize(dev)
-        reps = 3
-        e0.record()
-        for _ in range(reps):
-            ix.bm25_get_scores(ids, nts)
-        e1.record()
-        torch.cuda.synchronize(dev)
-        sp_ms = e0.elapsed_time(e1) / reps
-        postings = int(local_df[qt_np[:nsq]].sum())
-        sp_bytes = 8 * postings + 4 * n_local * nsq
-        sparse = {"kernel": "bm25_tile_scores_kernel (get_scores mode)", "queries": nsq, "docs": n_local,
-                  "postings_per_query": postings / nsq, "ms": sp_ms, "achieved": sp_bytes / sp_ms / 1e6,
-                  "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": sp_bytes / sp_ms / 1e6 / peaks["hbm_gbs"],
-                  "queries_per_s": nsq / (sp_ms / 1000.0)}
-    if world > 1:
-        dist.barrier()
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
@@ -500,7 +537,7 @@ def main():
         "config": {"workload": cfg["workload"], "docs": N, "docs_per_gpu": n_local, "dim": D, "vocab": V, "batch": B,
                    "query_terms": L, "k": K, "pool": fusion.pool, "weights": wts, "parallelism": f"row-sharded x{R}" + (f", query groups x{Q}" if Q > 1 else ""),
                    "l2": "inputs larger than L2 (bf16 corpus shard read every step)",
-                   "dense_path": dstats, "setup_s": setup_s},
+                   "dense_path": dstats, "setup_s": setup_s, "batches_in_flight": len(lanes)},
         "roofline": roofline, "kernels": kernels, "profiled_ms_per_step": profiled_ms_per_step, "sparse": sparse,
         "cpu_baseline": cpu_base,
         "clocks": {"sm_mhz": clock_info.get("sm_mhz"), "sm_max_mhz": clock_info.get("sm_max_mhz"),

@@ -205,6 +205,14 @@ int rr_hybrid_search(rr_index*, const float* d_q, const int32_t* d_term_ids, con
                      int32_t B, int32_t l_max, const rr_fusion_params*, int32_t dense_mode,
                      int64_t* d_top_row, float* d_top_final, rr_stream);
 
+/* Same without ANY host synchronisation, for callers that keep several batches in flight: the tensor path's
+ * read-back of the uncertified count is replaced by d_uncertified int32[B] (1 = this query's dense pool could not be
+ * proven exact from the bf16 shortlist; its outputs are best-effort and the caller must repeat the query through
+ * rr_hybrid_search, which redoes such queries on the exact fp32 path; 0 = final). */
+int rr_hybrid_search_deferred(rr_index*, const float* d_q, const int32_t* d_term_ids, const int32_t* d_n_terms,
+                              int32_t B, int32_t l_max, const rr_fusion_params*, int32_t dense_mode,
+                              int64_t* d_top_row, float* d_top_final, int32_t* d_uncertified, rr_stream);
+
 /* Same, HOST buffers in and out (pinned or pageable); copies are issued on the stream inside
  * the call and the stream is synchronised before returning.  This is the call the reference's
  * search functions make through the Python binding. */

@@ -85,6 +85,8 @@ SIGNATURES = {
     "rr_shard_tuples": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "rr_hybrid_search": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(FusionParams), C.c_int32,
                                    _P, _P, _P]),
+    "rr_hybrid_search_deferred": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(FusionParams), C.c_int32,
+                                            _P, _P, _P, _P]),
     "rr_hybrid_search_host": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(FusionParams), C.c_int32,
                                         _P, _P, _P]),
     "rr_launch_count": (C.c_int64, [C.c_int]),

@@ -438,7 +438,7 @@ extern "C" int rr_gate_fixed_bitmaps(const uint8_t* d_text, const int64_t* d_tex
 // ---------------------------------------------------------------------------------------------
 static int hybrid_locked(rr_index* ix, const float* d_q, const int32_t* d_term_ids, const int32_t* d_n_terms,
                          int32_t B, int32_t l_max, const rr_fusion_params* fp, int32_t dense_mode,
-                         int64_t* d_top_row, float* d_top_final, cudaStream_t s) {
+                         int64_t* d_top_row, float* d_top_final, cudaStream_t s, int32_t* d_uncertified = nullptr) {
     const int pool = fp->pool;
     const size_t bp = (size_t)B * pool;
     size_t bytes = 0;
@@ -455,7 +455,7 @@ static int hybrid_locked(rr_index* ix, const float* d_q, const int32_t* d_term_i
     double* nrev = c.take<double>(bp);
     double* avg = c.take<double>(bp);
     int32_t* count = c.take<int32_t>((size_t)B);
-    RR_TRY(dense_topk_locked(ix, d_q, B, pool, dense_mode, cand, dense, count, s));
+    RR_TRY(dense_topk_locked(ix, d_q, B, pool, dense_mode, cand, dense, count, s, d_uncertified));
     RR_TRY(candidates_locked(ix, d_term_ids, d_n_terms, B, l_max, cand, pool, bm25, nrev, avg, grow, s));
     return rr_launch_fuse(fp, B, pool, 1, 0, count, dense, bm25, nrev, avg, grow, nullptr, nullptr, nullptr, d_top_row,
                           d_top_final, nullptr, nullptr, nullptr, s);
@@ -478,6 +478,20 @@ extern "C" int rr_hybrid_search(rr_index* ix, const float* d_q, const int32_t* d
     ScratchFence fence(ix, static_cast<cudaStream_t>(stream));
     return hybrid_locked(ix, d_q, d_term_ids, d_n_terms, B, l_max, fp, dense_mode, d_top_row, d_top_final,
                          static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rr_hybrid_search_deferred(rr_index* ix, const float* d_q, const int32_t* d_term_ids,
+                                         const int32_t* d_n_terms, int32_t B, int32_t l_max, const rr_fusion_params* fp,
+                                         int32_t dense_mode, int64_t* d_top_row, float* d_top_final,
+                                         int32_t* d_uncertified, rr_stream stream) {
+    RR_TRY(check_hybrid_args(ix, d_q, fp, d_top_row, d_top_final, B));
+    if (!d_uncertified) return rr_fail(RR_EINVAL, "rr_hybrid_search_deferred: d_uncertified is required");
+    if (B == 0) return RR_OK;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    RR_CUDA(cudaSetDevice(ix->device));
+    ScratchFence fence(ix, static_cast<cudaStream_t>(stream));
+    return hybrid_locked(ix, d_q, d_term_ids, d_n_terms, B, l_max, fp, dense_mode, d_top_row, d_top_final,
+                         static_cast<cudaStream_t>(stream), d_uncertified);
 }
 
 extern "C" int rr_hybrid_search_host(rr_index* ix, const float* h_q, const int32_t* h_term_ids,

@@ -255,9 +255,20 @@ class HybridIndex:
                          self.fwd_data.data_ptr() if self.fwd_data is not None else None,
                          self.n_reviews.data_ptr() if self.n_reviews is not None else None,
                          self.avg_stars.data_ptr() if self.avg_stars is not None else None)
+        self._desc = desc
         h = C.c_void_p(0)
         check(self.lib.rr_index_create(C.byref(h), C.byref(desc), self.device.index or 0))
         self._h = h
+
+    def view(self) -> "HybridIndex":
+        """A second handle over the SAME device buffers with its own scratch memory, so that two batches can be in
+        flight on two CUDA streams (the handle only borrows the index tensors; this object keeps them alive)."""
+        import copy
+        other = copy.copy(self)                      # shares every tensor attribute
+        h = C.c_void_p(0)
+        check(self.lib.rr_index_create(C.byref(h), C.byref(self._desc), self.device.index or 0))
+        other._h = h
+        return other
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -419,6 +430,28 @@ class HybridIndex:
                                         _ptr(rows), _ptr(final), _stream()))
         return rows, final
 
+    def hybrid_search_begin(self, q, term_ids, n_terms, fusion: Fusion, mode: int = _lib.RR_DENSE_AUTO) -> "PendingSearch":
+        """Enqueue a whole hybrid search on the current stream without any host synchronisation and return a token;
+        `token.result()` waits for it and repeats the (rare) queries the tensor path could not certify.  Several
+        tokens may be pending at once, each on its own stream and its own handle (`view()`)."""
+        q = self._dev(q, torch.float32)
+        B = int(q.shape[0])
+        lmax = 0
+        if term_ids is not None:
+            term_ids = self._dev(term_ids, torch.int32)
+            n_terms = self._dev(n_terms, torch.int32)
+            lmax = int(term_ids.shape[1])
+        p = fusion.to_c()
+        rows = torch.empty((B, fusion.k), dtype=torch.int64, device=self.device)
+        final = torch.empty((B, fusion.k), dtype=torch.float32, device=self.device)
+        unc = torch.empty((B,), dtype=torch.int32, device=self.device)
+        check(self.lib.rr_hybrid_search_deferred(self._h, _ptr(q), _ptr(term_ids), _ptr(n_terms), B, lmax, C.byref(p),
+                                                 mode, _ptr(rows), _ptr(final), _ptr(unc), _stream()))
+        n_unc = unc.sum()                                        # enqueued on the same stream, read in result()
+        done = torch.cuda.Event()
+        done.record()
+        return PendingSearch(self, q, term_ids, n_terms, fusion, mode, rows, final, unc, n_unc, done)
+
     def hybrid_search_host(self, q: np.ndarray, term_ids: Optional[np.ndarray], n_terms: Optional[np.ndarray],
                            fusion: Fusion, mode: int = _lib.RR_DENSE_AUTO, out_rows: Optional[np.ndarray] = None,
                            out_final: Optional[np.ndarray] = None):
@@ -437,6 +470,32 @@ class HybridIndex:
         check(self.lib.rr_hybrid_search_host(self._h, _ptr(q), _ptr(term_ids), _ptr(n_terms), B, lmax, C.byref(p),
                                              mode, _ptr(rows), _ptr(final), _stream()))
         return rows, final
+
+
+class PendingSearch:
+    """A hybrid search in flight (HybridIndex.hybrid_search_begin)."""
+
+    def __init__(self, ix, q, term_ids, n_terms, fusion, mode, rows, final, unc, n_unc, done):
+        self.ix, self.q, self.term_ids, self.n_terms, self.fusion, self.mode = ix, q, term_ids, n_terms, fusion, mode
+        self.rows, self.final, self.unc, self.n_unc, self.done = rows, final, unc, n_unc, done
+        self.repeated = 0
+
+    def result(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(global rows int64[B, k], final float32[B, k]) -- exact, like hybrid_search."""
+        if self.done is not None:
+            self.done.synchronize()
+            self.done = None
+            nf = int(self.n_unc.item())
+            self.repeated = nf
+            if nf > 0:
+                idx = torch.nonzero(self.unc, as_tuple=False).view(-1)
+                r2, f2 = self.ix.hybrid_search(self.q[idx].contiguous(),
+                                               None if self.term_ids is None else self.term_ids[idx].contiguous(),
+                                               None if self.n_terms is None else self.n_terms[idx].contiguous(),
+                                               self.fusion, self.mode)
+                self.rows[idx] = r2
+                self.final[idx] = f2
+        return self.rows, self.final
 
 
 class ReviewIndex:

@@ -98,3 +98,41 @@ def test_concurrent_calls_on_one_handle():
         np.testing.assert_array_equal(r0, r1)
         np.testing.assert_array_equal(f0, f1)
     ix.close()
+
+
+def test_batches_in_flight_on_two_handles_equal_the_synchronous_search():
+    """hybrid_search_begin / PendingSearch.result on two handles (view()) and two streams over the same index
+    tensors; a query the tensor path cannot certify (600 near-duplicates of its target) is repeated exactly."""
+    import torch
+    rr = _rr()
+    n, d, v = 90_000, 128, 3000
+    c = rr.synth.make_corpus(n, d, v)
+    rng = np.random.default_rng(3)
+    base = c.emb[17].copy()
+    for r in range(1000, 1600):
+        x = base + 1e-4 * rng.standard_normal(d).astype(np.float32)
+        c.emb[r] = x / np.linalg.norm(x)
+    ix = rr.engine.HybridIndex(c.emb, c.doc_offsets, c.token_ids, v, c.n_reviews, c.avg_stars)
+    lanes = [(ix, torch.cuda.Stream()), (ix.view(), torch.cuda.Stream())]
+    fusion = rr.engine.Fusion(k=50, rerank_k=0, w_rerank=0.0, w_best=0.0)
+    batches = []
+    for t in range(5):
+        q = np.roll(rr.synth.queries(64, d), 3 * t, axis=0)
+        if t == 2:
+            q[5] = base
+        qt = np.roll(rr.synth.query_terms(64, 4, c.doc_offsets, c.token_ids, v).astype(np.int32), t, axis=0)
+        batches.append(tuple(torch.from_numpy(x).cuda() for x in (q, qt, np.full(64, 4, dtype=np.int32))))
+    want = [ix.hybrid_search(*b, fusion, mode=rr._lib.RR_DENSE_EXACT) for b in batches]
+    torch.cuda.synchronize()
+    tokens = []
+    for i, b in enumerate(batches):
+        h, st = lanes[i % 2]
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            tokens.append(h.hybrid_search_begin(*b, fusion, mode=rr._lib.RR_DENSE_TENSOR))
+    got = [t.result() for t in tokens]
+    assert tokens[2].repeated >= 1 and tokens[0].repeated == 0
+    for (r0, f0), (r1, f1) in zip(want, got):
+        assert torch.equal(r0, r1) and torch.equal(f0, f1)
+    lanes[1][0].close()
+    ix.close()

@@ -384,6 +384,45 @@ __device__ void bitonic_keys_desc(unsigned long long* key, int n_pad) {
     }
 }
 
+
+// Gather of one query's keys into shared memory with GU loads in flight per thread: positions [0, kc) come from
+// the kept list, positions [kc, total) from the candidate sub-lists (sub-list r by binary search over s_off).
+// The addresses of a batch are computed first, then all loads are issued, then the keys are converted and stored
+// (r02 profile: the one-load-per-iteration loop left the selection waiting on a chain of global-load latencies).
+template <int GU>
+__device__ __forceinline__ void gather_query_keys(unsigned long long* sk, const unsigned long long* kept,
+                                                  int kc, const unsigned long long* cand, const int* s_off,
+                                                  int n_sub, int cap_sub, int total, int t, int stride) {
+    for (int p0 = t; p0 < total; p0 += stride * GU) {
+        const unsigned long long* src[GU];
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            const int p = p0 + u * stride;
+            src[u] = nullptr;
+            if (p < kc) {
+                src[u] = kept + p;
+            } else if (p < total) {
+                int lo_r = 0, hi_r = n_sub;                 // largest r with s_off[r] <= p
+                while (hi_r - lo_r > 1) { const int mid = (lo_r + hi_r) >> 1; if (s_off[mid] <= p) lo_r = mid; else hi_r = mid; }
+                src[u] = cand + (size_t)lo_r * cap_sub + (p - s_off[lo_r]);
+            }
+        }
+        unsigned long long raw[GU];
+#pragma unroll
+        for (int u = 0; u < GU; ++u) raw[u] = src[u] ? *src[u] : 0ull;     // plain loads: the kept list is rewritten below
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            const int p = p0 + u * stride;
+            if (p < kc) {
+                sk[p] = raw[u];
+            } else if (p < total) {
+                const unsigned long long k = rr_make_key(__uint_as_float((uint32_t)raw[u]), (uint32_t)(raw[u] >> 32));   // {score bits, doc}
+                sk[p] = k ? k : 1ull;
+            }
+        }
+    }
+}
+
 // Per query: pool = kept list + the candidate sub-lists of this segment.  Keeps the KP largest 64-bit keys
 // (unordered) and raises tau to the KP-th score.  Selection is an MSB-first radix select over the key
 // bits below the common prefix of (min, max): 8-bit digits, warp-aggregated shared-memory histogram,
@@ -441,16 +480,8 @@ tc_select_kernel(const unsigned long long* __restrict__ cand_keys, unsigned* __r
     const int total = min(total_all, sort_cap);
 
     // gather into shared memory
-    for (int i = tid; i < kc; i += 256) sk[i] = kept_keys[(size_t)q * KP + i];
-    // flat gather: position p -> (sub-list r by binary search over the offsets, entry p - off[r]); every load
-    // is independent, so a thread keeps several in flight instead of walking the sub-lists one by one
-    for (int p = kc + tid; p < total; p += 256) {
-        int lo_r = 0, hi_r = n_sub;                 // largest r with s_off[r] <= p
-        while (hi_r - lo_r > 1) { const int mid = (lo_r + hi_r) >> 1; if (s_off[mid] <= p) lo_r = mid; else hi_r = mid; }
-        const unsigned long long raw = cand_keys[((size_t)q * n_sub + lo_r) * cap_sub + (p - s_off[lo_r])];
-        unsigned long long k = rr_make_key(__uint_as_float((uint32_t)raw), (uint32_t)(raw >> 32));   // {score bits, doc}
-        sk[p] = k ? k : 1ull;
-    }
+    gather_query_keys<8>(sk, kept_keys + (size_t)q * KP, kc, cand_keys + (size_t)q * n_sub * cap_sub, s_off, n_sub, cap_sub,
+                         total, tid, 256);
     __syncthreads();
 
     int newk = total;
@@ -602,14 +633,8 @@ tc_select_warp_kernel(const unsigned long long* __restrict__ cand_keys, unsigned
     __syncwarp();
 
     // ---- gather ----------------------------------------------------------------------------------
-    for (int i = lane; i < kc; i += 32) sk[i] = kept_keys[(size_t)q * KP + i];
-    for (int p = kc + lane; p < total; p += 32) {      // flat gather, independent loads (see tc_select_kernel)
-        int lo_r = 0, hi_r = n_sub;
-        while (hi_r - lo_r > 1) { const int mid = (lo_r + hi_r) >> 1; if (s_off[mid] <= p) lo_r = mid; else hi_r = mid; }
-        const unsigned long long raw = cand_keys[((size_t)q * n_sub + lo_r) * cap_sub + (p - s_off[lo_r])];
-        const unsigned long long k = rr_make_key(__uint_as_float((uint32_t)raw), (uint32_t)(raw >> 32));
-        sk[p] = k ? k : 1ull;
-    }
+    gather_query_keys<8>(sk, kept_keys + (size_t)q * KP, kc, cand_keys + (size_t)q * n_sub * cap_sub, s_off, n_sub, cap_sub,
+                         total, lane, 32);
     __syncwarp();
 
     int newk = total;

@@ -523,12 +523,7 @@ tc_select_kernel(const unsigned long long* __restrict__ cand_keys, unsigned* __r
                     in = bits == 0 || (k >> (64 - bits)) == prefix;
                     b = (unsigned)((k >> shift) & ((1u << dig) - 1u));
                 }
-                // warp-aggregated histogram update
-                const unsigned act = __ballot_sync(0xffffffffu, in);
-                if (in) {
-                    const unsigned peers = __match_any_sync(act, b);
-                    if ((int)(__ffs(peers) - 1) == lane) atomicAdd(&s_hist[b], (unsigned)__popc(peers));
-                }
+                if (in) atomicAdd(&s_hist[b], 1u);
             }
             __syncthreads();
             if (wid == 0) {
@@ -667,11 +662,9 @@ tc_select_warp_kernel(const unsigned long long* __restrict__ cand_keys, unsigned
                     in = bits == 0 || (k >> (64 - bits)) == prefix;
                     b = (unsigned)((k >> shift) & ((1u << dig) - 1u));
                 }
-                const unsigned act = __ballot_sync(FULL, in);
-                if (in) {
-                    const unsigned peers = __match_any_sync(act, b);
-                    if ((int)(__ffs(peers) - 1) == lane) atomicAdd(&hist[b], (unsigned)__popc(peers));
-                }
+                // plain shared-memory atomics: the r02 source profile had the warp-aggregated version
+                // (match.any + ffs + popc) waiting on MATCH for most of the kernel
+                if (in) atomicAdd(&hist[b], 1u);
             }
             __syncwarp();
             unsigned loc[8], sum = 0;

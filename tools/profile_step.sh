@@ -10,5 +10,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:tc_filter -s 12 -c 2 -o gpurun_out/prof_tc_filter_r2 -f $CMD > gpurun_out/ncu_b.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:bm25_tile -c 1 -o gpurun_out/prof_bm25_tile_r2 -f $CMD > gpurun_out/ncu_c.log 2>&1
 ncu --set full --clock-control none --import-source on -k "regex:tc_select|rescore|tc_finalize|bm25_candidates|fuse_topk" -s 7 -c 5 -o gpurun_out/prof_small_r2 -f $CMD > gpurun_out/ncu_d.log 2>&1
-tail -2 gpurun_out/ncu_a.log gpurun_out/ncu_b.log gpurun_out/ncu_c.log gpurun_out/ncu_d.log
+for f in a b c d; do tail -n 2 gpurun_out/ncu_$f.log; done
 ls -la gpurun_out/*.ncu-rep

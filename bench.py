@@ -197,16 +197,15 @@ def device_shard(cfg, row0: int, n: int, dev):
         u = torch.rand(int(ln.sum().item()), generator=g, device=dev, dtype=torch.float64)
         tok = torch.searchsorted(cdf, u).clamp_(max=V - 1).to(torch.int32)
         start = int(ln[:within].sum().item())
-        lens_all.append(ln[within:].cpu().numpy())
-        toks_all.append(tok[start:].cpu().numpy())
+        lens_all.append(ln[within:].clone())
+        toks_all.append(tok[start:].clone())
         del u, tok, ln
         r += take
-    lens = np.concatenate(lens_all)
-    offs = np.zeros(n + 1, dtype=np.int64)
-    np.cumsum(lens, out=offs[1:])
-    toks = np.concatenate(toks_all)
+    offs = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(torch.cat(lens_all), 0, out=offs[1:])
+    toks = torch.cat(toks_all)
     nrev, avg = syn.metadata(n, row0)
-    return emb, offs, toks, nrev, avg
+    return emb, offs, toks, nrev, avg          # the tokenised corpus stays in device memory (GpuIndexBuilder)
 
 
 class ClockSampler:
@@ -302,23 +301,29 @@ def main():
     t_setup = time.perf_counter()
     emb, offs, toks, nrev, avg = device_shard(cfg, row0, n_local, dev)
     # global BM25 statistics (every query group holds the whole corpus: reduce inside the row group)
-    tok_counts = torch.tensor([int(offs[-1])], dtype=torch.int64, device=dev)
+    tok_counts = torch.tensor([int(offs[-1].item())], dtype=torch.int64, device=dev)
     pos0 = 0
     if R > 1:
         allc = [torch.zeros_like(tok_counts) for _ in range(R)]
         dist.all_gather(allc, tok_counts, group=searcher.row_group)
         pos0 = int(sum(int(c.item()) for c in allc[:shard]))
-    stats = eng.BM25Stats.local(offs, toks, V, token_pos0=pos0)
+    # index build on the GPU: token keys -> unique (doc, term) pairs -> statistics -> impacts, forward index, postings
+    t_build = time.perf_counter()
+    builder = eng.GpuIndexBuilder(offs, toks, V)
+    stats = builder.local_stats(token_pos0=pos0)
     local_df = stats.df.copy()
     if R > 1:
         rr.dist.all_reduce_stats(stats, group=searcher.row_group, device=dev)
     stats.finalize()
-    ix = eng.HybridIndex(emb, offs, toks, V, nrev, avg, device=dev, row_offset=row0, stats=stats)
+    postings = builder.finish(stats)
+    torch.cuda.synchronize(dev)
+    build_s = time.perf_counter() - t_build
+    ix = eng.HybridIndex(emb, None, None, V, nrev, avg, device=dev, row_offset=row0, stats=stats, postings=postings)
     del emb
     # queries (identical on every rank)
     q_np = rr.synth.queries(B, D)
     if rank == 0:
-        qt_np = rr.synth.query_terms(B, L, offs, toks, V).astype(np.int32)
+        qt_np = rr.synth.query_terms(B, L, offs.cpu().numpy(), toks.cpu().numpy(), V).astype(np.int32)
     else:
         qt_np = np.zeros((B, L), dtype=np.int32)
     if world > 1:
@@ -537,7 +542,7 @@ def main():
         "config": {"workload": cfg["workload"], "docs": N, "docs_per_gpu": n_local, "dim": D, "vocab": V, "batch": B,
                    "query_terms": L, "k": K, "pool": fusion.pool, "weights": wts, "parallelism": f"row-sharded x{R}" + (f", query groups x{Q}" if Q > 1 else ""),
                    "l2": "inputs larger than L2 (bf16 corpus shard read every step)",
-                   "dense_path": dstats, "setup_s": setup_s, "batches_in_flight": len(lanes)},
+                   "dense_path": dstats, "setup_s": setup_s, "index_build_s": build_s, "batches_in_flight": len(lanes)},
         "roofline": roofline, "kernels": kernels, "profiled_ms_per_step": profiled_ms_per_step, "sparse": sparse,
         "cpu_baseline": cpu_base,
         "clocks": {"sm_mhz": clock_info.get("sm_mhz"), "sm_max_mhz": clock_info.get("sm_max_mhz"),

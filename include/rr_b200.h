@@ -81,6 +81,24 @@ const uint64_t* rr_postings_fwd_off(const rr_postings*);    /* host, n_docs+1 */
 const uint64_t* rr_postings_fwd_data(const rr_postings*);   /* host, fwd_off[n_docs] entries */
 void            rr_postings_free(rr_postings*);
 
+/* The same construction on the GPU, for a tokenised corpus that is already in device memory (bit-identical output).
+ * begin:  sorts the (doc, term) token keys, finds the unique pairs and the tile geometry; reports how many forward
+ *         entries (n_unique) and postings incl. alignment padding (n_postings) the caller has to allocate;
+ * stats:  adds this shard's df to d_df int64[V] (caller-zeroed) and lowers d_first_pos int64[V] (caller-initialised to
+ *         INT64_MAX) -- all-reduce them over the shards, then rr_bm25_idf on the host;
+ * finish: impacts, forward index, tile-blocked postings, tile_base[n_tiles+1], blk_off[n_tiles*(V+1)], fwd_off[n_docs+1]
+ *         into caller-owned device buffers.  d_doc_offsets / d_token_ids must stay valid until finish.
+ * vocab_size <= 2^24, tile_docs <= 65536 (multiple of 4), fewer than 2^31 tokens per shard. */
+typedef struct rr_bm25_gpu_builder rr_bm25_gpu_builder;
+int rr_bm25_gpu_build_begin(rr_bm25_gpu_builder** out, const int64_t* d_doc_offsets, const int32_t* d_token_ids,
+                            int64_t n_docs, int64_t n_tokens, int32_t vocab_size, int32_t tile_docs,
+                            int64_t* n_unique_out, int64_t* n_postings_out, int32_t* n_tiles_out, int device, rr_stream);
+int rr_bm25_gpu_build_stats(rr_bm25_gpu_builder*, int64_t token_pos0, int64_t* d_df, int64_t* d_first_pos, rr_stream);
+int rr_bm25_gpu_build_finish(rr_bm25_gpu_builder*, const double* d_idf, double avgdl, double k1, double b,
+                             uint64_t* d_postings, uint64_t* d_tile_base, uint32_t* d_blk_off,
+                             uint64_t* d_fwd_off, uint64_t* d_fwd_data, rr_stream);
+void rr_bm25_gpu_build_free(rr_bm25_gpu_builder*);
+
 /* ------------------------------------------------------------------------------------------
  * Device index
  * ---------------------------------------------------------------------------------------- */

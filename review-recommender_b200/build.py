@@ -11,7 +11,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "librr_b200.so"
-SOURCES = ["api.cu", "bm25_kernels.cu", "dense_exact.cu", "dense_tc.cu", "fuse.cu", "gate.cu", "prep.cu", "bm25_build.cpp"]
+SOURCES = ["api.cu", "bm25_kernels.cu", "dense_exact.cu", "dense_tc.cu", "fuse.cu", "gate.cu", "prep.cu", "bm25_build_gpu.cu", "bm25_build.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "--extended-lambda",
               "-Xcompiler", "-fPIC,-O3,-ffp-contract=off,-pthread", "-Xptxas", "-v"]

@@ -848,8 +848,18 @@ struct rr_tc_state {
     CUtensorMap tmap_c;
     const void* tmap_c_base = nullptr;
     Buf q_bf16, qnorm, cand_keys, cand_cnt, kept_keys, kept_cnt, tau, overflow, rows, exact, flags, fb_q, fb_idx, fb_sims, fb_cnt;
-    int* h_nflag = nullptr;   // pinned
+    int* h_nflag = nullptr;   // pinned: [0] read-back of the synchronous path, [1] of the last deferred call
     bool attr_set = false;
+    // Shortlist feedback.  How many rows lie within the certification margin of the pool-th score depends on the data
+    // (score spread ~ 1/sqrt(D) for unit rows: 768-d needs a longer shortlist than 384-d for the same pool).  When
+    // more than 1/64 of a batch comes back uncertified, the shortlist of the following calls on this index grows.
+    double boost = 1.0;
+    cudaEvent_t deferred_done = nullptr;
+    bool deferred_pending = false;
+    int deferred_batch = 0;
+    void feedback(int n_flagged, int B) {
+        if (n_flagged > std::max(1, B / 64)) boost = std::min(boost * 1.3, 4.0);
+    }
 };
 
 bool rr_tc_supported(int cc_major, int) { return cc_major == 10; }
@@ -860,6 +870,7 @@ void rr_tc_destroy(rr_tc_state* s) {
                    &s->rows, &s->exact, &s->flags, &s->fb_q, &s->fb_idx, &s->fb_sims, &s->fb_cnt})
         b->release();
     if (s->h_nflag) cudaFreeHost(s->h_nflag);
+    if (s->deferred_done) cudaEventDestroy(s->deferred_done);
     delete s;
 }
 
@@ -887,15 +898,21 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
                      rr_exact_fn exact_fn, void* exact_ctx, int32_t* d_uncertified, cudaStream_t s) {
     if (d->dim_pad > TC_MAX_KB_STREAMED * TC_BK)
         return rr_fail(RR_EUNSUPPORTED, "tensor path supports dim <= %d in this build", TC_MAX_KB_STREAMED * TC_BK);
-    const int growth = KP_growth(shortlist_size(pool));
-    const int KP = shortlist_size(pool);
-    if (KP > TC_SORT_MAX / 4) return rr_fail(RR_EUNSUPPORTED, "tensor path supports pool <= %d", (int)(TC_SORT_MAX / 4 / 2.6));
+    if (shortlist_size(pool) > TC_SORT_MAX / 4)
+        return rr_fail(RR_EUNSUPPORTED, "tensor path supports pool <= %d", (int)(TC_SORT_MAX / 4 / 2.6));
     if (!*state) {
         *state = new (std::nothrow) rr_tc_state();
         if (!*state) return rr_fail(RR_ENOMEM, "out of host memory");
     }
     rr_tc_state* st = *state;
-    if (!st->h_nflag) RR_CUDA(cudaMallocHost(&st->h_nflag, sizeof(int)));
+    if (!st->h_nflag) RR_CUDA(cudaMallocHost(&st->h_nflag, 2 * sizeof(int)));
+    if (!st->deferred_done) RR_CUDA(cudaEventCreateWithFlags(&st->deferred_done, cudaEventDisableTiming));
+    if (st->deferred_pending && cudaEventQuery(st->deferred_done) == cudaSuccess) {
+        st->feedback(st->h_nflag[1], st->deferred_batch);          // outcome of the previous sync-free call
+        st->deferred_pending = false;
+    }
+    const int KP = std::min(TC_SORT_MAX / 4, (int)((std::ceil(shortlist_size(pool) * st->boost) + 63) / 64) * 64);
+    const int growth = KP_growth(KP);
     if (!st->attr_set) {
         RR_CUDA(cudaFuncSetAttribute(tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
         RR_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SORT_MAX * 8));
@@ -1047,11 +1064,18 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
             stats->path = 2; stats->n_uncertified = -1; stats->n_overflow = 0; stats->shortlist = KP;
             stats->n_segments = n_segments; stats->eps = eps_rel;
         }
+        if (!st->deferred_pending) {       // feedback for the next call, read without ever blocking
+            RR_CUDA(cudaMemcpyAsync(st->h_nflag + 1, n_flagged, sizeof(int), cudaMemcpyDeviceToHost, s));
+            RR_CUDA(cudaEventRecord(st->deferred_done, s));
+            st->deferred_pending = true;
+            st->deferred_batch = B;
+        }
         return RR_OK;
     }
     RR_CUDA(cudaMemcpyAsync(st->h_nflag, n_flagged, sizeof(int), cudaMemcpyDeviceToHost, s));
     RR_CUDA(cudaStreamSynchronize(s));
     const int nf = *st->h_nflag;
+    st->feedback(nf, B);
     if (stats) {
         stats->path = 2; stats->n_uncertified = nf; stats->n_overflow = 0; stats->shortlist = KP;
         stats->n_segments = n_segments; stats->eps = eps_rel;

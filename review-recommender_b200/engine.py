@@ -131,6 +131,86 @@ def build_postings(doc_offsets: np.ndarray, token_ids: np.ndarray, stats: BM25St
     return HostPostings(data, tile_base, blk_off, n_tiles, tile_docs, stats.vocab_size, fwd_off, fwd_data)
 
 
+@dataclass
+class DevicePostings:
+    """The same index as HostPostings, built on the GPU (GpuIndexBuilder) and already resident in HBM."""
+    data: torch.Tensor        # int64[nnz]   {u32 doc, f32 impact}
+    tile_base: torch.Tensor   # int64[n_tiles+1]
+    blk_off: torch.Tensor     # int32[n_tiles*(V+1)]
+    n_tiles: int
+    tile_docs: int
+    vocab_size: int
+    fwd_off: torch.Tensor     # int64[N+1]
+    fwd_data: torch.Tensor    # int64[fwd_off[N]]  {u32 term, f32 impact}
+
+
+class GpuIndexBuilder:
+    """BM25Okapi.__init__ (app/test.py:156, app/app_product_search.py:142) for a tokenised corpus that already lives in
+    device memory: statistics, forward index and tile-blocked postings are built by rr_bm25_gpu_build_* and are
+    bit-identical to the host builder's.  Usage (row-sharded: all-reduce the statistics between the two calls):
+
+        b = GpuIndexBuilder(doc_offsets_dev, token_ids_dev, V)
+        stats = b.local_stats(token_pos0); [dist.all_reduce_stats(stats)]; stats.finalize()
+        postings = b.finish(stats)          # DevicePostings, pass as HybridIndex(postings=...)
+    """
+
+    def __init__(self, doc_offsets: torch.Tensor, token_ids: torch.Tensor, vocab_size: int,
+                 tile_docs: int = DEFAULT_TILE_DOCS):
+        self.lib = _lib.load()
+        if not (doc_offsets.is_cuda and token_ids.is_cuda):
+            raise RRError("GpuIndexBuilder needs device tensors (use build_postings for a host corpus)")
+        self.device = doc_offsets.device
+        self.doc_offsets = doc_offsets.to(torch.int64).contiguous()
+        self.token_ids = token_ids.to(torch.int32).contiguous()
+        self.n_docs = int(self.doc_offsets.numel()) - 1
+        self.n_tokens = int(self.token_ids.numel())
+        self.vocab_size, self.tile_docs = int(vocab_size), int(tile_docs)
+        nu, npost, nt = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+        h = C.c_void_p(0)
+        with torch.cuda.device(self.device):
+            check(self.lib.rr_bm25_gpu_build_begin(C.byref(h), _ptr(self.doc_offsets), _ptr(self.token_ids), self.n_docs,
+                                                   self.n_tokens, self.vocab_size, self.tile_docs, C.byref(nu), C.byref(npost),
+                                                   C.byref(nt), self.device.index or 0, _stream()))
+        self._h = h
+        self.n_unique, self.n_postings, self.n_tiles = int(nu.value), int(npost.value), int(nt.value)
+
+    def local_stats(self, token_pos0: int = 0) -> BM25Stats:
+        df = torch.zeros(self.vocab_size, dtype=torch.int64, device=self.device)
+        fp = torch.full((self.vocab_size,), INT64_MAX, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.rr_bm25_gpu_build_stats(self._h, int(token_pos0), _ptr(df), _ptr(fp), _stream()))
+        return BM25Stats(self.vocab_size, df.cpu().numpy(), fp.cpu().numpy(), self.n_tokens, self.n_docs)
+
+    def finish(self, stats: BM25Stats, k1: float = K1_DEFAULT, b: float = B_DEFAULT) -> DevicePostings:
+        if stats.idf is None:
+            raise RRError("BM25Stats.finalize() has not been called")
+        dev = self.device
+        idf = torch.from_numpy(np.ascontiguousarray(stats.idf, dtype=np.float64)).to(dev)
+        data = torch.empty(max(self.n_postings, 2), dtype=torch.int64, device=dev)
+        tile_base = torch.empty(self.n_tiles + 1, dtype=torch.int64, device=dev)
+        blk_off = torch.empty(self.n_tiles * (self.vocab_size + 1), dtype=torch.int32, device=dev)
+        fwd_off = torch.empty(self.n_docs + 1, dtype=torch.int64, device=dev)
+        fwd_data = torch.empty(max(self.n_unique, 1), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            check(self.lib.rr_bm25_gpu_build_finish(self._h, _ptr(idf), float(stats.avgdl), float(k1), float(b), _ptr(data),
+                                                    _ptr(tile_base), _ptr(blk_off), _ptr(fwd_off), _ptr(fwd_data), _stream()))
+            torch.cuda.current_stream().synchronize()            # `idf` and the builder scratch may be released now
+        self.close()
+        return DevicePostings(data[:max(self.n_postings, 2)], tile_base, blk_off, self.n_tiles, self.tile_docs, self.vocab_size,
+                              fwd_off, fwd_data)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.rr_bm25_gpu_build_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # --------------------------------------------------------------------------------------------
 # fusion parameters
 # --------------------------------------------------------------------------------------------
@@ -217,12 +297,25 @@ class HybridIndex:
         self.k1, self.b = k1, b
         self.post = self.tile_base = self.blk_off = self.fwd_off = self.fwd_data = None
         self.tile_docs, self.n_tiles = 0, 0
+        if postings is None and isinstance(doc_offsets, torch.Tensor) and doc_offsets.is_cuda and vocab_size > 0:
+            # corpus already in device memory: build the index on the GPU
+            gb = GpuIndexBuilder(doc_offsets, token_ids, vocab_size, tile_docs)
+            if stats is None:
+                stats = gb.local_stats().finalize(epsilon)
+                self.stats = stats
+            postings = gb.finish(stats, k1, b)
         if postings is None and doc_offsets is not None and vocab_size > 0:
             if stats is None:
                 stats = BM25Stats.local(doc_offsets, token_ids, vocab_size).finalize(epsilon)
                 self.stats = stats
             postings = build_postings(doc_offsets, token_ids, stats, k1, b, tile_docs)
-        if postings is not None:
+        if isinstance(postings, DevicePostings):
+            self.vocab_size = postings.vocab_size
+            self.tile_docs, self.n_tiles = postings.tile_docs, postings.n_tiles
+            self.post, self.tile_base, self.blk_off = postings.data, postings.tile_base, postings.blk_off
+            if forward_index:
+                self.fwd_off, self.fwd_data = postings.fwd_off, postings.fwd_data
+        elif postings is not None:
             self.vocab_size = postings.vocab_size
             self.tile_docs, self.n_tiles = postings.tile_docs, postings.n_tiles
             self.post = torch.from_numpy(postings.data.view(np.int64)).to(self.device)

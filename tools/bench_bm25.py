@@ -36,10 +36,13 @@ def main():
     t0 = time.perf_counter()
     emb, offs, toks, nrev, avg = B.device_shard(cfg, 0, args.docs, dev)
     t1 = time.perf_counter()
-    stats = rr.engine.BM25Stats.local(offs, toks, args.vocab).finalize()
-    ix = rr.engine.HybridIndex(emb, offs, toks, args.vocab, device=dev, stats=stats, tile_docs=args.tile_docs,
+    gb = rr.engine.GpuIndexBuilder(offs, toks, args.vocab, args.tile_docs)       # corpus is in device memory
+    stats = gb.local_stats().finalize()
+    ix = rr.engine.HybridIndex(emb, None, None, args.vocab, device=dev, stats=stats, postings=gb.finish(stats),
                                make_bf16=False)
+    torch.cuda.synchronize()
     t2 = time.perf_counter()
+    offs, toks = offs.cpu().numpy(), toks.cpu().numpy()
     peaks = B.load_peaks()
     bmax = max(int(b) for b in args.batches.split(","))
     qt = rr.synth.query_terms(bmax, args.terms, offs, toks, args.vocab).astype(np.int32)

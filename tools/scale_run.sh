@@ -2,7 +2,7 @@
 # usage: bash tools/scale_run.sh N  -- bench at N GPUs: plain row sharding, then the row-shard x query-group grids
 N=$1
 port=29600
-for Q in 1 2 4; do
+for Q in ${QS:-1 2 4}; do
   if [ $((N % Q)) -ne 0 ] || [ $Q -gt $N ]; then continue; fi
   port=$((port+1))
   out=gpurun_out/scale_g${N}_q${Q}

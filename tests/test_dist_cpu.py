@@ -87,3 +87,60 @@ def test_two_rank_exchange_and_stats(tmp_path):
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+
+
+GRID_WORKER = textwrap.dedent('''
+    import os, sys
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.environ["RR_REPO"])
+    import review_recommender_b200 as rr
+
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+
+    class FakeIndex:
+        """Stands in for the CUDA index: the 'answer' of query i is (i*10 + j, i + j/100)."""
+        def hybrid_search(self, q, term_ids, n_terms, fusion, mode=0):
+            ids = q[:, 0].to(torch.int64)
+            k = fusion.k
+            rows = ids[:, None] * 10 + torch.arange(k)[None, :]
+            final = ids[:, None].to(torch.float32) + torch.arange(k)[None, :].to(torch.float32) / 100
+            return rows, final
+
+    class F:
+        k, pool = 3, 5
+
+    B = 8
+    q = torch.arange(B, dtype=torch.float32)[:, None].repeat(1, 4)
+    for Q in (1, 2):
+        g, s, R = rr.dist.GridSearcher.layout(rank, world, Q)
+        assert (g, s, R) == (divmod(rank, world // Q) + (world // Q,))
+        if Q == 1:
+            continue            # R = 2 needs the CUDA kernels (tests/test_gpu_dist.py); here: groups only
+        grid = rr.dist.GridSearcher(FakeIndex(), Q)
+        assert grid.inner is None and grid.col_group is not None
+        rows, final = grid.search(q, None, None, F())
+        want_rows = torch.arange(B)[:, None] * 10 + torch.arange(3)[None, :]
+        assert torch.equal(rows, want_rows), rows
+        assert torch.allclose(final, torch.arange(B)[:, None].float() + torch.arange(3)[None, :].float() / 100)
+    dist.barrier()
+    dist.destroy_process_group()
+    print(f"rank {rank} grid ok", flush=True)
+''')
+
+
+def test_query_group_grid_on_two_ranks(tmp_path):
+    """GridSearcher plumbing (sub-groups, batch slicing, the column all-gather) with two gloo ranks and a stub index."""
+    script = tmp_path / "grid_worker.py"
+    script.write_text(GRID_WORKER)
+    env = dict(os.environ, RR_REPO=str(REPO), OMP_NUM_THREADS="1")
+    import socket
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "rank 0 grid ok" in r.stdout and "rank 1 grid ok" in r.stdout

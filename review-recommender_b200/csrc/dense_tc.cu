@@ -881,11 +881,13 @@ static int shortlist_size(int pool) {
     const char* env = getenv("RR_TC_SHORTLIST_FACTOR");
     double f = env ? atof(env) : 2.6;
     if (!(f >= 1.0)) f = 2.6;
-    // rows within the certification margin of the pool-th score: ~0.9*pool on unit-norm data, plus six
-    // standard deviations and a constant so that small pools (sharded round 1) certify as reliably as big ones
+    // rows within the certification margin of the pool-th score: ~0.9*pool on unit-norm 384-d data, plus five
+    // standard deviations and a constant so that small pools (sharded round 1) certify as reliably as big ones.
+    // This is only the starting point: the shortlist feedback (rr_tc_state::boost) lengthens it when the data
+    // needs more (wider rows, clustered catalogues).
     const double base = 1.9 * pool;
-    int kp = (int)std::ceil(std::max(pool * f, base + 6.0 * std::sqrt(base) + 16.0));
-    kp = (kp + 63) / 64 * 64;
+    int kp = (int)std::ceil(std::max(pool * f, base + 5.0 * std::sqrt(base) + 16.0));
+    kp = (kp + 31) / 32 * 32;
     return std::max(kp, 64);
 }
 
@@ -911,7 +913,7 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
         st->feedback(st->h_nflag[1], st->deferred_batch);          // outcome of the previous sync-free call
         st->deferred_pending = false;
     }
-    const int KP = std::min(TC_SORT_MAX / 4, (int)((std::ceil(shortlist_size(pool) * st->boost) + 63) / 64) * 64);
+    const int KP = std::min(TC_SORT_MAX / 4, (int)((std::ceil(shortlist_size(pool) * st->boost) + 31) / 32) * 32);
     const int growth = KP_growth(KP);
     if (!st->attr_set) {
         RR_CUDA(cudaFuncSetAttribute(tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));

@@ -4,24 +4,26 @@
 // (app/test.py:170, app/app_product_search.py:206) and behind the candidate gathers that follow
 // it (app/test.py:171-173, app/app_product_search.py:207-208).
 //
-// Layout (built by bm25_build.cpp): docs are cut into tiles of T docs.  Inside tile i the
+// Layout (built by bm25_build.cpp on the host or bm25_build_gpu.cu on the device): docs are cut into tiles of T docs.  Inside tile i the
 // postings {u32 doc, f32 impact} are grouped by term (doc ascending inside a term);
 // blk_off[i*(V+1)+t .. +t+1] bounds term t's segment relative to tile_base[i] (always even, so
 // a tile's postings start on a 16-byte boundary).
 //
 //  bm25_tile_scores_kernel   one CTA per (tile, query): T fp32 accumulators live in shared
 //      memory, the CTA streams the <= L segments of its query's terms with 16-byte loads
-//      (2 postings per load, double-buffered in registers so the next round's loads are in
-//      flight while this round is accumulated), adds impacts in QUERY-TERM ORDER (a barrier
+//      (2 postings per load, 4 loads in flight per thread; latency is hidden by 4 resident
+//      CTAs per SM), adds impacts in QUERY-TERM ORDER (a barrier
 //      separates consecutive terms, postings of one term hit distinct docs so plain
 //      read-modify-write is race free), then writes the tile's scores coalesced.
 //      HBM traffic = 8 B per posting of the query's terms + 4 B per doc: the algorithmic bytes.
 //      Summation order = the reference's (`score += ...` per query token), in fp32.
 //
-//  bm25_candidates_kernel    one thread per (query, candidate): binary search of the
-//      candidate's doc id inside each term segment of the doc's tile; same impacts, same
-//      order => bit-identical to the tile kernel at those docs.  Also gathers n_reviews /
-//      avg_stars / global row so that the fusion kernel gets complete tuples.
+//  bm25_candidates_kernel    one thread per (query, candidate): binary search of each query
+//      term in the candidate's forward list (or of the candidate's doc id inside the term's
+//      segment of the doc's tile when no forward index is loaded); same impacts, same order =>
+//      bit-identical to the tile kernel at those docs.  Also gathers n_reviews / avg_stars /
+//      global row so that the fusion kernel gets complete tuples, optionally straight into the
+//      all-to-all send buffer of a sharded search.
 #include <cstdlib>
 #include <type_traits>
 

@@ -11,7 +11,7 @@
 //                    256-doc tiles (UMMA N).  The 128 x D query tile is loaded once by TMA and
 //                    stays in shared memory; 256 x 64 corpus k-blocks stream through a 4-stage
 //                    TMA/mbarrier ring; one thread issues tcgen05.mma (K=16) into a double-
-//                    buffered TMEM accumulator (2 x 256 columns); four epilogue warps read the
+//                    buffered TMEM accumulator (2 x 256 columns); eight epilogue warps read the
 //                    accumulator with tcgen05.ld (thread = query row) and keep only scores
 //                    >= the query's running threshold tau, appended as 64-bit (score, doc) keys.
 //   tc_select_kernel per query: merge kept list + new candidates, keep the best k', raise tau to

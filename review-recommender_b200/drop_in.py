@@ -123,6 +123,28 @@ def _cosine_pool(qvec: np.ndarray, mat: np.ndarray, pool: int):
 # --------------------------------------------------------------------------------------------
 # sparse
 # --------------------------------------------------------------------------------------------
+def flatten_corpus(corpus: Sequence[Sequence[str]]):
+    """list of token lists -> (doc_offsets int64[N+1], token_ids int32[total], {token: id}) with ids assigned in
+    first-appearance order (the insertion order of rank_bm25's dicts).  One C-level pass (itertools.chain +
+    pandas.factorize) instead of a Python loop per token."""
+    import itertools
+    import pandas as pd
+    n = len(corpus)
+    lens = np.fromiter((len(d) for d in corpus), dtype=np.int64, count=n)
+    offs = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    flat = list(itertools.chain.from_iterable(corpus))
+    if not flat:
+        return offs, np.zeros(0, dtype=np.int32), {}
+    codes, uniques = pd.factorize(np.asarray(flat, dtype=object))
+    return offs, codes.astype(np.int32), {w: i for i, w in enumerate(uniques.tolist())}
+
+
+def _on_device(a: np.ndarray, device: str):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
 class BM25Okapi:
     """rank_bm25.BM25Okapi drop-in: same constructor and `get_scores(tokens) -> float64[N]`.
 
@@ -141,32 +163,22 @@ class BM25Okapi:
             corpus = [tokenizer(doc) for doc in corpus]
         self.k1, self.b, self.epsilon = k1, b, epsilon
         self.tokenizer = tokenizer
-        vocab: Dict[str, int] = {}
-        ids: List[int] = []
-        offs = [0]
-        for doc in corpus:
-            for w in doc:
-                i = vocab.get(w)
-                if i is None:
-                    i = len(vocab)
-                    vocab[w] = i
-                ids.append(i)
-            offs.append(len(ids))
-        self.corpus_size = len(offs) - 1
+        self._offs, self._ids, vocab = flatten_corpus(corpus)
+        self.corpus_size = len(self._offs) - 1
         if self.corpus_size == 0:
             raise ZeroDivisionError("division by zero")          # what rank_bm25 raises for an empty corpus
         self.vocab = vocab
-        self._offs = np.asarray(offs, dtype=np.int64)
-        self._ids = np.asarray(ids, dtype=np.int32)
         self.doc_len = np.diff(self._offs).tolist()
         v = max(1, len(vocab))
-        stats = engine.BM25Stats.local(self._offs, self._ids, v).finalize(epsilon)
+        # statistics, forward index and postings are built on the GPU from the integer ids
+        gb = engine.GpuIndexBuilder(_on_device(self._offs, device), _on_device(self._ids, device), v, tile_docs)
+        stats = gb.local_stats().finalize(epsilon)
         self.avgdl = stats.avgdl
         self.average_idf = stats.average_idf
         self.idf = {w: float(stats.idf[i]) for w, i in vocab.items()}
         placeholder = np.zeros((self.corpus_size, 4), dtype=np.float32)
-        self._ix = engine.HybridIndex(placeholder, self._offs, self._ids, v, device=device, stats=stats, k1=k1, b=b,
-                                      tile_docs=tile_docs, make_bf16=False)
+        self._ix = engine.HybridIndex(placeholder, None, None, v, device=device, stats=stats, k1=k1, b=b,
+                                      postings=gb.finish(stats, k1, b), make_bf16=False)
 
     def term_ids(self, tokens: Sequence[str]) -> List[int]:
         return [self.vocab.get(t, -1) for t in tokens]
@@ -285,30 +297,22 @@ class SearchEngine:
         if bm25_corpus is not None:
             # align BM25 documents to meta rows: by SKU (run_search, :207-208: last duplicate wins, missing -> 0)
             sku_to_doc = {str(s): i for i, s in enumerate(bm25_skus)}
-            ids: List[int] = []
-            o = [0]
             # term ids in first-appearance order OF THE BLOB (the library's dict order decides the idf mean)
-            for doc in bm25_corpus:
-                for w in doc:
-                    if w not in self.vocab:
-                        self.vocab[w] = len(self.vocab)
+            flat_offs, flat_ids, self.vocab = flatten_corpus(bm25_corpus)
             v = max(1, len(self.vocab))
-            flat_offs = [0]
-            flat_ids: List[int] = []
-            for doc in bm25_corpus:
-                flat_ids.extend(self.vocab[w] for w in doc)
-                flat_offs.append(len(flat_ids))
-            stats = engine.BM25Stats.local(np.asarray(flat_offs, dtype=np.int64), np.asarray(flat_ids, dtype=np.int32),
-                                           v).finalize()
-            for s in self.meta["sku"].astype(str).tolist():
-                d = sku_to_doc.get(s, -1)
-                if d >= 0:
-                    ids.extend(flat_ids[flat_offs[d]:flat_offs[d + 1]])
-                o.append(len(ids))
-            # document lengths / statistics are those of the blob; rows without a BM25 doc get no postings
-            offs, toks = np.asarray(o, dtype=np.int64), np.asarray(ids, dtype=np.int32)
+            stats = engine.BM25Stats.local(flat_offs, flat_ids, v).finalize()
+            # meta row r holds the tokens of BM25 document doc_of_row[r] (-1: no document, no postings)
+            doc_of_row = np.fromiter((sku_to_doc.get(s, -1) for s in self.meta["sku"].astype(str).tolist()),
+                                     dtype=np.int64, count=n)
+            lens = np.where(doc_of_row >= 0, np.diff(flat_offs)[np.maximum(doc_of_row, 0)], 0)
+            offs = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(lens, out=offs[1:])
+            src = np.repeat(flat_offs[np.maximum(doc_of_row, 0)] - offs[:-1], lens) + np.arange(int(offs[-1]), dtype=np.int64)
+            toks = flat_ids[src] if len(src) else np.zeros(0, dtype=np.int32)
+            # document lengths / statistics are those of the blob; the index itself is built on the GPU
             self._stats = stats
-            self.ix = engine.HybridIndex(Vn, offs, toks, v, nrev, avg, device=device, stats=stats, normalize=normalize)
+            self.ix = engine.HybridIndex(Vn, _on_device(offs, device), _on_device(toks, device), v, nrev, avg, device=device,
+                                         stats=stats, normalize=normalize)
         else:
             self.ix = engine.HybridIndex(Vn, n_reviews=nrev, avg_stars=avg, device=device, normalize=normalize)
 

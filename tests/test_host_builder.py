@@ -74,3 +74,22 @@ def test_sharded_stats_reduce_to_global(lib):
                                  a.total_tokens + b.total_tokens, a.n_docs + b.n_docs).finalize()
     np.testing.assert_array_equal(merged.idf, whole.idf)
     assert merged.avgdl == whole.avgdl and merged.average_idf == whole.average_idf
+
+
+def test_flatten_corpus_matches_the_dict_walk():
+    """drop_in.flatten_corpus (itertools.chain + pandas.factorize) assigns the ids a Python dict walk would
+    (first-appearance order, which rank_bm25's idf mean depends on), including empty documents."""
+    import review_recommender_b200 as rr
+    from oracle.bm25_okapi import flatten_corpus as dict_walk
+    offs, toks = rr.synth.corpus_tokens(2000, 300)
+    corpus = rr.synth.corpus_as_lists(offs, toks)
+    corpus[0] = []
+    corpus[7] = []
+    corpus.append(["new-token", "t1", "new-token"])
+    o1, i1, v1 = rr.drop_in.flatten_corpus(corpus)
+    o2, i2, v2 = dict_walk(corpus)
+    np.testing.assert_array_equal(o1, o2)
+    np.testing.assert_array_equal(i1, i2)
+    assert list(v1.keys()) == v2 and list(v1.values()) == list(range(len(v2)))
+    o3, i3, v3 = rr.drop_in.flatten_corpus([[], []])
+    assert o3.tolist() == [0, 0, 0] and i3.size == 0 and v3 == {}

@@ -257,12 +257,13 @@ int rr_launch_bm25_tile_scores(const uint64_t* d_postings, const uint64_t* d_til
                                cudaStream_t stream) {
     if (B <= 0 || n_tiles <= 0) return RR_OK;
     const size_t smem = (size_t)T * sizeof(float);
-    static size_t configured = 0;
-    if (configured == 0 || smem > configured) {
+    static RrSmemOptIn optin;
+    int dev = 0;
+    if (optin.needed(smem, &dev)) {
         RR_CUDA(cudaFuncSetAttribute(bm25_tile_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // without this the driver sizes the shared-memory carveout for ONE resident CTA (ncu r01: occupancy limit 1)
         RR_CUDA(cudaFuncSetAttribute(bm25_tile_scores_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        configured = smem > 0 ? smem : 1;
+        optin.done(smem, dev);
     }
     for (int b0 = 0; b0 < B; b0 += 65535) {
         const int nb = min(65535, B - b0);

@@ -142,10 +142,11 @@ int rr_launch_normalize_rows(const float* d_in, int64_t n_rows, int D, float* d_
     if (plan.n_leaves > PREP_MAX_LEAVES) return rr_fail(RR_EUNSUPPORTED, "rr_normalize_rows: dim %d too large", D);
     const size_t smem = sizeof(float) * (size_t)PREP_WARPS * (D + plan.n_leaves * 9);
     if (smem > 200 * 1024) return rr_fail(RR_EUNSUPPORTED, "rr_normalize_rows: dim %d too large", D);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static RrSmemOptIn optin;
+    int dev = 0;
+    if (smem > 48 * 1024 && optin.needed(smem, &dev)) {
         RR_CUDA(cudaFuncSetAttribute(normalize_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        optin.done(smem, dev);
     }
     RrProfScope prof(RR_PROF_MISC, stream);
     normalize_rows_kernel<<<(unsigned)((n_rows + PREP_WARPS - 1) / PREP_WARPS), PREP_WARPS * 32, smem, stream>>>(

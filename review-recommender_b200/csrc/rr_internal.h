@@ -39,6 +39,24 @@ inline void rr_count_launch(int n = 1) { g_rr_launches.fetch_add(n, std::memory_
         if (_rc != RR_OK) return _rc; \
     } while (0)
 
+// Per-device high-water mark of the dynamic shared memory a kernel has been opted in for.  cudaFuncSetAttribute is
+// per device, and launchers may be called from several threads (one per index handle), hence atomics.
+struct RrSmemOptIn {
+    std::atomic<size_t> cap[64];
+    // true if `bytes` exceeds what the current device was configured for; the caller then sets the attribute and
+    // calls done().  Racing callers may both set the attribute, which is harmless.
+    bool needed(size_t bytes, int* device) {
+        int d = 0;
+        cudaGetDevice(&d);
+        *device = d & 63;
+        return bytes + 1 > cap[*device].load(std::memory_order_acquire);
+    }
+    void done(size_t bytes, int device) {
+        size_t cur = cap[device].load(std::memory_order_relaxed);
+        while (cur < bytes + 1 && !cap[device].compare_exchange_weak(cur, bytes + 1, std::memory_order_release)) {}
+    }
+};
+
 // device-side timing of one kernel class (no-op unless rr_profile_enable(1))
 struct RrProfScope {
     int cls; cudaStream_t stream; void* rec;

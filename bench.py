@@ -458,20 +458,27 @@ def main():
     rows_pin = torch.empty((B, K), dtype=torch.int64).pin_memory()
     final_pin = torch.empty((B, K), dtype=torch.float32).pin_memory()
 
+    nb_q, nb_t, nb_n = q_np.nbytes, qt_np.nbytes, nt_np.nbytes
+    batch_pin = torch.empty(nb_q + nb_t + nb_n, dtype=torch.uint8).pin_memory()
+    batch_pin[:nb_q] = torch.from_numpy(q_np).view(-1).view(torch.uint8)
+    batch_pin[nb_q:nb_q + nb_t] = torch.from_numpy(qt_np).view(-1).view(torch.uint8)
+    batch_pin[nb_q + nb_t:] = torch.from_numpy(nt_np).view(-1).view(torch.uint8)
+    batch_dev = torch.empty_like(batch_pin, device=dev)
+    bq = batch_dev[:nb_q].view(torch.float32).view(B, D)
+    bqt = batch_dev[nb_q:nb_q + nb_t].view(torch.int32).view(B, L)
+    bnt = batch_dev[nb_q + nb_t:].view(torch.int32)
+
     def step_e2e():
         if searcher is None:
             ix.hybrid_search_host(q_pin.numpy(), qt_pin.numpy(), nt_pin.numpy(), fusion, mode=args.dense_mode,
                                   out_rows=rows_pin.numpy(), out_final=final_pin.numpy())
             return
-        # the query batch enters on rank 0 and is broadcast once; results are read back on rank 0
+        # the query batch (vectors | term ids | term counts, one packed buffer) enters on rank 0 and is broadcast
+        # ONCE; results are read back on rank 0
         if rank == 0:
-            q_dev.copy_(q_pin, non_blocking=True)
-            qt_dev.copy_(qt_pin, non_blocking=True)
-            nt_dev.copy_(nt_pin, non_blocking=True)
-        dist.broadcast(q_dev, 0)
-        dist.broadcast(qt_dev, 0)
-        dist.broadcast(nt_dev, 0)
-        r, f = searcher.search(q_dev, qt_dev, nt_dev, fusion, mode=args.dense_mode)
+            batch_dev.copy_(batch_pin, non_blocking=True)
+        dist.broadcast(batch_dev, 0)
+        r, f = searcher.search(bq, bqt, bnt, fusion, mode=args.dense_mode)
         if rank == 0:
             rows_pin.copy_(r, non_blocking=True)
             final_pin.copy_(f, non_blocking=True)

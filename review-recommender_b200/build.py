@@ -37,6 +37,19 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB
     objdir = HERE / "build"
     objdir.mkdir(exist_ok=True)
+    # several ranks of one job may get here at once: one builds, the others wait and then find the library current
+    import fcntl
+    with open(objdir / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB
+            return _build_locked(objdir, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(objdir: Path, verbose: bool) -> Path:
     nvcc = _nvcc()
     objs = []
     procs = []

@@ -40,6 +40,9 @@ typedef void* rr_stream;       /* cudaStream_t */
 
 const char* rr_last_error(void);
 int rr_abi_version(void);
+/* out3 = { sizeof(rr_index_desc), sizeof(rr_fusion_params), sizeof(rr_dense_stats) }: lets a binding check its
+ * struct layouts against the library it loaded (the Python binding does so in _lib.load()). */
+void rr_struct_sizes(int32_t* out3);
 
 /* ------------------------------------------------------------------------------------------
  * Host-side BM25 index construction.

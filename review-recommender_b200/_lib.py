@@ -73,6 +73,7 @@ SIGNATURES = {
                                _P, _P, _P, _P, C.c_int, _P]),
     "rr_fuse_topk_sharded": (C.c_int, [C.POINTER(FusionParams), C.c_int32, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P,
                                        _P, _P, _P, _P, _P, C.c_int, _P]),
+    "rr_struct_sizes": (None, [_P]),
     "rr_profile_enable": (C.c_int, [C.c_int]),
     "rr_profile_collect": (C.c_int, [_P, _P, C.c_int32]),
     "rr_best_review_scores": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P,
@@ -113,6 +114,11 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    sizes = (C.c_int32 * 3)()
+    lib.rr_struct_sizes(sizes)
+    mine = (C.sizeof(IndexDesc), C.sizeof(FusionParams), C.sizeof(DenseStats))
+    if tuple(sizes) != mine:
+        raise RRError(f"struct layout mismatch between _lib.py {mine} and {LIB_PATH.name} {tuple(sizes)}: rebuild the library")
     _lib = lib
     return lib
 

@@ -26,7 +26,14 @@ int rr_fail(int code, const char* fmt, ...) {
 }
 
 extern "C" const char* rr_last_error(void) { return t_err; }
-extern "C" int rr_abi_version(void) { return 1; }
+extern "C" int rr_abi_version(void) { return 2; }
+// sizeof of the three structs that cross the boundary, so that a binding can verify its own layout at load time
+extern "C" void rr_struct_sizes(int32_t* out3) {
+    if (!out3) return;
+    out3[0] = (int32_t)sizeof(rr_index_desc);
+    out3[1] = (int32_t)sizeof(rr_fusion_params);
+    out3[2] = (int32_t)sizeof(rr_dense_stats);
+}
 extern "C" int64_t rr_launch_count(int reset) {
     return reset ? g_rr_launches.exchange(0) : g_rr_launches.load();
 }

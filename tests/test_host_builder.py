@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(rr._lib.SIGNATURES), declared ^ set(rr._lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.rr_abi_version() == 1
+    assert lib.rr_abi_version() == 2
 
 
 @pytest.mark.parametrize("n,v,tile", [(37, 50, 16), (3000, 400, 256), (5000, 2000, 16384)])

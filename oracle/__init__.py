@@ -2,7 +2,7 @@
 
 This package restates, in NumPy / pure Python, the arithmetic of the reference's
 first-stage hybrid retrieval path (`utils.py`, `app/test.py`,
-`app/app_product_search.py:179-317` and the third-party `rank_bm25.BM25Okapi`).
+`app/app_product_search.py:179-370` and the third-party `rank_bm25.BM25Okapi`).
 It exists to *check* the CUDA path; it is never the product:
 
 * only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline /
@@ -12,7 +12,7 @@ It exists to *check* the CUDA path; it is never the product:
 
 Pinning status
 --------------
-* `oracle.primitives`, `oracle.hybrid`: PINNED.  Checked against the reference's own
+* `oracle.primitives`, `oracle.hybrid`, `oracle.snippets`, `oracle.gates`: PINNED.  Checked against the reference's own
   functions run in the build container (`/root/reference/utils.py`,
   `/root/reference/app/test.py`, and `app/app_product_search.py` imported under a
   stub `streamlit`), via `tests/golden/make_golden.py` -> `tests/golden/*.json|npz`

@@ -47,6 +47,7 @@ CONFIGS = {
 }
 METRIC = "hybrid top-100 queries/sec at 10M x 384 docs"
 UNIT = "queries/s"
+OUT = sys.stdout
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -166,7 +167,7 @@ def run_reference(args, cfg):
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -256,7 +257,18 @@ class ClockSampler:
         return out
 
 
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: keep a private handle on it and point file descriptor 1 at stderr, so
+    that anything native code prints there (NCCL's version banner at communicator creation) cannot precede the line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    global OUT
+    OUT = _claim_stdout()
     args = parse_args()
     cfg = dict(CONFIGS[args.config])
     args.cpu_sample_docs = min(args.cpu_sample_docs, args.docs or cfg["docs"])
@@ -559,7 +571,7 @@ def main():
                 "d2h_bytes_per_step": int(B * K * 12), "results_equal_device_path": same},
         "gpu_launches": int(launches),
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -23,7 +23,6 @@ There is no CPU fallback: without the CUDA library or a GPU these raise RRError.
 from __future__ import annotations
 
 import re
-import weakref
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np

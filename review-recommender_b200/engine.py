@@ -14,8 +14,8 @@ Reference seams (paths relative to the reference root):
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Tuple
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -7,7 +7,6 @@ algorithmic bytes of SURVEY.md section 8d:  8 B per posting of the query's terms
 """
 import argparse
 import json
-import os
 import sys
 import time
 from pathlib import Path

@@ -62,7 +62,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=0, help="override batch size (debug)")
     ap.add_argument("--dense-mode", type=int, default=0, help="0 auto, 1 exact fp32, 2 tensor")
     ap.add_argument("--cpu-sample-docs", type=int, default=100_000)
-    ap.add_argument("--cpu-sample-queries", type=int, default=8)
+    ap.add_argument("--cpu-sample-queries", type=int, default=64, help="queries per step of the CPU reference arm")
+    ap.add_argument("--cpu-workers", type=int, default=0, help="worker processes of the CPU arm (0 = all host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sparse-queries", type=int, default=32, help="queries of the BM25 get_scores sweep")
     ap.add_argument("--in-flight", type=int, default=1,
@@ -99,31 +100,60 @@ def load_peaks():
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm (oracle port of the reference path; rank_bm25 restated, see oracle/)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_sample(cfg, sample_docs: int, n_queries: int, repeats: int = 1):
-    """Times the reference's single-query loop (cosine_search -> BM25Okapi.get_scores -> minmax /
-    prior / trust / blend / sort, exactly the order of run_search) on the first `sample_docs` docs of
-    the same synthetic recipe.  Returns (queries/s on the sample, seconds per repeat list)."""
+_CPU = {}          # state of the CPU reference arm, inherited by the forked workers
+
+
+def _cpu_worker_init():
+    try:                                   # one BLAS thread per worker process: the workers are the parallelism
+        from threadpoolctl import threadpool_limits
+        _CPU["blas_limit"] = threadpool_limits(limits=1)
+    except Exception:
+        pass
+
+
+def _cpu_one_query(i: int) -> int:
+    from oracle.hybrid import run_search_core
+    c, cfg = _CPU["corpus"], _CPU["cfg"]
+    toks = [f"t{int(t) + 1}" for t in _CPU["qt"][i]]
+    top, _ = run_search_core(_CPU["q"][i], c.emb, _CPU["meta"], _CPU["bm25"], _CPU["skus"], toks, k=cfg["k"], rerank_k=0)
+    return len(top)
+
+
+def cpu_reference_sample(cfg, sample_docs: int, n_queries: int, repeats: int = 1, workers: int = 0):
+    """Times the reference's single-query path (cosine_search -> BM25Okapi.get_scores -> minmax / prior / trust /
+    blend / sort, exactly the order of run_search) on the first `sample_docs` docs of the same synthetic recipe.
+    The reference answers one query at a time in one interpreter; to use all host cores, `workers` processes
+    (forked after the index is built, so they share it) each answer a slice of the step's queries.
+    Returns (seconds per repeat, worker count).  Must run before CUDA is initialised in this process (fork)."""
+    import multiprocessing as mp
     import pandas as pd
     import review_recommender_b200 as rr
     from oracle.bm25_okapi import BM25Okapi
-    from oracle.hybrid import run_search_core
 
     syn = rr.synth
     c = syn.make_corpus(sample_docs, cfg["dim"], cfg["vocab"])
-    q = syn.queries(n_queries, cfg["dim"])
-    qt = syn.query_terms(n_queries, cfg["terms"], c.doc_offsets, c.token_ids, cfg["vocab"])
     corpus = syn.corpus_as_lists(c.doc_offsets, c.token_ids)
     skus = syn.skus(sample_docs)
-    meta = pd.DataFrame({"sku": skus, "n_reviews": c.n_reviews, "avg_stars": c.avg_stars})
-    bm25 = BM25Okapi(corpus)                      # index build is not timed (neither is the GPU's)
+    _CPU.update(cfg=cfg, corpus=c, q=syn.queries(n_queries, cfg["dim"]),
+                qt=syn.query_terms(n_queries, cfg["terms"], c.doc_offsets, c.token_ids, cfg["vocab"]), skus=skus,
+                meta=pd.DataFrame({"sku": skus, "n_reviews": c.n_reviews, "avg_stars": c.avg_stars}),
+                bm25=BM25Okapi(corpus))            # index build is not timed (neither is the GPU's)
+    workers = max(1, min(workers or (os.cpu_count() or 1), n_queries))
     times = []
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        for i in range(n_queries):
-            toks = [f"t{int(t) + 1}" for t in qt[i]]
-            run_search_core(q[i], c.emb, meta, bm25, skus, toks, k=cfg["k"], rerank_k=0)
-        times.append(time.perf_counter() - t0)
-    return times
+    if workers == 1:
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            for i in range(n_queries):
+                _cpu_one_query(i)
+            times.append(time.perf_counter() - t0)
+        return times, 1
+    with mp.get_context("fork").Pool(workers, initializer=_cpu_worker_init) as pool:
+        pool.map(_cpu_one_query, range(min(n_queries, workers)))         # start-up of the workers is not timed
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            pool.map(_cpu_one_query, range(n_queries), chunksize=max(1, n_queries // (workers * 2)))
+            times.append(time.perf_counter() - t0)
+    return times, workers
 
 
 def blas_threads() -> int:
@@ -134,17 +164,17 @@ def blas_threads() -> int:
         return os.cpu_count() or 1
 
 
-def cpu_baseline_obj(cfg, args, times):
+def cpu_baseline_obj(cfg, args, times, workers):
     per_rep = statistics.median(times)
     qps_sample = args.cpu_sample_queries / per_rep
     scaled = qps_sample * args.cpu_sample_docs / cfg["docs"]
     return {
-        "value": scaled, "unit": UNIT, "cores": blas_threads(), "kind": "port",
-        "sample": (f"first {args.cpu_sample_docs} docs of the same synthetic recipe, {args.cpu_sample_queries} queries, "
-                   f"single-query loop in run_search order (NumPy BLAS gemv + pure-Python rank_bm25 restatement, "
-                   f"interpreter loop is 1 thread): {qps_sample:.3f} q/s on the sample; value is that figure scaled "
-                   f"linearly to {cfg['docs']} docs (per-query cost is O(N)); 10M docs is infeasible for the "
-                   f"dict-per-document index"),
+        "value": scaled, "unit": UNIT, "cores": workers, "kind": "port",
+        "sample": (f"first {args.cpu_sample_docs} docs of the same synthetic recipe, {args.cpu_sample_queries} queries per "
+                   f"step, the reference's single-query path in run_search order (NumPy gemv + pure-Python rank_bm25 "
+                   f"restatement) in {workers} forked worker processes sharing one index: {qps_sample:.3f} q/s on the "
+                   f"sample; value is that figure scaled linearly to {cfg['docs']} docs (per-query cost is O(N)); "
+                   f"10M docs is infeasible for the dict-per-document index"),
         "sample_queries_per_s": qps_sample,
     }
 
@@ -153,9 +183,10 @@ def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    times = cpu_reference_sample(cfg, args.cpu_sample_docs, args.cpu_sample_queries, repeats=args.warmup + args.steps)
+    times, workers = cpu_reference_sample(cfg, args.cpu_sample_docs, args.cpu_sample_queries,
+                                          repeats=args.warmup + args.steps, workers=args.cpu_workers)
     timed = times[args.warmup:]
-    base = cpu_baseline_obj(cfg, args, timed)
+    base = cpu_baseline_obj(cfg, args, timed, workers)
     ms = 1000.0 * statistics.mean(timed)
     line = {
         "impl": "reference", "metric": cfg.get("metric", METRIC), "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -281,6 +312,14 @@ def main():
     if args.impl == "reference":
         run_reference(args, cfg)
         return
+    # CPU baseline leg (rank 0 at N = 1 only): first, because its worker processes are forked and that has to happen
+    # before this process initialises CUDA
+    cpu_base = None
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_cpu_baseline:
+        times, workers = cpu_reference_sample(cfg, args.cpu_sample_docs, args.cpu_sample_queries, repeats=3,
+                                              workers=args.cpu_workers)
+        cpu_base = cpu_baseline_obj(cfg, args, times[1:], workers)
+        _CPU.clear()
 
     import torch
     import torch.distributed as dist
@@ -548,10 +587,6 @@ def main():
             dist.destroy_process_group()
         return
 
-    cpu_base = None
-    if world == 1 and not args.no_cpu_baseline:
-        times = cpu_reference_sample(cfg, args.cpu_sample_docs, args.cpu_sample_queries, repeats=2)
-        cpu_base = cpu_baseline_obj(cfg, args, times[1:])
 
     line = {
         "metric": cfg.get("metric", METRIC), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

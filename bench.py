@@ -69,6 +69,14 @@ def parse_args():
     ap.add_argument("--in-flight", type=int, default=1,
                     help="batches in flight in the device-resident loop (2 = consecutive steps alternate between two "
                          "handles / CUDA streams over the same index, so one step's tail overlaps the next step's GEMM)")
+    ap.add_argument("--synth", default="recipe", choices=["recipe", "device"],
+                    help="recipe = the SURVEY 8d NumPy recipe, generated per 1 M-row chunk on the host (default; the only "
+                         "mode with id_parity); device = same distributions drawn with torch generators in HBM (fast set-up "
+                         "for profiling runs, not comparable with the oracle)")
+    ap.add_argument("--parity-queries", type=int, default=32,
+                    help="queries of the batch that are also answered by the CPU oracle (oracle/sharded.py) -> id_parity")
+    ap.add_argument("--synth-workers", type=int, default=0, help="host threads generating recipe chunks (0 = all cores)")
+    ap.add_argument("--no-c1", action="store_true", help="skip the configs[0] single-query latency block")
     ap.add_argument("--query-groups", type=int, default=1,
                     help="Q query groups x (gpus/Q) row shards (dist.GridSearcher); 1 = plain row sharding")
     return ap.parse_args()
@@ -240,6 +248,93 @@ def device_shard(cfg, row0: int, n: int, dev):
     return emb, offs, toks, nrev, avg          # the tokenised corpus stays in device memory (GpuIndexBuilder)
 
 
+def recipe_shard(cfg, row0: int, n: int, dev, oracle=None, workers: int = 0):
+    """This rank's rows of the SURVEY 8d recipe (rr.synth, NumPy generators, reference l2_normalize), generated chunk
+    by chunk on host threads and uploaded as they arrive; every chunk is also folded into the sharded CPU oracle
+    (in the worker thread) when one is given.  Returns what device_shard returns."""
+    import torch
+    import review_recommender_b200 as rr
+    syn = rr.synth
+    D, V = cfg["dim"], cfg["vocab"]
+    emb = torch.empty((n, D), dtype=torch.float32, device=dev)
+    lens_all, toks_all, nrev_all, avg_all = [], [], [], []
+
+    def fold(piece):
+        if oracle is not None:
+            oracle.add_chunk(piece.row0, piece.emb, piece.lens, piece.token_ids, piece.n_reviews, piece.avg_stars)
+
+    for piece in syn.chunk_stream(row0, n, D, V, workers=workers, per_chunk=fold):
+        r = piece.row0 - row0
+        emb[r:r + piece.emb.shape[0]].copy_(torch.from_numpy(piece.emb))
+        lens_all.append(piece.lens)
+        toks_all.append(piece.token_ids)
+        nrev_all.append(piece.n_reviews)
+        avg_all.append(piece.avg_stars)
+    offs_h = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.concatenate(lens_all), out=offs_h[1:])
+    offs = torch.from_numpy(offs_h).to(dev)
+    toks = torch.from_numpy(np.concatenate(toks_all)).to(dev)
+    return emb, offs, toks, np.concatenate(nrev_all), np.concatenate(avg_all)
+
+
+def c1_block(args, fusion_cls):
+    """configs[0] WHOLE on both arms, no scaling: 10 k products x 384-d, 20 k-vocab BM25, one query at a time, hybrid
+    top-10 (the shape Streamlit issues, app/app_product_search.py:245-261).  GPU arm: host buffers in / out through
+    rr_hybrid_search_host per query; CPU arm: the oracle port of run_search (NumPy gemv + pure-Python rank_bm25
+    restatement) in one interpreter, as the reference runs it."""
+    import pandas as pd
+    import torch
+    import review_recommender_b200 as rr
+    from oracle.bm25_okapi import BM25Okapi
+    from oracle.hybrid import run_search_core
+    cfg = CONFIGS["c1"]
+    syn = rr.synth
+    n, d, v, l, k = cfg["docs"], cfg["dim"], cfg["vocab"], cfg["terms"], cfg["k"]
+    c = syn.make_corpus(n, d, v)
+    nq = 200
+    q = syn.queries(nq, d)
+    qt = syn.query_terms(nq, l, c.doc_offsets, c.token_ids, v).astype(np.int32)
+    fusion = fusion_cls(k=k, rerank_k=0, w_rerank=0.0, w_best=0.0, driver="streamlit")
+    ix = rr.engine.HybridIndex(c.emb, torch.from_numpy(c.doc_offsets).cuda(), torch.from_numpy(c.token_ids).cuda(), v,
+                               c.n_reviews, c.avg_stars, device="cuda:0")
+    nt = np.full(1, l, dtype=np.int32)
+    rows = np.empty((nq, k), dtype=np.int64)
+    final = np.empty((nq, k), dtype=np.float32)
+    for i in range(10):
+        ix.hybrid_search_host(q[i:i + 1], qt[i:i + 1], nt, fusion, out_rows=rows[i:i + 1], out_final=final[i:i + 1])
+    lat = []
+    for i in range(nq):
+        t0 = time.perf_counter()
+        ix.hybrid_search_host(q[i:i + 1], qt[i:i + 1], nt, fusion, out_rows=rows[i:i + 1], out_final=final[i:i + 1])
+        lat.append(time.perf_counter() - t0)
+    ix.close()
+    lat_us = np.sort(np.asarray(lat)) * 1e6
+    # CPU arm: the same queries through the oracle port, whole corpus
+    skus = syn.skus(n)
+    meta = pd.DataFrame({"sku": skus, "n_reviews": c.n_reviews, "avg_stars": c.avg_stars})
+    bm25 = BM25Okapi(syn.corpus_as_lists(c.doc_offsets, c.token_ids))
+    n_cpu = 60
+    same = 0
+    t0 = time.perf_counter()
+    tops = []
+    for i in range(n_cpu):
+        toks = [f"t{int(t) + 1}" for t in qt[i]]
+        top, _ = run_search_core(q[i], c.emb, meta, bm25, skus, toks, k=k, rerank_k=0)
+        tops.append(top["_row"].values)
+    cpu_s = time.perf_counter() - t0
+    for i in range(n_cpu):
+        same += int(np.sum(rows[i, :len(tops[i])] == tops[i]))
+    gpu_qps = nq / float(np.sum(lat))
+    cpu_qps = n_cpu / cpu_s
+    return {"workload": cfg["workload"], "queries_gpu": nq, "queries_cpu": n_cpu,
+            "gpu_p50_us": float(lat_us[nq // 2]), "gpu_p99_us": float(lat_us[min(nq - 1, int(nq * 0.99))]),
+            "gpu_qps": gpu_qps, "cpu_qps": cpu_qps, "cpu_cores": 1, "ratio": gpu_qps / cpu_qps,
+            "ids_bit_exact_rate": same / float(n_cpu * k),
+            "how": "one rr_hybrid_search_host call per query (pageable host buffers in, results out, stream synchronised "
+                   "inside the call), wall clock per call; CPU = oracle port of run_search in one interpreter on the same "
+                   "queries, whole 10 k-doc corpus, no scaling"}
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -350,7 +445,22 @@ def main():
     row0 = N * shard // R
     n_local = N * (shard + 1) // R - row0
     t_setup = time.perf_counter()
-    emb, offs, toks, nrev, avg = device_shard(cfg, row0, n_local, dev)
+    wts = dict(w_dense=0.55, w_bm25=0.20, w_prior=0.20) | cfg.get("weights", {})
+    fusion = eng.Fusion(k=K, rerank_k=0, w_rerank=0.0, w_best=0.0, prior_C=20.0, min_reviews=8, driver="streamlit", **wts)
+    # queries first (identical on every rank and for every GPU count: the recipe alone decides them), so that the
+    # sampled ones can be folded into the CPU oracle while the corpus chunks stream through the host
+    q_np = rr.synth.queries(B, D)
+    oracle = None
+    sample = np.zeros(0, dtype=np.int64)
+    if args.synth == "recipe":
+        qt_np = rr.synth.query_terms_global(B, L, N, V).astype(np.int32)
+        if args.parity_queries > 0 and qg == 0:
+            from oracle.sharded import ShardedOracle
+            sample = np.unique(np.linspace(0, B - 1, min(args.parity_queries, B)).astype(np.int64))
+            oracle = ShardedOracle(q_np[sample], qt_np[sample], V, fusion.pool)
+        emb, offs, toks, nrev, avg = recipe_shard(cfg, row0, n_local, dev, oracle, args.synth_workers)
+    else:
+        emb, offs, toks, nrev, avg = device_shard(cfg, row0, n_local, dev)
     # global BM25 statistics (every query group holds the whole corpus: reduce inside the row group)
     tok_counts = torch.tensor([int(offs[-1].item())], dtype=torch.int64, device=dev)
     pos0 = 0
@@ -371,22 +481,20 @@ def main():
     build_s = time.perf_counter() - t_build
     ix = eng.HybridIndex(emb, None, None, V, nrev, avg, device=dev, row_offset=row0, stats=stats, postings=postings)
     del emb
-    # queries (identical on every rank)
-    q_np = rr.synth.queries(B, D)
-    if rank == 0:
-        qt_np = rr.synth.query_terms(B, L, offs.cpu().numpy(), toks.cpu().numpy(), V).astype(np.int32)
-    else:
-        qt_np = np.zeros((B, L), dtype=np.int32)
-    if world > 1:
-        t = torch.from_numpy(qt_np).to(dev)
-        dist.broadcast(t, 0)
-        qt_np = t.cpu().numpy()
+    if args.synth != "recipe":
+        # legacy device corpus: query terms come from rank 0's documents
+        if rank == 0:
+            qt_np = rr.synth.query_terms(B, L, offs.cpu().numpy(), toks.cpu().numpy(), V).astype(np.int32)
+        else:
+            qt_np = np.zeros((B, L), dtype=np.int32)
+        if world > 1:
+            t = torch.from_numpy(qt_np).to(dev)
+            dist.broadcast(t, 0)
+            qt_np = t.cpu().numpy()
     nt_np = np.full(B, L, dtype=np.int32)
     del toks
     setup_s = time.perf_counter() - t_setup
 
-    wts = dict(w_dense=0.55, w_bm25=0.20, w_prior=0.20) | cfg.get("weights", {})
-    fusion = eng.Fusion(k=K, rerank_k=0, w_rerank=0.0, w_best=0.0, prior_C=20.0, min_reviews=8, driver="streamlit", **wts)
     q_dev = torch.from_numpy(q_np).to(dev)
     qt_dev = torch.from_numpy(qt_np).to(dev)
     nt_dev = torch.from_numpy(nt_np).to(dev)
@@ -582,16 +690,50 @@ def main():
         roofline = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": None, "traffic": None}
 
+    # ---- parity at the benchmark configuration: sampled queries against the CPU oracle ---------------------
+    # every rank folded its own chunks into a partial oracle; rank 0 merges them (corpus statistics + the union of
+    # the per-chunk dense top-pools) and answers the sampled queries the way run_search would
+    id_parity = None
+    if args.synth == "recipe" and args.parity_queries > 0:
+        parts = [oracle.partial() if oracle is not None else []]
+        if world > 1:
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object(parts[0], gathered, dst=0)
+            parts = gathered
+        if rank == 0:
+            from oracle.sharded import compare_with_oracle
+            t_or = time.perf_counter()
+            oracle.merge(parts).finalize()
+            id_parity = compare_with_oracle(oracle, sample, rows.cpu().numpy(), final.cpu().numpy(), K, "streamlit",
+                                            rerank_k=0, w_rerank=0.0, w_best=0.0, prior_C=20.0, min_reviews=8, **wts)
+            id_parity["oracle_s"] = time.perf_counter() - t_or
+            id_parity["how"] = ("oracle/sharded.py: run_search_core (pinned restatement of app/app_product_search.py:253-312) "
+                                "over the union of per-chunk dense top-(pool+32) rows with corpus-global BM25 statistics; "
+                                "same recipe arrays as the GPU index")
+    digest = None
+    if rank == 0:
+        import hashlib
+        h = hashlib.sha256()
+        h.update(np.ascontiguousarray(rows.cpu().numpy()).tobytes())
+        h.update(np.ascontiguousarray(final.cpu().numpy()).tobytes())
+        digest = h.hexdigest()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    c1 = None
+    if world == 1 and not args.no_c1 and args.config == "c3":
+        ix.close()
+        del ix
+        torch.cuda.empty_cache()
+        c1 = c1_block(args, eng.Fusion)
 
 
     line = {
         "metric": cfg.get("metric", METRIC), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
+        "dtype": "bf16", "data": "synthetic" + (" (SURVEY 8d NumPy recipe)" if args.synth == "recipe" else " (device generators)"),
         "dtype_note": "bf16 tensor-core shortlist (fp32 accumulate), exact f32 rescoring, f32/f64 fusion as the reference",
         "config": {"workload": cfg["workload"], "docs": N, "docs_per_gpu": n_local, "dim": D, "vocab": V, "batch": B,
                    "query_terms": L, "k": K, "pool": fusion.pool, "weights": wts, "parallelism": f"row-sharded x{R}" + (f", query groups x{Q}" if Q > 1 else ""),
@@ -605,6 +747,7 @@ def main():
                 "h2d_bytes_per_step": int(q_np.nbytes + qt_np.nbytes + nt_np.nbytes),
                 "d2h_bytes_per_step": int(B * K * 12), "results_equal_device_path": same},
         "gpu_launches": int(launches),
+        "id_parity": id_parity, "result_digest": digest, "c1": c1,
     }
     print(json.dumps(line), file=OUT, flush=True)
     if world > 1:

@@ -101,6 +101,30 @@ class BM25Okapi:
         return score
 
 
+def idf_from_stats(df: np.ndarray, first_pos: np.ndarray, corpus_size: int, epsilon: float = EPSILON_DEFAULT):
+    """`BM25Okapi._calc_idf` from corpus statistics: df int64[V] (documents containing the term) and first_pos int64[V]
+    (flat position of the term's first occurrence -- the insertion order of the library's dict, in which the idf
+    mean is accumulated).  -> (idf float64[V] with the epsilon floor applied, average_idf, number of present terms)."""
+    present = np.nonzero(np.asarray(df) > 0)[0]
+    appear = present[np.argsort(np.asarray(first_pos)[present], kind="stable")]
+    idf = np.zeros(len(df), dtype=np.float64)
+    idf_sum = 0
+    negative = []
+    for t in appear.tolist():
+        freq = int(df[t])
+        x = math.log(corpus_size - freq + 0.5) - math.log(freq + 0.5)
+        idf[t] = x
+        idf_sum += x
+        if x < 0:
+            negative.append(t)
+    n_terms = int(appear.shape[0])
+    average_idf = idf_sum / n_terms
+    eps = epsilon * average_idf
+    for t in negative:
+        idf[t] = eps
+    return idf, average_idf, n_terms
+
+
 class BM25OkapiCSR:
     """Same arithmetic as `BM25Okapi`, over integer token ids (term id in [0, V)).
 
@@ -131,22 +155,9 @@ class BM25OkapiCSR:
         np.cumsum(self.df, out=self.term_off[1:])
         # idf, with the mean accumulated in first-appearance order like the dict walk
         present, first_idx = np.unique(token_ids, return_index=True)
-        appear = present[np.argsort(first_idx, kind="stable")]
-        self.idf = np.zeros(v, dtype=np.float64)
-        idf_sum = 0
-        negative = []
-        for t in appear.tolist():
-            freq = int(self.df[t])
-            idf = math.log(n - freq + 0.5) - math.log(freq + 0.5)
-            self.idf[t] = idf
-            idf_sum += idf
-            if idf < 0:
-                negative.append(t)
-        self.n_terms = int(appear.shape[0])
-        self.average_idf = idf_sum / self.n_terms
-        eps = self.epsilon * self.average_idf
-        for t in negative:
-            self.idf[t] = eps
+        first_pos = np.full(v, np.iinfo(np.int64).max, dtype=np.int64)
+        first_pos[present] = first_idx
+        self.idf, self.average_idf, self.n_terms = idf_from_stats(self.df, first_pos, n, self.epsilon)
 
     def impacts(self, term: int) -> tuple[np.ndarray, np.ndarray]:
         """(doc ids, float64 per-posting contribution) of one term."""

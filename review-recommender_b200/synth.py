@@ -155,3 +155,62 @@ def make_corpus(n: int, d: int, v: int, row0: int = 0) -> SynthCorpus:
     offs, toks = corpus_tokens(n, v, row0)
     nr, av = metadata(n, row0)
     return SynthCorpus(embeddings(n, d, row0), offs, toks, nr, av, v)
+
+
+def query_terms_global(b: int, l: int, n_total: int, v: int) -> np.ndarray:
+    """query_terms() with the source documents taken from the first min(n_total, CHUNK) rows of the corpus, so that
+    the query set does not depend on how the corpus is sharded (every rank / every GPU count derives the same
+    int32[b, l] from the recipe alone)."""
+    offs, toks = corpus_tokens(min(int(n_total), CHUNK), v, 0)
+    return query_terms(b, l, offs, toks, v)
+
+
+@dataclass
+class SynthChunk:
+    row0: int                 # global row of the first row of this piece
+    emb: np.ndarray           # f32[n, D] unit rows (reference l2_normalize)
+    lens: np.ndarray          # i64[n] document lengths
+    token_ids: np.ndarray     # i32[sum(lens)]
+    n_reviews: np.ndarray     # i64[n]
+    avg_stars: np.ndarray     # f64[n]
+    extra: object = None      # whatever `per_chunk` returned (computed in the worker thread)
+
+
+def chunk_stream(row0: int, n: int, d: int, v: int, workers: int = 0, piece_rows: int = CHUNK, per_chunk=None):
+    """Yields the rows [row0, row0+n) of the section-8d recipe as SynthChunk pieces in row order, generated by a pool of
+    threads (NumPy's generators, sort and searchsorted release the GIL).  A piece never crosses a 1 M-row recipe
+    chunk; at most `workers` pieces are in flight, so host memory stays bounded (~2.2 GB per piece at 384-d).
+    `per_chunk(piece) -> extra` runs in the worker thread (used by the tests / bench to fold every piece into the
+    sharded CPU oracle while the next ones are generated)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    pieces = []
+    r = row0
+    while r < row0 + n:
+        within = r % CHUNK
+        take = min(CHUNK - within, piece_rows, row0 + n - r)
+        pieces.append((r, take))
+        r += take
+    workers = max(1, min(workers or (os.cpu_count() or 1), len(pieces)))
+
+    def make(r0, take):
+        offs, toks = corpus_tokens(take, v, r0)
+        nr, av = metadata(take, r0)
+        piece = SynthChunk(r0, embeddings(take, d, r0) if d > 0 else None, np.diff(offs), toks, nr, av)   # d = 0: BM25-only corpora
+        if per_chunk is not None:
+            piece.extra = per_chunk(piece)
+        return piece
+
+    with ThreadPoolExecutor(workers) as ex:
+        pending = []
+        it = iter(pieces)
+        for _ in range(workers):
+            p = next(it, None)
+            if p is not None:
+                pending.append(ex.submit(make, *p))
+        while pending:
+            piece = pending.pop(0).result()
+            p = next(it, None)
+            if p is not None:
+                pending.append(ex.submit(make, *p))
+            yield piece

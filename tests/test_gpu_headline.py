@@ -1,0 +1,98 @@
+"""Parity at BASELINE.json's full sizes, built from the SURVEY 8d recipe (rr.synth chunks, reference l2_normalize):
+
+  configs[2]  10 M products x 384-d, 50 k-vocab BM25, batch 4096, hybrid top-100 -- 32 sampled queries of the batch
+              against the sharded CPU oracle (oracle/sharded.py: run_search_core over a provably sufficient subset with
+              corpus-global BM25 statistics): fused scores within 1e-5 relative, ids >= 90 % bit-exact (north_star),
+              every differing id explained by a tie within tolerance;
+  configs[3]  BM25-only, 20 M documents, 200 k-term Zipf vocabulary, 16-term queries -- rr_bm25_get_scores over ALL
+              documents against BM25Okapi.get_scores restated chunk by chunk (float64), 1e-5 relative.
+
+Set RR_HEADLINE_DOCS / RR_C4_DOCS to shrink the corpora when iterating (the assertions do not change).
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle.sharded import ChunkedBM25Scores, ShardedOracle, compare_with_oracle
+from tests.parity import BM25_RTOL, FUSED_RTOL
+
+N3, D3, V3, B3, L3, K3 = int(os.environ.get("RR_HEADLINE_DOCS", 10_000_000)), 384, 50_000, 4096, 4, 100
+N4, V4, L4 = int(os.environ.get("RR_C4_DOCS", 20_000_000)), 200_000, 16
+
+
+def test_configs2_headline_parity_against_the_oracle():
+    import torch
+    import review_recommender_b200 as rr
+    syn, eng = rr.synth, rr.engine
+    dev = torch.device("cuda:0")
+    fusion = eng.Fusion(k=K3, rerank_k=0, w_dense=0.55, w_bm25=0.20, w_rerank=0.0, w_prior=0.20, w_best=0.0,
+                        prior_C=20.0, min_reviews=8, driver="streamlit")
+    q = syn.queries(B3, D3)
+    qt = syn.query_terms_global(B3, L3, N3, V3).astype(np.int32)
+    sample = np.unique(np.linspace(0, B3 - 1, 32).astype(np.int64))
+    so = ShardedOracle(q[sample], qt[sample], V3, fusion.pool)
+    emb = torch.empty((N3, D3), dtype=torch.float32, device=dev)
+    lens, toks, nrev, avg = [], [], [], []
+    fold = lambda p: so.add_chunk(p.row0, p.emb, p.lens, p.token_ids, p.n_reviews, p.avg_stars)
+    for p in syn.chunk_stream(0, N3, D3, V3, per_chunk=fold):
+        emb[p.row0:p.row0 + len(p.lens)].copy_(torch.from_numpy(p.emb))
+        lens.append(p.lens); toks.append(p.token_ids); nrev.append(p.n_reviews); avg.append(p.avg_stars)
+    offs = np.zeros(N3 + 1, dtype=np.int64)
+    np.cumsum(np.concatenate(lens), out=offs[1:])
+    ix = eng.HybridIndex(emb, torch.from_numpy(offs).to(dev), torch.from_numpy(np.concatenate(toks)).to(dev), V3,
+                         np.concatenate(nrev), np.concatenate(avg), device=dev)
+    del emb, toks
+    so.finalize()
+    # the library's corpus statistics are the oracle's
+    assert ix.stats.avgdl == so.avgdl and ix.stats.average_idf == so.average_idf
+    np.testing.assert_array_equal(ix.stats.idf, so.idf)
+    rows, final = ix.hybrid_search_host(q, qt, np.full(B3, L3, dtype=np.int32), fusion)
+    st = ix.dense_stats()
+    assert st["path"] == 2, "the batch must take the tcgen05 shortlist path"
+    rep = compare_with_oracle(so, sample, rows, final, K3, "streamlit", rtol=FUSED_RTOL, rerank_k=0, w_dense=0.55,
+                              w_bm25=0.20, w_rerank=0.0, w_prior=0.20, w_best=0.0, prior_C=20.0, min_reviews=8)
+    print(f"\nconfigs[2] {N3} x {D3}: id parity {rep}")
+    assert rep["max_rel_fused"] <= FUSED_RTOL
+    assert rep["bit_exact_rate"] >= 0.90
+    assert rep["unexplained"] == 0 and rep["min_set_overlap"] >= 0.98
+    # size-independent properties over the whole batch
+    assert np.all(np.diff(final.astype(np.float64), axis=1) <= 0)
+    assert rows.min() >= 0 and rows.max() < N3
+    ix.close()
+
+
+def test_configs3_bm25_get_scores_at_20m_documents():
+    import torch
+    import review_recommender_b200 as rr
+    syn, eng = rr.synth, rr.engine
+    dev = torch.device("cuda:0")
+    ch = ChunkedBM25Scores(V4)
+    lens, toks = [], []
+    for p in syn.chunk_stream(0, N4, 0, V4, per_chunk=lambda p: ch.add_chunk(p.row0, p.lens, p.token_ids)):
+        lens.append(p.lens); toks.append(p.token_ids)
+    ch.finalize()
+    offs = np.zeros(N4 + 1, dtype=np.int64)
+    np.cumsum(np.concatenate(lens), out=offs[1:])
+    qt = syn.query_terms_global(4, L4, N4, V4).astype(np.int32)
+    qt[3, 5] = qt[3, 2]                                     # a duplicate term is summed twice
+    qt[2, 7] = V4 + 3                                       # an unknown term contributes nothing
+    placeholder = torch.zeros((N4, 4), dtype=torch.float32, device=dev)
+    ix = eng.HybridIndex(placeholder, torch.from_numpy(offs).to(dev), torch.from_numpy(np.concatenate(toks)).to(dev), V4,
+                         device=dev, make_bf16=False)
+    assert ix.stats.avgdl == ch.avgdl and ix.stats.average_idf == ch.average_idf
+    np.testing.assert_array_equal(ix.stats.idf, ch.idf)
+    got = ix.bm25_get_scores(qt, np.full(4, L4, dtype=np.int32)).cpu().numpy()
+    want = ch.get_scores_many([row.tolist() for row in qt])
+    assert got.shape == want.shape == (4, N4)
+    for i in range(4):
+        np.testing.assert_allclose(got[i], want[i], rtol=BM25_RTOL, atol=0)
+        assert np.array_equal(got[i] == 0, want[i].astype(np.float32) == 0)
+    # index metadata (tile directory + term tables) stays a small fraction of the postings
+    meta_bytes = ix.index_bytes()["directory"]
+    post_bytes = ix.index_bytes()["postings"]
+    print(f"\nconfigs[3] {N4} docs: directory {meta_bytes / 1e6:.1f} MB = {100 * meta_bytes / post_bytes:.2f} % of postings")
+    assert meta_bytes <= 0.05 * post_bytes
+    ix.close()

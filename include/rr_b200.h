@@ -66,18 +66,31 @@ int rr_bm25_local_stats(const int64_t* h_doc_offsets, const int32_t* h_token_ids
 int rr_bm25_idf(const int64_t* h_df, const int64_t* h_first_pos, int32_t vocab_size,
                 int64_t corpus_size, double epsilon, double* h_idf, double* h_average_idf);
 
-/* Tile-blocked CSR postings of the local docs with per-posting fp32 impact
+/* Index layout ("hybrid-blocked postings").  posting = {uint32 local doc, float impact} with
  *   impact = (float)( idf[t] * ( tf*(k1+1) / (tf + k1*(1 - b + b*len/avgdl)) ) )   (float64 math)
- * Layout: docs are cut into tiles of tile_docs; inside a tile postings are
- * grouped by term, doc-ascending.  posting = {uint32 local doc, float impact}. */
+ * Documents are cut into tiles of tile_docs.  Terms fall in two classes by their LOCAL document frequency:
+ *   FREQUENT  df >= rr_bm25_dir_threshold(n_tiles) = RR_DIR_MIN_PER_TILE * n_tiles (at least 8 postings per tile on
+ *             average): tile-blocked -- inside tile i the postings are grouped by frequent slot (= term-ascending),
+ *             doc-ascending inside a group; dir[i*(n_freq+1) + f .. + f+1] bounds slot f's group relative to
+ *             tile_base[i] (every tile starts on a 16-byte boundary).  term_slot[t] = f.
+ *   RARE      everything else (term_slot[t] = -1): ONE term-major list per term, doc-ascending, at
+ *             tile_base[n_tiles] + rare_off[t] .. + rare_off[t+1]; the part of a list that falls into a tile is
+ *             found by a lower-bound on the doc id (per batch, rr_bm25_get_scores does it for all tiles at once).
+ * Metadata is n_tiles*(n_freq+1)*4 + vocab*12 bytes: the dense [n_tiles, vocab+1] table of ABI 2 (1.3 GB at 20 M
+ * documents x 200 k terms) is gone; a directory entry is only spent where it indexes >= 64 bytes of postings. */
+#define RR_DIR_MIN_PER_TILE 8
+int32_t rr_bm25_dir_threshold(int32_t n_tiles);
 int rr_bm25_build_postings(const int64_t* h_doc_offsets, const int32_t* h_token_ids, int64_t n_docs,
                            int32_t vocab_size, const double* h_idf, double avgdl, double k1, double b,
                            int32_t tile_docs, int32_t n_threads, rr_postings** out);
-int64_t         rr_postings_nnz(const rr_postings*);        /* entries incl. alignment padding */
+int64_t         rr_postings_nnz(const rr_postings*);        /* entries incl. alignment padding (both regions) */
 int32_t         rr_postings_n_tiles(const rr_postings*);
+int32_t         rr_postings_n_freq(const rr_postings*);
 const uint64_t* rr_postings_data(const rr_postings*);       /* host, nnz x {u32 doc, f32 impact} */
 const uint64_t* rr_postings_tile_base(const rr_postings*);  /* host, n_tiles+1 */
-const uint32_t* rr_postings_blk_off(const rr_postings*);    /* host, n_tiles*(vocab_size+1) */
+const uint32_t* rr_postings_dir(const rr_postings*);        /* host, n_tiles*(n_freq+1) */
+const int32_t*  rr_postings_term_slot(const rr_postings*);  /* host, vocab_size */
+const uint64_t* rr_postings_rare_off(const rr_postings*);   /* host, vocab_size+1 */
 /* Forward (doc-major) copy of the same impacts for candidate-mode scoring: doc d's entries
  * {u32 term, f32 impact}, term-ascending, are fwd_data[fwd_off[d] .. fwd_off[d+1]). */
 const uint64_t* rr_postings_fwd_off(const rr_postings*);    /* host, n_docs+1 */
@@ -85,21 +98,24 @@ const uint64_t* rr_postings_fwd_data(const rr_postings*);   /* host, fwd_off[n_d
 void            rr_postings_free(rr_postings*);
 
 /* The same construction on the GPU, for a tokenised corpus that is already in device memory (bit-identical output).
- * begin:  sorts the (doc, term) token keys, finds the unique pairs and the tile geometry; reports how many forward
- *         entries (n_unique) and postings incl. alignment padding (n_postings) the caller has to allocate;
+ * begin:  sorts the (doc, term) token keys, finds the unique pairs, classifies the terms by local df and derives the
+ *         tile geometry; reports how many forward entries (n_unique), postings incl. alignment padding (n_postings)
+ *         and frequent terms (n_freq) the caller has to allocate for;
  * stats:  adds this shard's df to d_df int64[V] (caller-zeroed) and lowers d_first_pos int64[V] (caller-initialised to
  *         INT64_MAX) -- all-reduce them over the shards, then rr_bm25_idf on the host;
- * finish: impacts, forward index, tile-blocked postings, tile_base[n_tiles+1], blk_off[n_tiles*(V+1)], fwd_off[n_docs+1]
- *         into caller-owned device buffers.  d_doc_offsets / d_token_ids must stay valid until finish.
+ * finish: impacts, forward index, postings of both regions, tile_base[n_tiles+1], dir[n_tiles*(n_freq+1)],
+ *         term_slot[V], rare_off[V+1], fwd_off[n_docs+1] into caller-owned device buffers.
+ *         d_doc_offsets / d_token_ids must stay valid until finish.
  * vocab_size <= 2^24, tile_docs <= 65536 (multiple of 4), fewer than 2^31 tokens per shard. */
 typedef struct rr_bm25_gpu_builder rr_bm25_gpu_builder;
 int rr_bm25_gpu_build_begin(rr_bm25_gpu_builder** out, const int64_t* d_doc_offsets, const int32_t* d_token_ids,
                             int64_t n_docs, int64_t n_tokens, int32_t vocab_size, int32_t tile_docs,
-                            int64_t* n_unique_out, int64_t* n_postings_out, int32_t* n_tiles_out, int device, rr_stream);
+                            int64_t* n_unique_out, int64_t* n_postings_out, int32_t* n_tiles_out, int32_t* n_freq_out,
+                            int device, rr_stream);
 int rr_bm25_gpu_build_stats(rr_bm25_gpu_builder*, int64_t token_pos0, int64_t* d_df, int64_t* d_first_pos, rr_stream);
 int rr_bm25_gpu_build_finish(rr_bm25_gpu_builder*, const double* d_idf, double avgdl, double k1, double b,
-                             uint64_t* d_postings, uint64_t* d_tile_base, uint32_t* d_blk_off,
-                             uint64_t* d_fwd_off, uint64_t* d_fwd_data, rr_stream);
+                             uint64_t* d_postings, uint64_t* d_tile_base, uint32_t* d_dir, int32_t* d_term_slot,
+                             uint64_t* d_rare_off, uint64_t* d_fwd_off, uint64_t* d_fwd_data, rr_stream);
 void rr_bm25_gpu_build_free(rr_bm25_gpu_builder*);
 
 /* ------------------------------------------------------------------------------------------
@@ -116,9 +132,12 @@ typedef struct rr_index_desc {
     int32_t vocab_size;          /* 0 = no BM25 index ("BM25 absent": zeros, app/app_product_search.py:202) */
     int32_t tile_docs;
     int32_t n_tiles;
+    int32_t n_freq;              /* frequent terms (directory slots per tile) */
     const uint64_t* d_postings;  /* as rr_postings_data */
-    const uint64_t* d_tile_base;
-    const uint32_t* d_blk_off;
+    const uint64_t* d_tile_base; /* [n_tiles+1]; tile_base[n_tiles] = first posting of the rare region */
+    const uint32_t* d_dir;       /* [n_tiles, n_freq+1] */
+    const int32_t*  d_term_slot; /* [vocab_size] */
+    const uint64_t* d_rare_off;  /* [vocab_size+1] */
     const uint64_t* d_fwd_off;   /* [n_docs+1] forward index (optional: NULL = candidate mode searches the postings) */
     const uint64_t* d_fwd_data;  /* {u32 term, f32 impact} per (doc, term), term-ascending inside a doc */
     const double*   d_n_reviews; /* [n_docs] n_reviews with NaN already mapped to 0 (:264), or NULL */
@@ -158,6 +177,13 @@ int rr_bm25_candidates(rr_index*, const int32_t* d_term_ids, const int32_t* d_n_
 #define RR_DENSE_TENSOR 2
 int rr_dense_topk(rr_index*, const float* d_q, int32_t B, int32_t pool, int32_t mode,
                   int64_t* d_idx, float* d_sims, int32_t* d_count, rr_stream);
+
+/* Test / debug entry of the shortlist stage: the raw bf16 x bf16 -> fp32 tensor-core scores (tcgen05.mma, exactly what
+ * the threshold filter compares) of rows [row0, row0+n_rows) for B <= 128 queries, d_out float[B, n_rows].  row0 must be
+ * a multiple of 256 and n_rows <= 256 * (number of SMs).  north_star states "dense cosine within 1e-3 absolute before
+ * rescoring": tests compare these with the exact fp32 similarities. */
+int rr_dense_debug_bf16_scores(rr_index*, const float* d_q, int32_t B, int64_t row0, int32_t n_rows, float* d_out,
+                               rr_stream);
 
 /* Candidate tuples for fusion: BM25 at the candidates plus their metadata and global rows.
  * Output arrays are [B, pool]. */

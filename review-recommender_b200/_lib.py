@@ -25,8 +25,9 @@ class IndexDesc(C.Structure):
     _fields_ = [
         ("n_docs", C.c_int64), ("row_offset", C.c_int64), ("dim", C.c_int32), ("dim_pad", C.c_int32),
         ("d_emb_f32", C.c_void_p), ("d_emb_bf16", C.c_void_p), ("max_row_norm", C.c_float),
-        ("vocab_size", C.c_int32), ("tile_docs", C.c_int32), ("n_tiles", C.c_int32),
-        ("d_postings", C.c_void_p), ("d_tile_base", C.c_void_p), ("d_blk_off", C.c_void_p),
+        ("vocab_size", C.c_int32), ("tile_docs", C.c_int32), ("n_tiles", C.c_int32), ("n_freq", C.c_int32),
+        ("d_postings", C.c_void_p), ("d_tile_base", C.c_void_p), ("d_dir", C.c_void_p),
+        ("d_term_slot", C.c_void_p), ("d_rare_off", C.c_void_p),
         ("d_fwd_off", C.c_void_p), ("d_fwd_data", C.c_void_p),
         ("d_n_reviews", C.c_void_p), ("d_avg_stars", C.c_void_p),
     ]
@@ -59,7 +60,11 @@ SIGNATURES = {
     "rr_postings_n_tiles": (C.c_int32, [_P]),
     "rr_postings_data": (_P, [_P]),
     "rr_postings_tile_base": (_P, [_P]),
-    "rr_postings_blk_off": (_P, [_P]),
+    "rr_postings_n_freq": (C.c_int32, [_P]),
+    "rr_postings_dir": (_P, [_P]),
+    "rr_postings_term_slot": (_P, [_P]),
+    "rr_postings_rare_off": (_P, [_P]),
+    "rr_bm25_dir_threshold": (C.c_int32, [C.c_int32]),
     "rr_postings_fwd_off": (_P, [_P]),
     "rr_postings_fwd_data": (_P, [_P]),
     "rr_postings_free": (None, [_P]),
@@ -68,6 +73,7 @@ SIGNATURES = {
     "rr_bm25_get_scores": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "rr_bm25_candidates": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
     "rr_dense_topk": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "rr_dense_debug_bf16_scores": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, _P, _P]),
     "rr_candidate_tuples": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P]),
     "rr_fuse_topk": (C.c_int, [C.POINTER(FusionParams), C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                _P, _P, _P, _P, C.c_int, _P]),
@@ -78,9 +84,9 @@ SIGNATURES = {
     "rr_profile_collect": (C.c_int, [_P, _P, C.c_int32]),
     "rr_best_review_scores": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P,
                                         C.c_int, _P]),
-    "rr_bm25_gpu_build_begin": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_int, _P]),
+    "rr_bm25_gpu_build_begin": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int, _P]),
     "rr_bm25_gpu_build_stats": (C.c_int, [_P, C.c_int64, _P, _P, _P]),
-    "rr_bm25_gpu_build_finish": (C.c_int, [_P, _P, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P, _P, _P]),
+    "rr_bm25_gpu_build_finish": (C.c_int, [_P, _P, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rr_bm25_gpu_build_free": (None, [_P]),
     "rr_normalize_rows": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, C.c_int32, _P, C.c_int, _P]),
     "rr_bf16_rows": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int, _P]),

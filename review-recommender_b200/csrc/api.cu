@@ -26,7 +26,7 @@ int rr_fail(int code, const char* fmt, ...) {
 }
 
 extern "C" const char* rr_last_error(void) { return t_err; }
-extern "C" int rr_abi_version(void) { return 2; }
+extern "C" int rr_abi_version(void) { return 3; }
 // sizeof of the three structs that cross the boundary, so that a binding can verify its own layout at load time
 extern "C" void rr_struct_sizes(int32_t* out3) {
     if (!out3) return;
@@ -122,6 +122,7 @@ struct rr_index {
     DeviceBuf select;     // radix-select state
     DeviceBuf tuples;     // hybrid: candidate tuples
     DeviceBuf staging;    // *_host entry points
+    DeviceBuf rtab;       // rr_bm25_get_scores: tile bounds of the batch's rare terms
     rr_tc_state* tc = nullptr;
     rr_dense_stats stats{};
     // the scratch buffers above are shared by all callers of the handle: a call that uses them on another stream
@@ -166,7 +167,8 @@ extern "C" int rr_index_create(rr_index** out, const rr_index_desc* desc, int de
     if (desc->d_emb_bf16 && (desc->dim_pad < desc->dim || desc->dim_pad % 64))
         return rr_fail(RR_EINVAL, "rr_index_create: dim_pad must be a multiple of 64 and >= dim");
     if (desc->vocab_size > 0) {
-        if (!desc->d_postings || !desc->d_tile_base || !desc->d_blk_off || desc->tile_docs <= 0 || (desc->tile_docs & 3) ||
+        if (!desc->d_postings || !desc->d_tile_base || !desc->d_dir || !desc->d_term_slot || !desc->d_rare_off ||
+            desc->n_freq < 0 || desc->tile_docs <= 0 || (desc->tile_docs & 3) ||
             desc->n_tiles != (int32_t)((desc->n_docs + desc->tile_docs - 1) / desc->tile_docs))
             return rr_fail(RR_EINVAL, "rr_index_create: inconsistent BM25 postings description");
         if ((size_t)desc->tile_docs * 4 > 200 * 1024)
@@ -194,6 +196,7 @@ extern "C" void rr_index_destroy(rr_index* ix) {
     ix->select.release();
     ix->tuples.release();
     ix->staging.release();
+    ix->rtab.release();
     rr_tc_destroy(ix->tc);
     if (ix->fence) cudaEventDestroy(ix->fence);
     delete ix;
@@ -224,19 +227,25 @@ extern "C" int rr_bm25_get_scores(rr_index* ix, const int32_t* d_term_ids, const
         RR_CUDA(cudaMemset2DAsync(d_out, sizeof(float) * (size_t)ld_out, 0, sizeof(float) * (size_t)ix->d.n_docs, (size_t)B, s));
         return RR_OK;
     }
-    return rr_launch_bm25_tile_scores(ix->d.d_postings, ix->d.d_tile_base, ix->d.d_blk_off, ix->d.vocab_size,
-                                      ix->d.tile_docs, ix->d.n_tiles, ix->d.n_docs, d_term_ids, d_n_terms, B, l_max,
-                                      d_out, ld_out, s);
+    // per batch: where every tile starts in the lists of the batch's rare terms (scratch of the handle, <= 256 MB a go)
+    ScratchFence fence(ix, s);
+    const size_t per_q = rr_bm25_rtab_bytes(1, l_max, ix->d.n_tiles);
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, ((size_t)256 << 20) / std::max<size_t>(per_q, 1)));
+    RR_TRY(ix->rtab.ensure(per_q * (size_t)chunk));
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = std::min(chunk, B - b0);
+        RR_TRY(rr_launch_bm25_tile_scores(&ix->d, d_term_ids + (int64_t)b0 * l_max, d_n_terms + b0, nb, l_max,
+                                          d_out + (int64_t)b0 * ld_out, ld_out, static_cast<uint32_t*>(ix->rtab.p), s));
+    }
+    return RR_OK;
 }
 
 static int candidates_locked(rr_index* ix, const int32_t* d_term_ids, const int32_t* d_n_terms, int32_t B,
                              int32_t l_max, const int64_t* d_cand, int32_t pool, float* d_bm25, double* d_n,
                              double* d_avg, int64_t* d_grow, cudaStream_t s) {
     const bool have = ix->d.vocab_size > 0 && l_max > 0 && d_term_ids && d_n_terms;
-    return rr_launch_bm25_candidates(ix->d.d_postings, ix->d.d_tile_base, ix->d.d_blk_off,
-                                     ix->d.d_fwd_off, ix->d.d_fwd_data, have ? ix->d.vocab_size : 0, std::max(ix->d.tile_docs, 1), ix->d.n_docs,
-                                     have ? d_term_ids : nullptr, d_n_terms, B, l_max, d_cand, pool, ix->d.d_n_reviews,
-                                     ix->d.d_avg_stars, ix->d.row_offset, d_bm25, d_n, d_avg, d_grow, s);
+    return rr_launch_bm25_candidates(&ix->d, have ? ix->d.vocab_size : 0, have ? d_term_ids : nullptr, d_n_terms, B, l_max,
+                                     d_cand, pool, d_bm25, d_n, d_avg, d_grow, s);
 }
 
 extern "C" int rr_bm25_candidates(rr_index* ix, const int32_t* d_term_ids, const int32_t* d_n_terms, int32_t B,
@@ -294,12 +303,20 @@ static int dense_topk_locked(rr_index* ix, const float* d_q, int32_t B, int32_t 
         if (!ix->d.d_emb_bf16) return rr_fail(RR_EUNSUPPORTED, "tensor path needs the bf16 corpus copy (d_emb_bf16)");
         if (!rr_tc_supported(ix->cc_major, ix->cc_minor))
             return rr_fail(RR_EUNSUPPORTED, "tensor path needs an sm_100 device (found sm_%d%d)", ix->cc_major, ix->cc_minor);
-        return rr_tc_dense_topk(&ix->tc, &ix->d, ix->sm_count, d_q, B, pool, d_idx, d_sims, d_count, &ix->stats,
-                                [](void* ctx, const float* q, int32_t b, int32_t p, int64_t* idx, float* sims, int32_t* cnt,
-                                   cudaStream_t st) {
-                                    return dense_exact_locked(static_cast<rr_index*>(ctx), q, b, p, idx, sims, cnt, st);
-                                },
-                                ix, d_uncertified, s);
+        // the tensor path takes at most 8 x SM query tiles per call: very large batches go through in slices
+        const int32_t slice = 65536;
+        for (int32_t b0 = 0; b0 < B; b0 += slice) {
+            const int32_t nb = std::min(slice, B - b0);
+            RR_TRY(rr_tc_dense_topk(&ix->tc, &ix->d, ix->sm_count, d_q + (int64_t)b0 * ix->d.dim, nb, pool,
+                                    d_idx + (int64_t)b0 * pool, d_sims + (int64_t)b0 * pool, d_count ? d_count + b0 : nullptr,
+                                    &ix->stats,
+                                    [](void* ctx, const float* q, int32_t b, int32_t p, int64_t* idx, float* sims, int32_t* cnt,
+                                       cudaStream_t st) {
+                                        return dense_exact_locked(static_cast<rr_index*>(ctx), q, b, p, idx, sims, cnt, st);
+                                    },
+                                    ix, d_uncertified ? d_uncertified + b0 : nullptr, s));
+        }
+        return RR_OK;
     }
     if (mode != RR_DENSE_EXACT) return rr_fail(RR_EINVAL, "rr_dense_topk: unknown mode %d", mode);
     ix->stats = rr_dense_stats{};
@@ -317,6 +334,18 @@ extern "C" int rr_dense_topk(rr_index* ix, const float* d_q, int32_t B, int32_t 
     RR_CUDA(cudaSetDevice(ix->device));
     ScratchFence fence(ix, static_cast<cudaStream_t>(stream));
     return dense_topk_locked(ix, d_q, B, pool, mode, d_idx, d_sims, d_count, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rr_dense_debug_bf16_scores(rr_index* ix, const float* d_q, int32_t B, int64_t row0, int32_t n_rows,
+                                          float* d_out, rr_stream stream) {
+    if (!ix || !d_q || !d_out) return rr_fail(RR_EINVAL, "rr_dense_debug_bf16_scores: null argument");
+    if (!ix->d.d_emb_bf16) return rr_fail(RR_EUNSUPPORTED, "tensor path needs the bf16 corpus copy (d_emb_bf16)");
+    if (!rr_tc_supported(ix->cc_major, ix->cc_minor))
+        return rr_fail(RR_EUNSUPPORTED, "tensor path needs an sm_100 device (found sm_%d%d)", ix->cc_major, ix->cc_minor);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    RR_CUDA(cudaSetDevice(ix->device));
+    ScratchFence fence(ix, static_cast<cudaStream_t>(stream));
+    return rr_tc_debug_scores(&ix->tc, &ix->d, ix->sm_count, d_q, B, row0, n_rows, d_out, static_cast<cudaStream_t>(stream));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -369,10 +398,8 @@ extern "C" int rr_shard_tuples(rr_index* ix, const float* d_q, const int32_t* d_
     const size_t bp = (size_t)bg * m;
     char* base = static_cast<char*>(d_send);
     const bool have = ix->d.vocab_size > 0 && l_max > 0 && d_term_ids && d_n_terms;
-    return rr_launch_bm25_candidates(ix->d.d_postings, ix->d.d_tile_base, ix->d.d_blk_off, ix->d.d_fwd_off, ix->d.d_fwd_data,
-                                     have ? ix->d.vocab_size : 0, std::max(ix->d.tile_docs, 1), ix->d.n_docs,
-                                     have ? d_term_ids : nullptr, d_n_terms, B, l_max, idx, m, ix->d.d_n_reviews,
-                                     ix->d.d_avg_stars, ix->d.row_offset, reinterpret_cast<float*>(base + bp * 28),
+    return rr_launch_bm25_candidates(&ix->d, have ? ix->d.vocab_size : 0, have ? d_term_ids : nullptr, d_n_terms, B, l_max,
+                                     idx, m, reinterpret_cast<float*>(base + bp * 28),
                                      reinterpret_cast<double*>(base + bp * 8), reinterpret_cast<double*>(base + bp * 16),
                                      reinterpret_cast<int64_t*>(base), s, bg, (int64_t)(bp * 32), sims,
                                      reinterpret_cast<float*>(base + bp * 24), uncert);

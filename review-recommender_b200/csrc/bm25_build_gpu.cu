@@ -6,9 +6,12 @@
 //           with tf = run length, in doc-major / term-ascending order (= forward-index order)
 //   stats   df[t] += 1 per pair; first_pos[t] = min flat position of t (the dict order rank_bm25 sums idf in)
 //           -- the caller all-reduces them over the row shards and computes idf on the host (V values, libm log)
+//   begin   (cont.) local df -> term classes (frequent: directory slot, rare: term-major list; include/rr_b200.h
+//           "index layout"), frequent postings per tile -> tile bases (16-byte aligned tiles)
 //   finish  impact = (float)(idf * (tf*(k1+1) / (tf + k1*(1 - b + b*len/avgdl))))  in float64, the host builder's
-//           operation order; forward entries; key2 = tile | term | doc-in-tile -> radix sort -> postings in tile-blocked
-//           order; tile bases (16-byte aligned tiles), blk_off by a lower-bound per (tile, term).
+//           operation order; forward entries; key2 = frequent: tile | slot | doc-in-tile, rare: 1<<63 | term | doc
+//           -> radix sort -> frequent postings in tile-blocked order followed by the rare term-major lists;
+//           dir by a lower-bound per (tile, slot).
 //
 // Sorting and prefix sums use CUB (cub::DeviceRadixSort / DeviceScan, part of the CUDA toolkit); everything else
 // is hand-written.  This is the index-build path, not the query path.
@@ -89,11 +92,48 @@ __global__ void doc_starts_kernel(const unsigned long long* __restrict__ u_key, 
     fill_group_starts(u, n_unique, n_docs, fwd_off, [&](long long i) { return (long long)(u_key[i] >> 32); });
 }
 
-__global__ void pair_tile_starts_kernel(const unsigned long long* __restrict__ u_key, long long n_unique, long long n_tiles,
-                                        int T, unsigned long long* __restrict__ tile_start) {
+// local document frequency of every term (one unique pair = one document containing the term)
+__global__ void pair_df_kernel(const unsigned long long* __restrict__ u_key, long long n_unique, unsigned* __restrict__ df) {
     const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n_unique == 0) { if (u <= n_tiles) tile_start[u] = 0ull; return; }
-    fill_group_starts(u, n_unique, n_tiles, tile_start, [&](long long i) { return (long long)(u_key[i] >> 32) / T; });
+    if (u < n_unique) atomicAdd(&df[(unsigned)(u_key[u] & 0xffffffffull)], 1u);
+}
+// class flags: frequent (df >= theta) -> 1 in is_freq; rare -> its posting count in rare_cnt
+__global__ void classify_kernel(const unsigned* __restrict__ df, int V, unsigned theta, int* __restrict__ is_freq,
+                                unsigned long long* __restrict__ rare_cnt) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= V) return;
+    const bool f = df[t] >= theta;
+    is_freq[t] = f ? 1 : 0;
+    rare_cnt[t] = f ? 0ull : (unsigned long long)df[t];
+}
+// term_slot[t] = exclusive rank among the frequent terms, or -1; totals[0] = n_freq, totals[1] = rare postings
+__global__ void slots_kernel(const int* __restrict__ is_freq, const int* __restrict__ rank, const unsigned long long* __restrict__ rare_off,
+                             const unsigned long long* __restrict__ rare_cnt, int V, int* __restrict__ term_slot,
+                             unsigned long long* __restrict__ rare_off_out, unsigned long long* __restrict__ totals) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= V) return;
+    term_slot[t] = is_freq[t] ? rank[t] : -1;
+    rare_off_out[t] = rare_off[t];
+    if (t == V - 1) {
+        totals[0] = (unsigned long long)(rank[t] + is_freq[t]);
+        totals[1] = rare_off[t] + rare_cnt[t];
+        rare_off_out[V] = rare_off[t] + rare_cnt[t];
+    }
+}
+// frequent postings per tile (pairs are doc-major: neighbouring lanes mostly share the tile -> warp-aggregated add)
+__global__ void tile_count_kernel(const unsigned long long* __restrict__ u_key, long long n_unique, int T,
+                                  const int* __restrict__ term_slot, unsigned long long* __restrict__ tile_cnt) {
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    long long tile = -1;
+    if (u < n_unique) {
+        const unsigned long long k = u_key[u];
+        if (term_slot[(unsigned)(k & 0xffffffffull)] >= 0) tile = (long long)(k >> 32) / T;
+    }
+    const long long lead = __shfl_sync(0xffffffffu, tile, 0);
+    const unsigned same = __ballot_sync(0xffffffffu, tile == lead && tile >= 0);
+    if (tile >= 0 && tile != lead) atomicAdd(&tile_cnt[tile], 1ull);
+    if (lane == 0 && same) atomicAdd(&tile_cnt[lead], (unsigned long long)__popc(same));
 }
 
 __global__ void pair_stats_kernel(const unsigned long long* __restrict__ u_key, long long n_unique,
@@ -118,7 +158,8 @@ __device__ __forceinline__ unsigned long long pack_u32_f32(unsigned a, float f) 
 // impact of every unique (doc, term) pair; forward entry; key / value of the tile-blocked sort
 __global__ void impacts_kernel(const unsigned long long* __restrict__ u_key, const long long* __restrict__ u_start,
                                long long n_unique, const long long* __restrict__ doc_off, const double* __restrict__ idf,
-                               double avgdl, double k1, double b, int T, unsigned long long* __restrict__ fwd_data,
+                               double avgdl, double k1, double b, int T, const int* __restrict__ term_slot,
+                               unsigned long long* __restrict__ fwd_data,
                                unsigned long long* __restrict__ key2, unsigned long long* __restrict__ val2) {
     const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_unique) return;
@@ -133,61 +174,67 @@ __global__ void impacts_kernel(const unsigned long long* __restrict__ u_key, con
     const float imp = (float)v;
     fwd_data[u] = pack_u32_f32(term, imp);
     const long long tile = doc / T;
-    key2[u] = ((unsigned long long)tile << 40) | ((unsigned long long)term << 16) | (unsigned long long)(doc - tile * T);
+    const int slot = term_slot[term];
+    key2[u] = slot >= 0 ? (((unsigned long long)tile << 40) | ((unsigned long long)slot << 16) | (unsigned long long)(doc - tile * T))
+                        : ((1ull << 63) | ((unsigned long long)term << 32) | (unsigned long long)doc);
     val2[u] = pack_u32_f32((unsigned)doc, imp);
 }
 
-__global__ void tile_starts_kernel(const unsigned long long* __restrict__ key2, long long n_unique, long long n_tiles,
-                                   unsigned long long* __restrict__ tile_start) {
-    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n_unique == 0) { if (u <= n_tiles) tile_start[u] = 0ull; return; }
-    fill_group_starts(u, n_unique, n_tiles, tile_start, [&](long long i) { return (long long)(key2[i] >> 40); });
-}
-
-// tile_base[i] = sum over earlier tiles of their posting counts rounded up to an even number (16-byte aligned tiles)
-__global__ void tile_bases_kernel(const unsigned long long* __restrict__ tile_start, long long n_tiles,
-                                  unsigned long long* __restrict__ tile_base, int* __restrict__ overflow) {
+// tile_base[i] = sum over earlier tiles of their frequent posting counts rounded up to an even number (16-byte
+// aligned tiles); tile_start[i] = the same sum without the rounding (position in the sorted frequent pairs)
+__global__ void tile_bases_kernel(const unsigned long long* __restrict__ tile_cnt, long long n_tiles,
+                                  unsigned long long* __restrict__ tile_start, unsigned long long* __restrict__ tile_base,
+                                  int* __restrict__ overflow) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    unsigned long long total = 0;
+    unsigned long long total = 0, run = 0;
     for (long long t = 0; t < n_tiles; ++t) {
-        const unsigned long long nnz = tile_start[t + 1] - tile_start[t];
+        const unsigned long long nnz = tile_cnt[t];
         if (nnz > 0xFFFFFFFFull) *overflow = 1;
+        tile_start[t] = run;
         tile_base[t] = total;
+        run += nnz;
         total += (nnz + 1ull) & ~1ull;
     }
+    tile_start[n_tiles] = run;
     tile_base[n_tiles] = total;
 }
 
-// blk_off[tile][w] = number of postings of the tile whose term is < w  (w in [0, V]), by lower bound
-__global__ void blk_off_kernel(const unsigned long long* __restrict__ key2, const unsigned long long* __restrict__ tile_start,
-                               long long n_tiles, int V, unsigned* __restrict__ blk_off) {
+// dir[tile][f] = number of frequent postings of the tile whose slot is < f  (f in [0, n_freq]), by lower bound
+__global__ void dir_kernel(const unsigned long long* __restrict__ key2, const unsigned long long* __restrict__ tile_start,
+                           long long n_tiles, int n_freq, unsigned* __restrict__ dir) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)V + 1;
+    const long long stride = (long long)n_freq + 1;
     if (i >= n_tiles * stride) return;
     const long long tile = i / stride;
-    const unsigned long long w = (unsigned long long)(i - tile * stride);
+    const unsigned long long f = (unsigned long long)(i - tile * stride);
     long long lo = (long long)tile_start[tile], hi = (long long)tile_start[tile + 1];
     const long long s0 = lo;
     while (lo < hi) {
         const long long mid = (lo + hi) >> 1;
-        if (((key2[mid] >> 16) & 0xFFFFFFull) < w) lo = mid + 1; else hi = mid;
+        if (((key2[mid] >> 16) & 0xFFFFFFull) < f) lo = mid + 1; else hi = mid;
     }
-    blk_off[i] = (unsigned)(lo - s0);
+    dir[i] = (unsigned)(lo - s0);
 }
 
+// sorted pairs -> postings: [0, n_freq_pairs) tile-blocked, [n_freq_pairs, n_unique) the rare term-major lists
 __global__ void scatter_postings_kernel(const unsigned long long* __restrict__ key2, const unsigned long long* __restrict__ val2,
-                                        long long n_unique, const unsigned long long* __restrict__ tile_start,
+                                        long long n_unique, long long n_freq_pairs, const unsigned long long* __restrict__ tile_start,
                                         const unsigned long long* __restrict__ tile_base, long long n_tiles,
                                         unsigned long long* __restrict__ postings) {
     const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u < n_unique) {
+    const unsigned long long rare_base = tile_base[n_tiles];
+    if (u < n_freq_pairs) {
         const long long tile = (long long)(key2[u] >> 40);
         postings[tile_base[tile] + ((unsigned long long)u - tile_start[tile])] = val2[u];
+    } else if (u < n_unique) {
+        postings[rare_base + (unsigned long long)(u - n_freq_pairs)] = val2[u];
     }
     if (u < n_tiles) {          // the padding slot of a tile with an odd number of postings
         const unsigned long long nnz = tile_start[u + 1] - tile_start[u];
         if (nnz & 1ull) postings[tile_base[u] + nnz] = pack_u32_f32(0xFFFFFFFFu, 0.0f);
     }
+    if (u == 0 && ((n_unique - n_freq_pairs) & 1ll))
+        postings[rare_base + (unsigned long long)(n_unique - n_freq_pairs)] = pack_u32_f32(0xFFFFFFFFu, 0.0f);
 }
 
 inline unsigned grid_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -197,21 +244,25 @@ inline unsigned grid_for(long long n, int threads) { return (unsigned)((n + thre
 struct rr_bm25_gpu_builder {
     int device = 0;
     long long n_docs = 0, n_tokens = 0, n_valid = 0, n_unique = 0, n_tiles = 0, n_postings = 0;
-    int V = 0, T = 0;
+    long long n_freq_pairs = 0, n_rare = 0;
+    int V = 0, T = 0, n_freq = 0;
     const long long* doc_off = nullptr;
     const int* tok = nullptr;
     DBuf keys, keys_alt, tmp, head, uidx, u_key, u_start, counters, key2, key2_alt, val2, val2_alt, tile_start, tile_base;
+    DBuf df, is_freq, rank, rare_cnt, rare_scan, term_slot, rare_off, tile_cnt;
     void release_all() {
         for (DBuf* b : {&keys, &keys_alt, &tmp, &head, &uidx, &u_key, &u_start, &counters, &key2, &key2_alt, &val2, &val2_alt,
-                        &tile_start, &tile_base})
+                        &tile_start, &tile_base, &df, &is_freq, &rank, &rare_cnt, &rare_scan, &term_slot, &rare_off, &tile_cnt})
             b->release();
     }
 };
 
+extern "C" int32_t rr_bm25_dir_threshold(int32_t n_tiles);
+
 extern "C" int rr_bm25_gpu_build_begin(rr_bm25_gpu_builder** out, const int64_t* d_doc_offsets, const int32_t* d_token_ids,
                                        int64_t n_docs, int64_t n_tokens, int32_t vocab_size, int32_t tile_docs,
-                                       int64_t* n_unique_out, int64_t* n_postings_out, int32_t* n_tiles_out, int device,
-                                       rr_stream stream) {
+                                       int64_t* n_unique_out, int64_t* n_postings_out, int32_t* n_tiles_out,
+                                       int32_t* n_freq_out, int device, rr_stream stream) {
     if (!out || !d_doc_offsets || n_docs <= 0 || n_tokens < 0 || vocab_size <= 0 || vocab_size > (1 << 24) || tile_docs <= 0 ||
         (tile_docs & 3) || tile_docs > 65536 || n_docs > 0xFFFFFFF0ll || (!d_token_ids && n_tokens > 0))
         return rr_fail(RR_EINVAL, "rr_bm25_gpu_build_begin: bad argument (vocab <= 2^24, tile_docs <= 65536 and a multiple of 4)");
@@ -223,7 +274,7 @@ extern "C" int rr_bm25_gpu_build_begin(rr_bm25_gpu_builder** out, const int64_t*
     h->device = device; h->n_docs = n_docs; h->n_tokens = n_tokens; h->V = vocab_size; h->T = tile_docs;
     h->doc_off = reinterpret_cast<const long long*>(d_doc_offsets); h->tok = d_token_ids;
     h->n_tiles = (n_docs + tile_docs - 1) / tile_docs;
-    if (h->n_tiles >= (1ll << 24)) return fail(rr_fail(RR_EINVAL, "too many tiles"));
+    if (h->n_tiles >= (1ll << 23)) return fail(rr_fail(RR_EINVAL, "too many tiles"));
     int rc;
     const size_t nt = (size_t)std::max<long long>(n_tokens, 1);
     if ((rc = h->keys.ensure(nt * 8)) || (rc = h->keys_alt.ensure(nt * 8)) || (rc = h->counters.ensure(64))) return fail(rc);
@@ -274,32 +325,61 @@ extern "C" int rr_bm25_gpu_build_begin(rr_bm25_gpu_builder** out, const int64_t*
                                                                        h->u_key.as<unsigned long long>(), h->u_start.as<long long>(), n_unique);
         rr_count_launch();
     }
-    // the token keys are no longer needed: their buffers become the key / value buffers of the second sort
-    // tile geometry needs the second sort's keys, which need idf: the padded posting count only needs the pairs
-    // per tile, i.e. the doc ids -> count pairs per tile now
-    if ((rc = h->tile_start.ensure(((size_t)h->n_tiles + 1) * 8)) || (rc = h->tile_base.ensure(((size_t)h->n_tiles + 1) * 8)))
+    // term classes by local document frequency, then the tile geometry of the frequent region
+    const size_t V = (size_t)vocab_size;
+    if ((rc = h->df.ensure(V * 4)) || (rc = h->is_freq.ensure(V * 4)) || (rc = h->rank.ensure(V * 4)) ||
+        (rc = h->rare_cnt.ensure(V * 8)) || (rc = h->rare_scan.ensure(V * 8)) || (rc = h->term_slot.ensure(V * 4)) ||
+        (rc = h->rare_off.ensure((V + 1) * 8)) || (rc = h->tile_cnt.ensure(((size_t)h->n_tiles + 1) * 8)) ||
+        (rc = h->tile_start.ensure(((size_t)h->n_tiles + 1) * 8)) || (rc = h->tile_base.ensure(((size_t)h->n_tiles + 1) * 8)))
         return fail(rc);
-    {
-        // pairs are doc-major, so the tile of a pair is non-decreasing in u as well
-        const long long work = std::max<long long>(n_unique, h->n_tiles + 1);
-        pair_tile_starts_kernel<<<grid_for(work, 256), 256, 0, s>>>(h->u_key.as<unsigned long long>(), n_unique, h->n_tiles,
-                                                                    tile_docs, h->tile_start.as<unsigned long long>());
-        rr_count_launch();
-        tile_bases_kernel<<<1, 32, 0, s>>>(h->tile_start.as<unsigned long long>(), h->n_tiles,
-                                           h->tile_base.as<unsigned long long>(), h->counters.as<int>() + 4);
+    cudaMemsetAsync(h->df.p, 0, V * 4, s);
+    cudaMemsetAsync(h->tile_cnt.p, 0, ((size_t)h->n_tiles + 1) * 8, s);
+    if (n_unique > 0) {
+        pair_df_kernel<<<grid_for(n_unique, 256), 256, 0, s>>>(h->u_key.as<unsigned long long>(), n_unique, h->df.as<unsigned>());
         rr_count_launch();
     }
-    unsigned long long total = 0;
+    const unsigned theta = (unsigned)rr_bm25_dir_threshold((int32_t)h->n_tiles);
+    classify_kernel<<<grid_for((long long)V, 256), 256, 0, s>>>(h->df.as<unsigned>(), vocab_size, theta, h->is_freq.as<int>(),
+                                                                 h->rare_cnt.as<unsigned long long>());
+    rr_count_launch();
+    {
+        size_t t1 = 0, t2 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, t1, h->is_freq.as<int>(), h->rank.as<int>(), vocab_size, s);
+        cub::DeviceScan::ExclusiveSum(nullptr, t2, h->rare_cnt.as<unsigned long long>(), h->rare_scan.as<unsigned long long>(), vocab_size, s);
+        if ((rc = h->tmp.ensure(std::max(t1, t2)))) return fail(rc);
+        cub::DeviceScan::ExclusiveSum(h->tmp.p, t1, h->is_freq.as<int>(), h->rank.as<int>(), vocab_size, s);
+        cub::DeviceScan::ExclusiveSum(h->tmp.p, t2, h->rare_cnt.as<unsigned long long>(), h->rare_scan.as<unsigned long long>(), vocab_size, s);
+    }
+    slots_kernel<<<grid_for((long long)V, 256), 256, 0, s>>>(h->is_freq.as<int>(), h->rank.as<int>(), h->rare_scan.as<unsigned long long>(),
+                                                              h->rare_cnt.as<unsigned long long>(), vocab_size, h->term_slot.as<int>(),
+                                                              h->rare_off.as<unsigned long long>(), h->counters.as<unsigned long long>() + 4);
+    rr_count_launch();
+    if (n_unique > 0) {
+        tile_count_kernel<<<grid_for(n_unique, 256), 256, 0, s>>>(h->u_key.as<unsigned long long>(), n_unique, tile_docs,
+                                                                   h->term_slot.as<int>(), h->tile_cnt.as<unsigned long long>());
+        rr_count_launch();
+    }
+    tile_bases_kernel<<<1, 32, 0, s>>>(h->tile_cnt.as<unsigned long long>(), h->n_tiles, h->tile_start.as<unsigned long long>(),
+                                       h->tile_base.as<unsigned long long>(), h->counters.as<int>() + 4);
+    rr_count_launch();
+    unsigned long long total = 0, freq_pairs = 0, totals[2] = {0, 0};
     int overflow = 0;
     cudaMemcpyAsync(&total, h->tile_base.as<unsigned long long>() + h->n_tiles, 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(&freq_pairs, h->tile_start.as<unsigned long long>() + h->n_tiles, 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(totals, h->counters.as<unsigned long long>() + 4, 16, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(&overflow, h->counters.as<int>() + 4, 4, cudaMemcpyDeviceToHost, s);
     if (cudaStreamSynchronize(s) != cudaSuccess)
         return fail(rr_fail(RR_ECUDA, "tile geometry failed: %s", cudaGetErrorString(cudaGetLastError())));
     if (overflow) return fail(rr_fail(RR_EOVERFLOW, "tile has more than 2^32 postings"));
-    h->n_postings = (long long)total;
+    h->n_freq = (int)totals[0];
+    h->n_rare = (long long)totals[1];
+    h->n_freq_pairs = (long long)freq_pairs;
+    if (h->n_rare > 0xFFFFFFFFll) return fail(rr_fail(RR_EOVERFLOW, "more than 2^32 rare postings"));
+    h->n_postings = (long long)total + ((h->n_rare + 1) & ~1ll);
     if (n_unique_out) *n_unique_out = n_unique;
     if (n_postings_out) *n_postings_out = h->n_postings;
     if (n_tiles_out) *n_tiles_out = (int32_t)h->n_tiles;
+    if (n_freq_out) *n_freq_out = (int32_t)h->n_freq;
     *out = h;
     return RR_OK;
 }
@@ -323,9 +403,10 @@ extern "C" int rr_bm25_gpu_build_stats(rr_bm25_gpu_builder* h, int64_t token_pos
 }
 
 extern "C" int rr_bm25_gpu_build_finish(rr_bm25_gpu_builder* h, const double* d_idf, double avgdl, double k1, double b,
-                                        uint64_t* d_postings, uint64_t* d_tile_base, uint32_t* d_blk_off,
-                                        uint64_t* d_fwd_off, uint64_t* d_fwd_data, rr_stream stream) {
-    if (!h || !d_idf || !(avgdl > 0.0) || !d_postings || !d_tile_base || !d_blk_off || !d_fwd_off || !d_fwd_data)
+                                        uint64_t* d_postings, uint64_t* d_tile_base, uint32_t* d_dir, int32_t* d_term_slot,
+                                        uint64_t* d_rare_off, uint64_t* d_fwd_off, uint64_t* d_fwd_data, rr_stream stream) {
+    if (!h || !d_idf || !(avgdl > 0.0) || !d_postings || !d_tile_base || !d_dir || !d_term_slot || !d_rare_off || !d_fwd_off ||
+        !d_fwd_data)
         return rr_fail(RR_EINVAL, "rr_bm25_gpu_build_finish: bad argument");
     RR_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -340,7 +421,7 @@ extern "C" int rr_bm25_gpu_build_finish(rr_bm25_gpu_builder* h, const double* d_
     RR_LAUNCH_CHECK();
     if (nu > 0) {
         impacts_kernel<<<grid_for(nu, 256), 256, 0, s>>>(h->u_key.as<unsigned long long>(), h->u_start.as<long long>(), nu,
-                                                          h->doc_off, d_idf, avgdl, k1, b, h->T,
+                                                          h->doc_off, d_idf, avgdl, k1, b, h->T, h->term_slot.as<int>(),
                                                           reinterpret_cast<unsigned long long*>(d_fwd_data),
                                                           h->key2.as<unsigned long long>(), h->val2.as<unsigned long long>());
         RR_LAUNCH_CHECK();
@@ -354,17 +435,17 @@ extern "C" int rr_bm25_gpu_build_finish(rr_bm25_gpu_builder* h, const double* d_
         if (kb.Current() != h->key2.as<unsigned long long>()) std::swap(h->key2, h->key2_alt);
         if (vb.Current() != h->val2.as<unsigned long long>()) std::swap(h->val2, h->val2_alt);
     }
-    tile_starts_kernel<<<grid_for(std::max<long long>(nu, h->n_tiles + 1), 256), 256, 0, s>>>(
-        h->key2.as<unsigned long long>(), nu, h->n_tiles, h->tile_start.as<unsigned long long>());
-    RR_LAUNCH_CHECK();
     RR_CUDA(cudaMemcpyAsync(d_tile_base, h->tile_base.p, ((size_t)h->n_tiles + 1) * 8, cudaMemcpyDeviceToDevice, s));
-    const long long n_blk = h->n_tiles * ((long long)h->V + 1);
-    blk_off_kernel<<<grid_for(n_blk, 256), 256, 0, s>>>(h->key2.as<unsigned long long>(), h->tile_start.as<unsigned long long>(),
-                                                         h->n_tiles, h->V, d_blk_off);
+    RR_CUDA(cudaMemcpyAsync(d_term_slot, h->term_slot.p, (size_t)h->V * 4, cudaMemcpyDeviceToDevice, s));
+    RR_CUDA(cudaMemcpyAsync(d_rare_off, h->rare_off.p, ((size_t)h->V + 1) * 8, cudaMemcpyDeviceToDevice, s));
+    const long long n_dir = h->n_tiles * ((long long)h->n_freq + 1);
+    dir_kernel<<<grid_for(n_dir, 256), 256, 0, s>>>(h->key2.as<unsigned long long>(), h->tile_start.as<unsigned long long>(),
+                                                     h->n_tiles, h->n_freq, d_dir);
     RR_LAUNCH_CHECK();
-    scatter_postings_kernel<<<grid_for(std::max<long long>(nu, h->n_tiles), 256), 256, 0, s>>>(
-        h->key2.as<unsigned long long>(), h->val2.as<unsigned long long>(), nu, h->tile_start.as<unsigned long long>(),
-        h->tile_base.as<unsigned long long>(), h->n_tiles, reinterpret_cast<unsigned long long*>(d_postings));
+    scatter_postings_kernel<<<grid_for(std::max<long long>(std::max<long long>(nu, h->n_tiles), 1), 256), 256, 0, s>>>(
+        h->key2.as<unsigned long long>(), h->val2.as<unsigned long long>(), nu, h->n_freq_pairs,
+        h->tile_start.as<unsigned long long>(), h->tile_base.as<unsigned long long>(), h->n_tiles,
+        reinterpret_cast<unsigned long long*>(d_postings));
     RR_LAUNCH_CHECK();
     return RR_OK;
 }

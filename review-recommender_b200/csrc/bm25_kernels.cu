@@ -1,26 +1,33 @@
-// K1 -- BM25 scoring over the tile-blocked CSR postings (sm_100a).
+// K1 -- BM25 scoring over the hybrid-blocked postings (sm_100a).
 //
 // Stands behind rank_bm25.BM25Okapi.get_scores as the reference calls it
 // (app/test.py:170, app/app_product_search.py:206) and behind the candidate gathers that follow
 // it (app/test.py:171-173, app/app_product_search.py:207-208).
 //
-// Layout (built by bm25_build.cpp on the host or bm25_build_gpu.cu on the device): docs are cut into tiles of T docs.  Inside tile i the
-// postings {u32 doc, f32 impact} are grouped by term (doc ascending inside a term);
-// blk_off[i*(V+1)+t .. +t+1] bounds term t's segment relative to tile_base[i] (always even, so
-// a tile's postings start on a 16-byte boundary).
+// Layout (include/rr_b200.h "index layout"; built by bm25_build.cpp on the host or bm25_build_gpu.cu on the device):
+// docs are cut into tiles of T docs.  FREQUENT terms (directory slot f = term_slot[t]) are tile-blocked: inside tile i
+// the postings {u32 doc, f32 impact} are grouped by slot, doc-ascending, bounded by dir[i*(n_freq+1)+f .. +f+1]
+// relative to tile_base[i] (tiles start on a 16-byte boundary).  RARE terms have one term-major, doc-ascending list
+// behind the frequent region; bm25_rare_bounds_kernel finds, per batch, where every tile starts in the lists of the
+// batch's rare query terms.
 //
-//  bm25_tile_scores_kernel   one CTA per (tile, query): T fp32 accumulators live in shared
-//      memory, the CTA streams the <= L segments of its query's terms with 16-byte loads
-//      (2 postings per load, 4 loads in flight per thread; latency is hidden by 4 resident
-//      CTAs per SM), adds impacts in QUERY-TERM ORDER (a barrier
-//      separates consecutive terms, postings of one term hit distinct docs so plain
-//      read-modify-write is race free), then writes the tile's scores coalesced.
-//      HBM traffic = 8 B per posting of the query's terms + 4 B per doc: the algorithmic bytes.
-//      Summation order = the reference's (`score += ...` per query token), in fp32.
+//  bm25_tile_scores_kernel   one CTA per (query, tile): T fp32 accumulators live in shared memory.  A PRODUCER warp
+//      streams the <= 64 term segments of the CTA with 1-D TMA bulk copies (cp.async.bulk, mbarrier complete_tx)
+//      into a shared-memory ring, running up to NSTAGE chunks ahead of the eight CONSUMER warps, which add the
+//      impacts in QUERY-TERM ORDER (a named barrier separates consecutive terms; postings of one term hit distinct
+//      docs, so the plain read-modify-write is race free and the fp32 sum is deterministic), then write the tile's
+//      scores with coalesced 16-byte stores.  Loads are decoupled from the per-term barriers: the r01 kernel issued
+//      a round of register loads only after the previous round's adds (ncu: long-scoreboard + barrier stalls).
+//      The grid is query-fastest, so the CTAs that share a tile (and, for common terms, its segments) run together
+//      and the shared segments are served by L2.
+//      HBM traffic <= 8 B per posting of the query's terms + 4 B per doc: the algorithmic bytes.
+//      Summation: fp32 adds in the order of the query's token list.  rank_bm25 adds float64 terms and the callers cast
+//      once to float32; here every term is the correctly rounded fp32 of the float64 term and the adds are fp32, so
+//      a score differs from the reference's by at most ~L * 2^-24 relative (tests pin 1e-5, north_star's bound).
 //
 //  bm25_candidates_kernel    one thread per (query, candidate): binary search of each query
 //      term in the candidate's forward list (or of the candidate's doc id inside the term's
-//      segment of the doc's tile when no forward index is loaded); same impacts, same order =>
+//      segment / rare list when no forward index is loaded); same impacts, same order =>
 //      bit-identical to the tile kernel at those docs.  Also gathers n_reviews / avg_stars /
 //      global row so that the fusion kernel gets complete tuples, optionally straight into the
 //      all-to-all send buffer of a sharded search.
@@ -31,147 +38,202 @@
 
 namespace {
 
-constexpr int BM25_THREADS = 256;
-constexpr int BM25_U = 4;       // 16-byte units (2 postings each) per thread per round
-constexpr int BM25_MAXL = 64;   // query terms staged per pass over the accumulators
-constexpr int BM25_MIN_CTAS = 4;
+constexpr int BM25_CONSUMERS = 256;                 // 8 consumer warps
+constexpr int BM25_THREADS = BM25_CONSUMERS + 32;   // + 1 producer warp
+constexpr int BM25_MAXL = 64;                       // query terms staged per pass over the accumulators
+constexpr int BM25_MAX_STAGES = 8;
 
-__device__ __forceinline__ uint4 ldg_stream16(const uint4* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "BM25_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra BM25_DONE;\n\t"
+        "bra BM25_WAIT;\n\t"
+        "BM25_DONE:\n\t"
+        "}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA: `bytes` (multiple of 16) from global to shared, completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(BM25_CONSUMERS) : "memory"); }
 
-// One CTA per (doc tile, query).  Latency is hidden by residency (4 CTAs of 256 threads per SM with 12288-doc
-// tiles = 48 KB of accumulators each; every thread keeps 4 x 16 B loads in flight), not by register double-buffering:
-// the r01 profile showed the double-buffered 512-thread version at 92 registers -> 1 CTA/SM -> 31 % of HBM.
-__global__ void __launch_bounds__(BM25_THREADS, BM25_MIN_CTAS)
-bm25_tile_scores_kernel(const uint4* __restrict__ postings, const uint64_t* __restrict__ tile_base,
-                        const uint32_t* __restrict__ blk_off, int V, int T, long long n_docs,
-                        const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_len, int l_max,
-                        float* __restrict__ out, long long ld_out) {
-    extern __shared__ __align__(16) float acc[];
-    __shared__ uint32_t s_lo[BM25_MAXL], s_hi[BM25_MAXL];
-    __shared__ uint32_t s_ustart[BM25_MAXL + 1];
+struct Bm25Args {
+    const uint4* postings;            // 16-byte units (2 postings each)
+    const uint64_t* tile_base;        // [n_tiles+1]
+    const uint32_t* dir;              // [n_tiles, n_freq+1]
+    const int32_t* term_slot;         // [V]
+    const uint32_t* rtab;             // [B, l_max, n_tiles+1] rare-list tile bounds of this batch (relative to the rare region)
+    int V, T, n_freq, n_tiles, tile0;
+    long long n_docs;
+    const int32_t* q_terms;
+    const int32_t* q_len;
+    int l_max;
+    float* out;
+    long long ld_out;
+    int stage_units, n_stages;
+};
 
-    const int tile = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
-    const long long doc0 = (long long)tile * T;
+__global__ void __launch_bounds__(BM25_THREADS, 4)
+bm25_tile_scores_kernel(const Bm25Args a) {
+    extern __shared__ __align__(16) unsigned char bm25_smem[];
+    float* acc = reinterpret_cast<float*>(bm25_smem);
+    uint4* ring = reinterpret_cast<uint4*>(bm25_smem + (size_t)a.T * sizeof(float));
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)a.n_stages * a.stage_units);
+    uint64_t* empty = full + BM25_MAX_STAGES;
+    __shared__ unsigned long long s_lo[BM25_MAXL], s_hi[BM25_MAXL];
+
+    const int q = blockIdx.x, tile = a.tile0 + blockIdx.y, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const bool producer = warp == BM25_CONSUMERS / 32;
+    const long long doc0 = (long long)tile * a.T;
     const uint32_t doc0u = (uint32_t)doc0;
-    const int tile_n = (int)min((long long)T, n_docs - doc0);
+    const int tile_n = (int)min((long long)a.T, a.n_docs - doc0);
+    const int SU = a.stage_units, NS = a.n_stages;
 
-    int L = q_len[q];
-    if (L > l_max) L = l_max;
-    const uint4* base = postings + (tile_base[tile] >> 1);
-    const uint32_t* off = blk_off + (long long)tile * (V + 1);
-    constexpr int R = BM25_THREADS * BM25_U;
+    int L = a.q_len[q];
+    if (L > a.l_max) L = a.l_max;
+    if (tid == 0) {
+        for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], BM25_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (!producer)
+        for (int i = tid; i < a.T / 4; i += BM25_CONSUMERS) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    for (int i = tid; i < T / 4; i += BM25_THREADS) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-
+    int stage = 0;
+    uint32_t phase = 0;
+    bool dirty = false;                 // consumers: some term has been accumulated since the last consumer barrier
     for (int l0 = 0; l0 < L; l0 += BM25_MAXL) {
         const int nl = min(BM25_MAXL, L - l0);
-        __syncthreads();   // previous pass done with s_*, accumulators zeroed / settled
+        __syncthreads();                // barriers initialised / previous pass done with s_lo, s_hi
         if (tid < nl) {
-            const int t = q_terms[(long long)q * l_max + l0 + tid];
-            uint32_t lo = 0, hi = 0;
-            if (t >= 0 && t < V) { lo = off[t]; hi = off[t + 1]; }
+            const int l = l0 + tid;
+            const int t = a.q_terms[(long long)q * a.l_max + l];
+            unsigned long long lo = 0, hi = 0;
+            if (t >= 0 && t < a.V) {
+                const int slot = a.term_slot[t];
+                if (slot >= 0) {
+                    const unsigned long long base = a.tile_base[tile];
+                    const uint32_t* d = a.dir + (long long)tile * (a.n_freq + 1) + slot;
+                    lo = base + d[0];
+                    hi = base + d[1];
+                } else if (a.rtab != nullptr) {
+                    const unsigned long long base = a.tile_base[a.n_tiles];
+                    const uint32_t* r = a.rtab + ((long long)q * a.l_max + l) * (a.n_tiles + 1) + tile;
+                    lo = base + r[0];
+                    hi = base + r[1];
+                }
+            }
             s_lo[tid] = lo;
             s_hi[tid] = hi;
         }
         __syncthreads();
-        if (tid < 32) {
-            // exclusive scan of the per-term unit counts (nl <= 64: two per lane)
-            const int i0 = tid, i1 = tid + 32;
-            uint32_t u0 = 0, u1 = 0;
-            if (i0 < nl) { const uint32_t lo = s_lo[i0], hi = s_hi[i0]; u0 = hi > lo ? ((hi + 1) >> 1) - (lo >> 1) : 0u; }
-            if (i1 < nl) { const uint32_t lo = s_lo[i1], hi = s_hi[i1]; u1 = hi > lo ? ((hi + 1) >> 1) - (lo >> 1) : 0u; }
-            uint32_t x0 = u0, x1 = u1;
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o);
-                if (tid >= o) { x0 += y0; x1 += y1; }
-            }
-            const uint32_t tot0 = __shfl_sync(0xffffffffu, x0, 31);
-            if (i0 < nl) s_ustart[i0] = x0 - u0;
-            if (i1 < nl) s_ustart[i1] = tot0 + x1 - u1;
-            if (tid == 31) s_ustart[nl] = tot0 + x1;      // lane 31's inclusive sums are the totals
-        }
-        __syncthreads();
-        const uint32_t total = s_ustart[nl];
-        if (total == 0) continue;
-        const int n_rounds = (int)((total + R - 1) / R);
-
-        int load_cursor = 0;     // per-thread, monotone
-        int phase_first = 0;     // block-uniform, monotone
-        int prev_seg = -1;       // block-uniform: last term accumulated
-
-        // issue this thread's BM25_U 16-byte loads of round r (no wait)
-        auto load_round = [&](int r, uint4 (&p)[BM25_U], uint32_t (&unit_of)[BM25_U], int (&seg)[BM25_U]) {
-#pragma unroll
-            for (int u = 0; u < BM25_U; ++u) {
-                const uint32_t v = (uint32_t)(r * R + u * BM25_THREADS + tid);
-                seg[u] = -1;
-                if (v < total) {
-                    while (v >= s_ustart[load_cursor + 1]) ++load_cursor;
-                    const uint32_t unit = (s_lo[load_cursor] >> 1) + (v - s_ustart[load_cursor]);
-                    p[u] = ldg_stream16(base + unit);
-                    unit_of[u] = unit;
-                    seg[u] = load_cursor;
-                }
-            }
-        };
-        // add round r's impacts, term by term in query order (a barrier separates consecutive terms)
-        auto add_round = [&](int r, const uint4 (&p)[BM25_U], const uint32_t (&unit_of)[BM25_U], const int (&seg)[BM25_U]) {
-            const uint32_t v_first = (uint32_t)r * R;
-            const uint32_t v_last = min(total, v_first + (uint32_t)R) - 1u;
-            while (v_first >= s_ustart[phase_first + 1]) ++phase_first;
-            int phase_last = phase_first;
-            while (v_last >= s_ustart[phase_last + 1]) ++phase_last;
-            for (int s = phase_first; s <= phase_last; ++s) {
-                if (s_ustart[s + 1] == s_ustart[s]) continue;
-                if (s != prev_seg) {
-                    __syncthreads();    // all adds of the previous term are done
-                    prev_seg = s;
-                }
-                const uint32_t lo = s_lo[s], hi = s_hi[s];
-#pragma unroll
-                for (int u = 0; u < BM25_U; ++u) {
-                    if (seg[u] == s) {
-                        const uint32_t i0 = unit_of[u] * 2u;
-                        if (i0 >= lo && i0 < hi) {
-                            const uint32_t d = p[u].x - doc0u;
-                            acc[d] = __fadd_rn(acc[d], __uint_as_float(p[u].y));
-                        }
-                        if (i0 + 1u >= lo && i0 + 1u < hi) {
-                            const uint32_t d = p[u].z - doc0u;
-                            acc[d] = __fadd_rn(acc[d], __uint_as_float(p[u].w));
-                        }
+        if (producer) {
+            // ===== producer warp (one lane issues): chunk c of term l -> ring stage, up to NS chunks ahead =====
+            if (lane == 0) {
+                for (int l = 0; l < nl; ++l) {
+                    const unsigned long long lo = s_lo[l], hi = s_hi[l];
+                    if (hi <= lo) continue;
+                    const unsigned long long u0 = lo >> 1, u1 = (hi + 1) >> 1;
+                    for (unsigned long long u = u0; u < u1; u += (unsigned long long)SU) {
+                        const uint32_t n = (uint32_t)min((unsigned long long)SU, u1 - u);
+                        mbar_wait(&empty[stage], phase ^ 1u);
+                        mbar_expect_tx(&full[stage], n * 16u);
+                        bulk_g2s(ring + (size_t)stage * SU, a.postings + u, n * 16u, &full[stage]);
+                        if (++stage == NS) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
-        };
-
-        // one round of loads in flight per thread.  Issuing round r+1 before accumulating round r (two rounds in
-        // flight, 80 registers, 3 CTAs/SM) was measured SLOWER on B200 (r02: 49 % vs 62 % of HBM peak at 8 M docs),
-        // as was the 512-thread register double buffer of r01: latency is hidden by residency instead.
-        uint4 pa[BM25_U];
-        uint32_t ua[BM25_U];
-        int sa[BM25_U];
-        for (int r = 0; r < n_rounds; ++r) {
-            load_round(r, pa, ua, sa);
-            add_round(r, pa, ua, sa);
+        } else {
+            // ===== consumers: impacts added term by term in query order =====
+            for (int l = 0; l < nl; ++l) {
+                const unsigned long long lo = s_lo[l], hi = s_hi[l];
+                if (hi <= lo) continue;
+                if (dirty) consumer_barrier();          // all adds of the previous term are done
+                dirty = true;
+                const uint32_t n_post = (uint32_t)(hi - lo);
+                const int odd = (int)(lo & 1ull);
+                const uint32_t n_units = (uint32_t)(((hi + 1) >> 1) - (lo >> 1));
+                for (uint32_t c0 = 0; c0 < n_units; c0 += (uint32_t)SU) {
+                    const uint32_t n = min((uint32_t)SU, n_units - c0);
+                    mbar_wait(&full[stage], phase);
+                    const uint4* src = ring + (size_t)stage * SU;
+                    for (uint32_t u = (uint32_t)tid; u < n; u += BM25_CONSUMERS) {
+                        const uint4 p = src[u];
+                        const int r0 = (int)(2u * (c0 + u)) - odd;        // posting index relative to lo (-1: before it)
+                        if ((uint32_t)r0 < n_post) {
+                            const uint32_t d = p.x - doc0u;
+                            acc[d] = __fadd_rn(acc[d], __uint_as_float(p.y));
+                        }
+                        if ((uint32_t)(r0 + 1) < n_post) {
+                            const uint32_t d = p.z - doc0u;
+                            acc[d] = __fadd_rn(acc[d], __uint_as_float(p.w));
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[stage]);
+                    if (++stage == NS) { stage = 0; phase ^= 1u; }
+                }
+            }
         }
     }
-    __syncthreads();
-    float* dst = out + (long long)q * ld_out + doc0;
+    if (producer) return;
+    consumer_barrier();
+    float* dst = a.out + (long long)q * a.ld_out + doc0;
     const int n4 = tile_n >> 2;
-    for (int i = tid; i < n4; i += BM25_THREADS) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(acc)[i];
-    for (int i = (n4 << 2) + tid; i < tile_n; i += BM25_THREADS) dst[i] = acc[i];
+    for (int i = tid; i < n4; i += BM25_CONSUMERS) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(acc)[i];
+    for (int i = (n4 << 2) + tid; i < tile_n; i += BM25_CONSUMERS) dst[i] = acc[i];
+}
+
+// Where tile i starts in the list of every RARE term of the batch: rtab[(q*l_max + l)*(n_tiles+1) + i] = number of
+// postings of the term with doc < i*T (i = n_tiles: the list length).  One thread per (query, term slot, tile).
+__global__ void __launch_bounds__(256)
+bm25_rare_bounds_kernel(const uint2* __restrict__ postings, const uint64_t* __restrict__ tile_base,
+                        const int32_t* __restrict__ term_slot, const unsigned long long* __restrict__ rare_off, int V, int T,
+                        int n_tiles, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_len, int l_max, int B,
+                        uint32_t* __restrict__ rtab) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per_q = (long long)l_max * (n_tiles + 1);
+    if (gid >= (long long)B * per_q) return;
+    const int q = (int)(gid / per_q);
+    const int l = (int)((gid - (long long)q * per_q) / (n_tiles + 1));
+    const int i = (int)(gid - (long long)q * per_q - (long long)l * (n_tiles + 1));
+    if (l >= q_len[q]) return;
+    const int t = q_terms[(long long)q * l_max + l];
+    if (t < 0 || t >= V || term_slot[t] >= 0) return;
+    const unsigned long long b0 = rare_off[t], b1 = rare_off[t + 1];
+    const uint2* list = postings + tile_base[n_tiles] + b0;
+    uint32_t lo = 0, hi = (uint32_t)(b1 - b0);
+    if (i < n_tiles) {
+        const uint32_t target = (uint32_t)((long long)i * T);
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&list[mid].x) < target) lo = mid + 1; else hi = mid;
+        }
+    } else {
+        lo = hi;
+    }
+    rtab[gid] = (uint32_t)b0 + lo;
 }
 
 __global__ void __launch_bounds__(256)
 bm25_candidates_kernel(const uint2* __restrict__ postings, const uint64_t* __restrict__ tile_base,
-                       const uint32_t* __restrict__ blk_off, const unsigned long long* __restrict__ fwd_off,
+                       const uint32_t* __restrict__ dir, const int32_t* __restrict__ term_slot,
+                       const unsigned long long* __restrict__ rare_off, int n_freq, int n_tiles,
+                       const unsigned long long* __restrict__ fwd_off,
                        const uint2* __restrict__ fwd_data, int V, int T, long long n_docs,
                        const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_len, int l_max,
                        const long long* __restrict__ cand, int pool, int B,
@@ -220,21 +282,31 @@ bm25_candidates_kernel(const uint2* __restrict__ postings, const uint64_t* __res
             }
         }
     } else if (valid && V > 0 && q_terms != nullptr) {
+        // no forward index: look the doc up in the term's segment of the doc's tile (frequent) or in its list (rare)
         const int tile = (int)(doc / T);
-        const uint2* base = postings + tile_base[tile];
-        const uint32_t* off = blk_off + (long long)tile * (V + 1);
         const uint32_t d = (uint32_t)doc;
         int L = q_len[q];
         if (L > l_max) L = l_max;
         for (int l = 0; l < L; ++l) {
             const int t = q_terms[(long long)q * l_max + l];
             if (t < 0 || t >= V) continue;
-            uint32_t lo = off[t], hi = off[t + 1];
-            while (lo < hi) {                       // lower_bound on the doc ids of the segment
+            const int slot = term_slot[t];
+            const uint2* base;
+            uint32_t lo, end;
+            if (slot >= 0) {
+                const uint32_t* off = dir + (long long)tile * (n_freq + 1) + slot;
+                base = postings + tile_base[tile];
+                lo = off[0]; end = off[1];
+            } else {
+                base = postings + tile_base[n_tiles] + rare_off[t];
+                lo = 0; end = (uint32_t)(rare_off[t + 1] - rare_off[t]);
+            }
+            uint32_t hi = end;
+            while (lo < hi) {                       // lower_bound on the doc ids
                 const uint32_t mid = (lo + hi) >> 1;
                 if (__ldg(&base[mid].x) < d) lo = mid + 1; else hi = mid;
             }
-            if (lo < off[t + 1]) {
+            if (lo < end) {
                 const uint2 e = __ldg(&base[lo]);
                 if (e.x == d) sum = __fadd_rn(sum, __uint_as_float(e.y));
             }
@@ -251,12 +323,25 @@ bm25_candidates_kernel(const uint2* __restrict__ postings, const uint64_t* __res
 
 }  // namespace
 
-int rr_launch_bm25_tile_scores(const uint64_t* d_postings, const uint64_t* d_tile_base, const uint32_t* d_blk_off,
-                               int V, int T, int n_tiles, int64_t n_docs, const int32_t* d_terms,
-                               const int32_t* d_nterms, int B, int l_max, float* d_out, int64_t ld_out,
-                               cudaStream_t stream) {
-    if (B <= 0 || n_tiles <= 0) return RR_OK;
-    const size_t smem = (size_t)T * sizeof(float);
+size_t rr_bm25_rtab_bytes(int B, int l_max, int n_tiles) {
+    return sizeof(uint32_t) * (size_t)B * (size_t)l_max * ((size_t)n_tiles + 1);
+}
+
+static int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* e = getenv(name);
+    if (!e) return dflt;
+    const int v = atoi(e);
+    return v < lo || v > hi ? dflt : v;
+}
+
+int rr_launch_bm25_tile_scores(const rr_index_desc* d, const int32_t* d_terms, const int32_t* d_nterms, int B, int l_max,
+                               float* d_out, int64_t ld_out, uint32_t* d_rtab, cudaStream_t stream) {
+    if (B <= 0 || d->n_tiles <= 0) return RR_OK;
+    const int T = d->tile_docs;
+    // ring geometry: NSTAGE chunks of STAGE_UNITS 16-byte units in flight per CTA (defaults: 4 x 4 KB)
+    const int SU = env_int("RR_BM25_STAGE_UNITS", 256, 32, 4096) / 32 * 32;
+    const int NS = env_int("RR_BM25_STAGES", 4, 2, BM25_MAX_STAGES);
+    const size_t smem = (size_t)T * sizeof(float) + (size_t)NS * SU * 16 + 2 * BM25_MAX_STAGES * sizeof(uint64_t);
     static RrSmemOptIn optin;
     int dev = 0;
     if (optin.needed(smem, &dev)) {
@@ -265,22 +350,33 @@ int rr_launch_bm25_tile_scores(const uint64_t* d_postings, const uint64_t* d_til
         RR_CUDA(cudaFuncSetAttribute(bm25_tile_scores_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         optin.done(smem, dev);
     }
-    for (int b0 = 0; b0 < B; b0 += 65535) {
-        const int nb = min(65535, B - b0);
-        dim3 grid((unsigned)n_tiles, (unsigned)nb);
+    if (d_rtab != nullptr) {
+        const long long total = (long long)B * l_max * (d->n_tiles + 1);
+        RrProfScope prof(RR_PROF_MISC, stream);
+        bm25_rare_bounds_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+            reinterpret_cast<const uint2*>(d->d_postings), d->d_tile_base, d->d_term_slot,
+            reinterpret_cast<const unsigned long long*>(d->d_rare_off), d->vocab_size, T, d->n_tiles, d_terms, d_nterms, l_max, B,
+            d_rtab);
+        RR_LAUNCH_CHECK();
+    }
+    Bm25Args a;
+    a.postings = reinterpret_cast<const uint4*>(d->d_postings); a.tile_base = d->d_tile_base; a.dir = d->d_dir;
+    a.term_slot = d->d_term_slot; a.rtab = d_rtab; a.V = d->vocab_size; a.T = T; a.n_freq = d->n_freq; a.n_tiles = d->n_tiles;
+    a.n_docs = d->n_docs; a.q_terms = d_terms; a.q_len = d_nterms; a.l_max = l_max; a.out = d_out; a.ld_out = ld_out;
+    a.stage_units = SU; a.n_stages = NS;
+    // grid: query fastest, so that the CTAs sharing a tile (and the segments of common terms) are co-resident
+    for (int t0 = 0; t0 < d->n_tiles; t0 += 65535) {
+        a.tile0 = t0;
+        dim3 grid((unsigned)B, (unsigned)min(65535, d->n_tiles - t0));
         RrProfScope prof(RR_PROF_BM25_TILE, stream);
-        bm25_tile_scores_kernel<<<grid, BM25_THREADS, smem, stream>>>(
-            reinterpret_cast<const uint4*>(d_postings), d_tile_base, d_blk_off, V, T, (long long)n_docs,
-            d_terms + (int64_t)b0 * l_max, d_nterms + b0, l_max, d_out + (int64_t)b0 * ld_out, (long long)ld_out);
+        bm25_tile_scores_kernel<<<grid, BM25_THREADS, smem, stream>>>(a);
         RR_LAUNCH_CHECK();
     }
     return RR_OK;
 }
 
-int rr_launch_bm25_candidates(const uint64_t* d_postings, const uint64_t* d_tile_base, const uint32_t* d_blk_off,
-                              const uint64_t* d_fwd_off, const uint64_t* d_fwd_data, int V, int T, int64_t n_docs, const int32_t* d_terms, const int32_t* d_nterms,
-                              int B, int l_max, const int64_t* d_cand, int pool, const double* d_nrev,
-                              const double* d_avg, int64_t row_offset, float* d_bm25, double* d_n_out,
+int rr_launch_bm25_candidates(const rr_index_desc* d, int V, const int32_t* d_terms, const int32_t* d_nterms,
+                              int B, int l_max, const int64_t* d_cand, int pool, float* d_bm25, double* d_n_out,
                               double* d_avg_out, int64_t* d_grow_out, cudaStream_t stream, int pack_bg,
                               int64_t pack_stride, const float* d_dense_in, float* d_dense_out,
                               const int32_t* d_uncertified) {
@@ -290,10 +386,11 @@ int rr_launch_bm25_candidates(const uint64_t* d_postings, const uint64_t* d_tile
     RrProfScope prof(RR_PROF_BM25_CAND, stream);
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
     bm25_candidates_kernel<<<blocks, threads, 0, stream>>>(
-        reinterpret_cast<const uint2*>(d_postings), d_tile_base, d_blk_off,
-        reinterpret_cast<const unsigned long long*>(d_fwd_off), reinterpret_cast<const uint2*>(d_fwd_data), V, T,
-        (long long)n_docs, d_terms, d_nterms,
-        l_max, reinterpret_cast<const long long*>(d_cand), pool, B, d_nrev, d_avg, (long long)row_offset, d_bm25,
+        reinterpret_cast<const uint2*>(d->d_postings), d->d_tile_base, d->d_dir, d->d_term_slot,
+        reinterpret_cast<const unsigned long long*>(d->d_rare_off), d->n_freq, d->n_tiles,
+        reinterpret_cast<const unsigned long long*>(d->d_fwd_off), reinterpret_cast<const uint2*>(d->d_fwd_data), V,
+        d->tile_docs > 0 ? d->tile_docs : 1, (long long)d->n_docs, d_terms, d_nterms,
+        l_max, reinterpret_cast<const long long*>(d_cand), pool, B, d->d_n_reviews, d->d_avg_stars, (long long)d->row_offset, d_bm25,
         d_n_out, d_avg_out, reinterpret_cast<long long*>(d_grow_out), pack_bg, (long long)pack_stride, d_dense_in,
         d_dense_out, d_uncertified);
     RR_LAUNCH_CHECK();

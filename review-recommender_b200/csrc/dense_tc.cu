@@ -794,6 +794,21 @@ __global__ void tc_scatter_results_kernel(const int* __restrict__ flagged, int p
     if (threadIdx.x == 0 && cnt) cnt[dst] = cnt_in[blockIdx.x];
 }
 
+// debug: scatter the (score bits, doc) candidates of an all-pass filter launch into a dense [B, n_rows] matrix
+__global__ void tc_debug_scatter_kernel(const unsigned long long* __restrict__ cand_keys, const unsigned* __restrict__ cand_cnt,
+                                        int n_sub, int cap_sub, long long row0, int n_rows, float* __restrict__ out) {
+    const int q = blockIdx.x;
+    for (int s = 0; s < n_sub; ++s) {
+        const unsigned cnt = min(cand_cnt[(size_t)q * n_sub + s], (unsigned)cap_sub);
+        const unsigned long long* src = cand_keys + ((size_t)q * n_sub + s) * cap_sub;
+        for (unsigned e = threadIdx.x; e < cnt; e += blockDim.x) {
+            const unsigned long long k = src[e];
+            const long long r = (long long)(k >> 32) - row0;
+            if (r >= 0 && r < n_rows) out[(size_t)q * n_rows + r] = __uint_as_float((uint32_t)k);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1098,5 +1113,70 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
                                                      reinterpret_cast<long long*>(d_idx), d_sims, d_count);
         RR_LAUNCH_CHECK();
     }
+    return RR_OK;
+}
+
+// Debug / test entry: the raw bf16 x bf16 -> fp32 tensor-core scores of rows [row0, row0 + n_rows) for up to 128
+// queries, exactly as tc_filter_kernel sees them (tau = -inf, every score is kept), so that the stated tolerance of
+// the shortlist stage ("within 1e-3 absolute before rescoring") can be asserted against the exact similarities.
+int rr_tc_debug_scores(rr_tc_state** state, const rr_index_desc* d, int sm_count, const float* d_q, int32_t B,
+                       int64_t row0, int32_t n_rows, float* d_out, cudaStream_t s) {
+    if (B <= 0 || B > TC_BM) return rr_fail(RR_EINVAL, "rr_dense_debug_bf16_scores: 1..%d queries", TC_BM);
+    if (row0 < 0 || (row0 % TC_BN) || n_rows <= 0 || row0 + n_rows > d->n_docs)
+        return rr_fail(RR_EINVAL, "rr_dense_debug_bf16_scores: row0 must be a multiple of %d and the range inside the corpus", TC_BN);
+    const int n_dt = (n_rows + TC_BN - 1) / TC_BN;
+    if (n_dt > sm_count) return rr_fail(RR_EINVAL, "rr_dense_debug_bf16_scores: at most %d rows per call", sm_count * TC_BN);
+    if (d->dim_pad > TC_MAX_KB_STREAMED * TC_BK) return rr_fail(RR_EUNSUPPORTED, "tensor path supports dim <= %d", TC_MAX_KB_STREAMED * TC_BK);
+    if (!*state) {
+        *state = new (std::nothrow) rr_tc_state();
+        if (!*state) return rr_fail(RR_ENOMEM, "out of host memory");
+    }
+    rr_tc_state* st = *state;
+    if (!st->attr_set) {
+        RR_CUDA(cudaFuncSetAttribute(tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
+        RR_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SORT_MAX * 8));
+        RR_CUDA(cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SORT_MAX * 8));
+        RR_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        RR_CUDA(cudaFuncSetAttribute(tc_select_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        RR_CUDA(cudaFuncSetAttribute(tc_select_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        RR_CUDA(cudaFuncSetAttribute(tc_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        st->attr_set = true;
+    }
+    if (st->tmap_c_base != d->d_emb_bf16) {
+        RR_TRY(make_tmap_bf16_rows(&st->tmap_c, d->d_emb_bf16, (uint64_t)d->n_docs, (uint64_t)d->dim_pad, TC_BN));
+        st->tmap_c_base = d->d_emb_bf16;
+    }
+    const int B_pad = TC_BM, reps = n_dt, n_sub = 2 * reps, cap_sub = TC_BN / 2;
+    RR_TRY(st->q_bf16.ensure(sizeof(__nv_bfloat16) * (size_t)B_pad * d->dim_pad));
+    RR_TRY(st->qnorm.ensure(sizeof(float) * (size_t)B_pad));
+    RR_TRY(st->cand_keys.ensure(sizeof(unsigned long long) * (size_t)B * n_sub * cap_sub));
+    RR_TRY(st->cand_cnt.ensure(sizeof(unsigned) * (size_t)B * n_sub));
+    RR_TRY(st->kept_cnt.ensure(sizeof(int) * (size_t)B));
+    RR_TRY(st->tau.ensure(sizeof(float) * (size_t)B));
+    RR_TRY(st->overflow.ensure(sizeof(int) * (size_t)B));
+    RR_TRY(st->flags.ensure(sizeof(int) * ((size_t)B + 1)));
+    CUtensorMap tmap_q;
+    RR_TRY(make_tmap_bf16_rows(&tmap_q, st->q_bf16.p, (uint64_t)B_pad, (uint64_t)d->dim_pad, TC_BM));
+    cvt_queries_kernel<<<B_pad, 128, 0, s>>>(d_q, B, d->dim, d->dim_pad, B_pad, static_cast<__nv_bfloat16*>(st->q_bf16.p),
+                                             static_cast<float*>(st->qnorm.p));
+    RR_LAUNCH_CHECK();
+    const int n_cnt = B * n_sub;
+    tc_reset_kernel<<<(std::max(n_cnt, B) + 255) / 256, 256, 0, s>>>(static_cast<unsigned*>(st->cand_cnt.p), n_cnt,
+                                                                     static_cast<int*>(st->kept_cnt.p), static_cast<float*>(st->tau.p),
+                                                                     static_cast<int*>(st->overflow.p), static_cast<int*>(st->flags.p), B);
+    RR_LAUNCH_CHECK();
+    TcFilterArgs a;
+    a.n_docs = d->n_docs; a.n_kb = d->dim_pad / TC_BK; a.B = B; a.qt0 = 0; a.n_qt = 1; a.reps = reps;
+    a.dt_lo = (int)(row0 / TC_BN); a.dt_hi = a.dt_lo + n_dt; a.tau = static_cast<const float*>(st->tau.p);
+    a.q_resident = d->dim_pad <= TC_MAX_KB * TC_BK ? 1 : 0;
+    a.n_sub = n_sub; a.cap_sub = cap_sub;
+    a.cand_keys = static_cast<unsigned long long*>(st->cand_keys.p);
+    a.cand_cnt = static_cast<unsigned*>(st->cand_cnt.p);
+    tc_filter_kernel<<<reps, TC_THREADS, TC_SMEM_TOTAL, s>>>(tmap_q, st->tmap_c, a);
+    RR_LAUNCH_CHECK();
+    tc_debug_scatter_kernel<<<B, 256, 0, s>>>(static_cast<const unsigned long long*>(st->cand_keys.p),
+                                              static_cast<const unsigned*>(st->cand_cnt.p), n_sub, cap_sub, (long long)row0,
+                                              n_rows, d_out);
+    RR_LAUNCH_CHECK();
     return RR_OK;
 }

@@ -21,3 +21,7 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
 // `exact` before returning.  d_uncertified != NULL (int32[B]): nothing is read back, the mask says which queries'
 // results are not proven exact.
 void rr_tc_destroy(rr_tc_state* state);
+
+// debug: raw tensor-core scores of a row range (see dense_tc.cu)
+int rr_tc_debug_scores(rr_tc_state** state, const rr_index_desc* d, int sm_count, const float* d_q, int32_t B,
+                       int64_t row0, int32_t n_rows, float* d_out, cudaStream_t s);

@@ -7,14 +7,12 @@
 #include "../../include/rr_b200.h"
 
 // bm25_kernels.cu
-int rr_launch_bm25_tile_scores(const uint64_t* d_postings, const uint64_t* d_tile_base, const uint32_t* d_blk_off,
-                               int V, int T, int n_tiles, int64_t n_docs, const int32_t* d_terms,
-                               const int32_t* d_nterms, int B, int l_max, float* d_out, int64_t ld_out,
-                               cudaStream_t stream);
-int rr_launch_bm25_candidates(const uint64_t* d_postings, const uint64_t* d_tile_base, const uint32_t* d_blk_off,
-                              const uint64_t* d_fwd_off, const uint64_t* d_fwd_data, int V, int T, int64_t n_docs, const int32_t* d_terms, const int32_t* d_nterms,
-                              int B, int l_max, const int64_t* d_cand, int pool, const double* d_nrev,
-                              const double* d_avg, int64_t row_offset, float* d_bm25, double* d_n_out,
+size_t rr_bm25_rtab_bytes(int B, int l_max, int n_tiles);
+int rr_launch_bm25_tile_scores(const rr_index_desc* d, const int32_t* d_terms, const int32_t* d_nterms, int B, int l_max,
+                               float* d_out, int64_t ld_out, uint32_t* d_rtab, cudaStream_t stream);
+// V = 0: no BM25 terms (scores are zero), the metadata gather still runs
+int rr_launch_bm25_candidates(const rr_index_desc* d, int V, const int32_t* d_terms, const int32_t* d_nterms,
+                              int B, int l_max, const int64_t* d_cand, int pool, float* d_bm25, double* d_n_out,
                               double* d_avg_out, int64_t* d_grow_out, cudaStream_t stream, int pack_bg = 0,
                               int64_t pack_stride = 0, const float* d_dense_in = nullptr, float* d_dense_out = nullptr,
                               const int32_t* d_uncertified = nullptr);

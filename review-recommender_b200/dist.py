@@ -238,9 +238,15 @@ class GridSearcher:
             rows, final = self.ix.hybrid_search(qs, ts, ns, fusion, mode=mode)
         if self.Q == 1:
             return rows, final
-        mine = torch.cat([rows.reshape(-1).view(torch.uint8), final.reshape(-1).view(torch.uint8)])
-        out = torch.empty((self.Q, mine.numel()), dtype=torch.uint8, device=mine.device)
+        # one byte buffer [rows int64[Bq,k] | final f32[Bq,k] | pad]: every rank's block starts 8-byte aligned whatever
+        # the parity of Bq*k (rows of the gathered buffer are viewed as int64)
+        nb_r, nb_f = Bq * k * 8, Bq * k * 4
+        nbytes = (nb_r + nb_f + 7) // 8 * 8
+        mine = torch.zeros(nbytes, dtype=torch.uint8, device=rows.device)
+        mine[:nb_r] = rows.reshape(-1).view(torch.uint8)
+        mine[nb_r:nb_r + nb_f] = final.reshape(-1).view(torch.uint8)
+        out = torch.empty((self.Q, nbytes), dtype=torch.uint8, device=mine.device)
         dist.all_gather_into_tensor(out.view(-1), mine, group=self.col_group)
-        all_rows = out[:, :Bq * k * 8].view(torch.int64).reshape(B, k)
-        all_final = out[:, Bq * k * 8:].view(torch.float32).reshape(B, k)
+        all_rows = out[:, :nb_r].view(torch.int64).reshape(B, k)
+        all_final = out[:, nb_r:nb_r + nb_f].view(torch.float32).reshape(B, k)
         return all_rows, all_final

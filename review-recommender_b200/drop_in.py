@@ -78,22 +78,47 @@ def build_gate_groups(query: str) -> List[frozenset]:
 # --------------------------------------------------------------------------------------------
 # dense
 # --------------------------------------------------------------------------------------------
-_dense_cache: Dict[Tuple, "engine.HybridIndex"] = {}
+class _DenseCacheEntry:
+    __slots__ = ("mat", "fingerprint", "ix")
+
+    def __init__(self, mat, fingerprint, ix):
+        self.mat, self.fingerprint, self.ix = mat, fingerprint, ix
+
+
+_dense_cache: Dict[Tuple, _DenseCacheEntry] = {}
+_DENSE_CACHE_MAX = 4
+
+
+def _fingerprint(mat: np.ndarray) -> int:
+    """Cheap content check of a cached matrix: CRC of up to 64 evenly spaced rows (catches in-place edits of the
+    matrix between calls without re-reading all of it; the reference function is pure)."""
+    import zlib
+    n = mat.shape[0]
+    if n == 0:
+        return 0
+    rows = np.unique(np.linspace(0, n - 1, min(n, 64)).astype(np.int64))
+    return zlib.crc32(np.ascontiguousarray(mat[rows]).tobytes())
 
 
 def _dense_index_for(mat: np.ndarray, device: str = "cuda:0") -> "engine.HybridIndex":
-    """One GPU copy per embeddings matrix (keyed on its buffer, shape and strides: the reference
-    passes the same cached `Vn` on every call)."""
+    """One GPU copy per embeddings matrix OBJECT (the reference passes the same cached `Vn` on every call).  The entry
+    holds a reference to the array, so its address cannot be handed to another array while the entry lives, a hit
+    requires `entry.mat is mat`, and a row-sample fingerprint catches in-place edits."""
     if not isinstance(mat, np.ndarray) or mat.ndim != 2:
         raise RRError("embeddings_matrix must be a 2-D NumPy array")
-    key = (mat.__array_interface__["data"][0], mat.shape, mat.strides, mat.dtype.str, device)
-    ix = _dense_cache.get(key)
-    if ix is None:
-        if len(_dense_cache) >= 4:
-            _dense_cache.pop(next(iter(_dense_cache))).close()
-        ix = engine.HybridIndex(np.ascontiguousarray(mat, dtype=np.float32), device=device,
-                                make_bf16=mat.shape[0] >= 65536 and mat.shape[1] <= 384)
-        _dense_cache[key] = ix
+    key = (id(mat), device)
+    fp = _fingerprint(mat)
+    ent = _dense_cache.get(key)
+    if ent is not None and ent.mat is mat and ent.fingerprint == fp and ent.mat.shape == (ent.ix.n_docs, ent.ix.dim):
+        _dense_cache[key] = _dense_cache.pop(key)                 # most recently used last
+        return ent.ix
+    if ent is not None:
+        _dense_cache.pop(key).ix.close()
+    while len(_dense_cache) >= _DENSE_CACHE_MAX:
+        _dense_cache.pop(next(iter(_dense_cache))).ix.close()
+    ix = engine.HybridIndex(np.ascontiguousarray(mat, dtype=np.float32), device=device,
+                            make_bf16=mat.shape[0] >= 65536 and mat.shape[1] <= 384)
+    _dense_cache[key] = _DenseCacheEntry(mat, fp, ix)
     return ix
 
 
@@ -194,8 +219,27 @@ class BM25Okapi:
         return self._ix.bm25_candidates(ids, n, cand)[0].cpu().numpy().astype(np.float64).tolist()
 
 
+def ensure_same_order(meta, bm25_skus: Sequence[str]) -> Optional[List[int]]:
+    """app/test.py:159-166: the permutation that brings the BM25 documents into meta order (duplicate SKUs in the
+    blob: the last one wins), or None when ANY meta SKU is missing from the blob -- bm25_scores then reads the
+    scores in blob order (identity)."""
+    idx_map = {s: i for i, s in enumerate(bm25_skus)}
+    try:
+        return [idx_map[s] for s in meta["sku"].astype(str).tolist()]
+    except KeyError:
+        return None
+
+
 def bm25_scores(bm25, query_tokens: List[str], order_idx: Optional[List[int]], top_idx: np.ndarray) -> np.ndarray:
     """app/test.py:168-173: full scores cast to float32, optional permutation into meta order, gather."""
+    if isinstance(bm25, BM25Okapi):
+        # same values without materialising N scores: K1 candidate mode at the documents the gather would read
+        top_idx = np.asarray(top_idx, dtype=np.int64)
+        docs = top_idx if order_idx is None else np.asarray(order_idx, dtype=np.int64)[top_idx]
+        if docs.size and (docs.min() < -bm25.corpus_size or docs.max() >= bm25.corpus_size):
+            raise IndexError(f"index {int(docs.max())} is out of bounds for axis 0 with size {bm25.corpus_size}")
+        docs = np.where(docs < 0, docs + bm25.corpus_size, docs)
+        return np.asarray(bm25.get_batch_scores(query_tokens, docs.tolist()), dtype=np.float32)
     scores_all = np.array(bm25.get_scores(query_tokens), dtype=np.float32)
     if order_idx is not None:
         scores_all = scores_all[np.array(order_idx)]
@@ -291,29 +335,52 @@ class SearchEngine:
         nrev = pd.to_numeric(self.meta.get("n_reviews", pd.Series([np.nan] * n)), errors="coerce").fillna(0).values
         avg = pd.to_numeric(self.meta.get("avg_stars", pd.Series([np.nan] * n)), errors="coerce").values
         self.vocab: Dict[str, int] = {}
-        offs = toks = None
         self.bm25_active = bm25_corpus is not None
+        self._ix_cli = None                 # second BM25 alignment, only when the CLI's identity rule applies
+        self._cli_identity = False
+        self._device = device
         if bm25_corpus is not None:
-            # align BM25 documents to meta rows: by SKU (run_search, :207-208: last duplicate wins, missing -> 0)
-            sku_to_doc = {str(s): i for i, s in enumerate(bm25_skus)}
-            # term ids in first-appearance order OF THE BLOB (the library's dict order decides the idf mean)
-            flat_offs, flat_ids, self.vocab = flatten_corpus(bm25_corpus)
+            # term ids in first-appearance order OF THE BLOB (the library's dict order decides the idf mean);
+            # document lengths / statistics are those of the blob, whatever the alignment to meta rows
+            self._flat_offs, self._flat_ids, self.vocab = flatten_corpus(bm25_corpus)
+            self._n_blob = len(self._flat_offs) - 1
             v = max(1, len(self.vocab))
-            stats = engine.BM25Stats.local(flat_offs, flat_ids, v).finalize()
-            # meta row r holds the tokens of BM25 document doc_of_row[r] (-1: no document, no postings)
+            self._stats = engine.BM25Stats.local(self._flat_offs, self._flat_ids, v).finalize()
+            # Streamlit rule (:207-208): align BM25 documents to meta rows by SKU -- the last duplicate wins, a meta
+            # row without a document scores 0.  The CLI's ensure_same_order (app/test.py:159-166) gives the same
+            # alignment when every meta SKU is in the blob, and IDENTITY order (row r <-> blob document r) otherwise.
+            sku_to_doc = {str(s): i for i, s in enumerate(bm25_skus)}
             doc_of_row = np.fromiter((sku_to_doc.get(s, -1) for s in self.meta["sku"].astype(str).tolist()),
                                      dtype=np.int64, count=n)
-            lens = np.where(doc_of_row >= 0, np.diff(flat_offs)[np.maximum(doc_of_row, 0)], 0)
-            offs = np.zeros(n + 1, dtype=np.int64)
-            np.cumsum(lens, out=offs[1:])
-            src = np.repeat(flat_offs[np.maximum(doc_of_row, 0)] - offs[:-1], lens) + np.arange(int(offs[-1]), dtype=np.int64)
-            toks = flat_ids[src] if len(src) else np.zeros(0, dtype=np.int32)
-            # document lengths / statistics are those of the blob; the index itself is built on the GPU
-            self._stats = stats
-            self.ix = engine.HybridIndex(Vn, _on_device(offs, device), _on_device(toks, device), v, nrev, avg, device=device,
-                                         stats=stats, normalize=normalize)
+            self._cli_identity = bool(np.any(doc_of_row < 0))
+            self.ix = self._build_index(Vn, doc_of_row, nrev, avg, normalize, None)
         else:
             self.ix = engine.HybridIndex(Vn, n_reviews=nrev, avg_stars=avg, device=device, normalize=normalize)
+        self._nrev, self._avg = nrev, avg
+
+    def _build_index(self, Vn, doc_of_row: np.ndarray, nrev, avg, normalize: bool, share):
+        """HybridIndex whose row r holds the tokens of BM25 document doc_of_row[r] (-1: no document, no postings);
+        the index itself is built on the GPU from the integer ids."""
+        n = len(doc_of_row)
+        lens = np.where(doc_of_row >= 0, np.diff(self._flat_offs)[np.maximum(doc_of_row, 0)], 0)
+        offs = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens, out=offs[1:])
+        src = np.repeat(self._flat_offs[np.maximum(doc_of_row, 0)] - offs[:-1], lens) + np.arange(int(offs[-1]), dtype=np.int64)
+        toks = self._flat_ids[src] if len(src) else np.zeros(0, dtype=np.int32)
+        v = max(1, len(self.vocab))
+        return engine.HybridIndex(Vn, _on_device(offs, self._device), _on_device(toks, self._device), v, nrev, avg,
+                                  device=self._device, stats=self._stats, normalize=normalize, share=share)
+
+    def _index_for(self, driver: str) -> "engine.HybridIndex":
+        """The index whose BM25 alignment the driver's rule prescribes (see __init__)."""
+        if driver == "streamlit" or not (self.bm25_active and self._cli_identity):
+            return self.ix
+        if self._ix_cli is None:
+            n = len(self.meta)
+            ident = np.arange(n, dtype=np.int64)
+            ident[ident >= self._n_blob] = -1            # the reference raises IndexError when it reads such a row
+            self._ix_cli = self._build_index(None, ident, self._nrev, self._avg, False, self.ix)
+        return self._ix_cli
 
     def _terms(self, query: str):
         toks = tokenize_query(query)
@@ -379,15 +446,19 @@ class SearchEngine:
         qmat = np.stack([np.asarray(self.encode(q), dtype=np.float32) for q in queries])
         toks = [tokenize_query(q) for q in queries]
         pool = fusion.pool
-        cand, dense, cnt = self.ix.dense_topk(qmat, pool)
+        ix = self._index_for(fusion.driver)
+        cand, dense, cnt = ix.dense_topk(qmat, pool)
+        counts = cnt.cpu().numpy()
+        cand_h = cand.cpu().numpy()
+        if ix is self._ix_cli and len(self.meta) > self._n_blob and int(cand_h.max()) >= self._n_blob:
+            # identity order with a blob shorter than meta: `scores_all[top_idx]` (app/test.py:173) raises
+            raise IndexError(f"index {int(cand_h.max())} is out of bounds for axis 0 with size {self._n_blob}")
         if self.bm25_active and any(toks):
             # a query without tokens scores zeros (:203-204) -- an empty term list does exactly that
             tid, nt = engine.HybridIndex.pack_terms([[self.vocab.get(t, -1) for t in tk] for tk in toks])
-            bm25, n, avg, grow = self.ix.candidate_tuples(tid, nt, cand)
+            bm25, n, avg, grow = ix.candidate_tuples(tid, nt, cand)
         else:
-            bm25, n, avg, grow = self.ix.candidate_tuples(None, None, cand)
-        counts = cnt.cpu().numpy()
-        cand_h = cand.cpu().numpy()
+            bm25, n, avg, grow = ix.candidate_tuples(None, None, cand)
         frames = [self.meta.iloc[cand_h[b, :counts[b]]].reset_index(drop=True) for b in range(B)]
 
         rerank = gate = best = None
@@ -433,7 +504,7 @@ class SearchEngine:
                     # queries without any snippet keep an all-zero column, whose min-max is zeros as well (:288-294)
                     best = raw
                     fusion.best_is_raw = True
-        top_rows, final, pos, comp = self.ix.fuse(fusion, dense, bm25, n, avg, grow, count=cnt, rerank=rerank,
+        top_rows, final, pos, comp = ix.fuse(fusion, dense, bm25, n, avg, grow, count=cnt, rerank=rerank,
                                                   best=best, gate=gate, want_components=True)
         pos_h, comp_h = pos.cpu().numpy(), comp.cpu().numpy()
         gate_h = None if gate is None else (gate.cpu().numpy() if hasattr(gate, "cpu") else gate)

@@ -90,9 +90,12 @@ class BM25Stats:
 
 @dataclass
 class HostPostings:
-    data: np.ndarray        # uint64[nnz]   {u32 doc, f32 impact}
+    data: np.ndarray        # uint64[nnz]   {u32 doc, f32 impact}: tile-blocked frequent region, then the rare lists
     tile_base: np.ndarray   # uint64[n_tiles+1]
-    blk_off: np.ndarray     # uint32[n_tiles*(V+1)]
+    dir: np.ndarray         # uint32[n_tiles*(n_freq+1)]
+    term_slot: np.ndarray   # int32[V]   directory slot of a frequent term, -1 = rare
+    rare_off: np.ndarray    # uint64[V+1]
+    n_freq: int
     n_tiles: int
     tile_docs: int
     vocab_size: int
@@ -115,6 +118,7 @@ def build_postings(doc_offsets: np.ndarray, token_ids: np.ndarray, stats: BM25St
     try:
         nnz = int(lib.rr_postings_nnz(h))
         n_tiles = int(lib.rr_postings_n_tiles(h))
+        n_freq = int(lib.rr_postings_n_freq(h))
 
         def view(ptr, count, dtype):
             if count == 0:
@@ -123,12 +127,15 @@ def build_postings(doc_offsets: np.ndarray, token_ids: np.ndarray, stats: BM25St
             return np.frombuffer(buf, dtype=dtype, count=count).copy()
         data = view(lib.rr_postings_data(h), nnz, np.uint64)
         tile_base = view(lib.rr_postings_tile_base(h), n_tiles + 1, np.uint64)
-        blk_off = view(lib.rr_postings_blk_off(h), n_tiles * (stats.vocab_size + 1), np.uint32)
+        dir_ = view(lib.rr_postings_dir(h), n_tiles * (n_freq + 1), np.uint32)
+        term_slot = view(lib.rr_postings_term_slot(h), stats.vocab_size, np.int32)
+        rare_off = view(lib.rr_postings_rare_off(h), stats.vocab_size + 1, np.uint64)
         fwd_off = view(lib.rr_postings_fwd_off(h), n + 1, np.uint64)
         fwd_data = view(lib.rr_postings_fwd_data(h), int(fwd_off[-1]) if n > 0 else 0, np.uint64)
     finally:
         lib.rr_postings_free(h)
-    return HostPostings(data, tile_base, blk_off, n_tiles, tile_docs, stats.vocab_size, fwd_off, fwd_data)
+    return HostPostings(data, tile_base, dir_, term_slot, rare_off, n_freq, n_tiles, tile_docs, stats.vocab_size, fwd_off,
+                        fwd_data)
 
 
 @dataclass
@@ -136,7 +143,10 @@ class DevicePostings:
     """The same index as HostPostings, built on the GPU (GpuIndexBuilder) and already resident in HBM."""
     data: torch.Tensor        # int64[nnz]   {u32 doc, f32 impact}
     tile_base: torch.Tensor   # int64[n_tiles+1]
-    blk_off: torch.Tensor     # int32[n_tiles*(V+1)]
+    dir: torch.Tensor         # int32[n_tiles*(n_freq+1)]
+    term_slot: torch.Tensor   # int32[V]
+    rare_off: torch.Tensor    # int64[V+1]
+    n_freq: int
     n_tiles: int
     tile_docs: int
     vocab_size: int
@@ -165,14 +175,15 @@ class GpuIndexBuilder:
         self.n_docs = int(self.doc_offsets.numel()) - 1
         self.n_tokens = int(self.token_ids.numel())
         self.vocab_size, self.tile_docs = int(vocab_size), int(tile_docs)
-        nu, npost, nt = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+        nu, npost, nt, nf = C.c_int64(0), C.c_int64(0), C.c_int32(0), C.c_int32(0)
         h = C.c_void_p(0)
         with torch.cuda.device(self.device):
             check(self.lib.rr_bm25_gpu_build_begin(C.byref(h), _ptr(self.doc_offsets), _ptr(self.token_ids), self.n_docs,
                                                    self.n_tokens, self.vocab_size, self.tile_docs, C.byref(nu), C.byref(npost),
-                                                   C.byref(nt), self.device.index or 0, _stream()))
+                                                   C.byref(nt), C.byref(nf), self.device.index or 0, _stream()))
         self._h = h
         self.n_unique, self.n_postings, self.n_tiles = int(nu.value), int(npost.value), int(nt.value)
+        self.n_freq = int(nf.value)
 
     def local_stats(self, token_pos0: int = 0) -> BM25Stats:
         df = torch.zeros(self.vocab_size, dtype=torch.int64, device=self.device)
@@ -188,16 +199,19 @@ class GpuIndexBuilder:
         idf = torch.from_numpy(np.ascontiguousarray(stats.idf, dtype=np.float64)).to(dev)
         data = torch.empty(max(self.n_postings, 2), dtype=torch.int64, device=dev)
         tile_base = torch.empty(self.n_tiles + 1, dtype=torch.int64, device=dev)
-        blk_off = torch.empty(self.n_tiles * (self.vocab_size + 1), dtype=torch.int32, device=dev)
+        dir_ = torch.empty(max(self.n_tiles * (self.n_freq + 1), 1), dtype=torch.int32, device=dev)
+        term_slot = torch.empty(self.vocab_size, dtype=torch.int32, device=dev)
+        rare_off = torch.empty(self.vocab_size + 1, dtype=torch.int64, device=dev)
         fwd_off = torch.empty(self.n_docs + 1, dtype=torch.int64, device=dev)
         fwd_data = torch.empty(max(self.n_unique, 1), dtype=torch.int64, device=dev)
         with torch.cuda.device(dev):
             check(self.lib.rr_bm25_gpu_build_finish(self._h, _ptr(idf), float(stats.avgdl), float(k1), float(b), _ptr(data),
-                                                    _ptr(tile_base), _ptr(blk_off), _ptr(fwd_off), _ptr(fwd_data), _stream()))
+                                                    _ptr(tile_base), _ptr(dir_), _ptr(term_slot), _ptr(rare_off), _ptr(fwd_off),
+                                                    _ptr(fwd_data), _stream()))
             torch.cuda.current_stream().synchronize()            # `idf` and the builder scratch may be released now
         self.close()
-        return DevicePostings(data[:max(self.n_postings, 2)], tile_base, blk_off, self.n_tiles, self.tile_docs, self.vocab_size,
-                              fwd_off, fwd_data)
+        return DevicePostings(data[:max(self.n_postings, 2)], tile_base, dir_, term_slot, rare_off, self.n_freq, self.n_tiles,
+                              self.tile_docs, self.vocab_size, fwd_off, fwd_data)
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -257,14 +271,17 @@ class HybridIndex:
                  row_offset: int = 0, stats: Optional[BM25Stats] = None, k1: float = K1_DEFAULT,
                  b: float = B_DEFAULT, epsilon: float = EPSILON_DEFAULT, tile_docs: int = DEFAULT_TILE_DOCS,
                  make_bf16: bool = True, postings: Optional[HostPostings] = None, forward_index: bool = True,
-                 normalize: bool = False):
+                 normalize: bool = False, share: Optional["HybridIndex"] = None):
         """`normalize=True`: `emb` holds the raw rows of product_emb.npy; they are L2-normalised on the device
-        exactly like the reference does at load (rr_normalize_rows), fused with the bf16 copy."""
+        exactly like the reference does at load (rr_normalize_rows), fused with the bf16 copy.
+        `share`: reuse the embedding tensors (fp32 + bf16) of another index over the same rows (`emb` is ignored)."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RRError("HybridIndex needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
+        if share is not None:
+            emb, normalize, make_bf16 = share.emb, False, False
         if isinstance(emb, np.ndarray):
             emb = torch.from_numpy(np.ascontiguousarray(emb, dtype=np.float32))
         self.emb = emb.to(self.device, dtype=torch.float32).contiguous()
@@ -282,7 +299,10 @@ class HybridIndex:
             check(self.lib.rr_normalize_rows(_ptr(self.emb), self.n_docs, self.dim, _ptr(self.emb), _ptr(bf), self.dim_pad,
                                              _ptr(None), self.device.index or 0, _stream()))
             self.emb_bf16 = bf
-        self.max_row_norm = float(torch.linalg.vector_norm(self.emb, dim=1).max().item()) if self.n_docs else 0.0
+        if share is not None:
+            self.emb_bf16, self.dim_pad, self.max_row_norm = share.emb_bf16, share.dim_pad, share.max_row_norm
+        else:
+            self.max_row_norm = float(torch.linalg.vector_norm(self.emb, dim=1).max().item()) if self.n_docs else 0.0
         if make_bf16 and self.emb_bf16 is None:
             self.dim_pad = (self.dim + 63) // 64 * 64
             bf = torch.empty((self.n_docs, self.dim_pad), dtype=torch.bfloat16, device=self.device)
@@ -295,8 +315,8 @@ class HybridIndex:
         self.vocab_size = 0
         self.stats = stats
         self.k1, self.b = k1, b
-        self.post = self.tile_base = self.blk_off = self.fwd_off = self.fwd_data = None
-        self.tile_docs, self.n_tiles = 0, 0
+        self.post = self.tile_base = self.dir = self.term_slot = self.rare_off = self.fwd_off = self.fwd_data = None
+        self.tile_docs, self.n_tiles, self.n_freq = 0, 0, 0
         if postings is None and isinstance(doc_offsets, torch.Tensor) and doc_offsets.is_cuda and vocab_size > 0:
             # corpus already in device memory: build the index on the GPU
             gb = GpuIndexBuilder(doc_offsets, token_ids, vocab_size, tile_docs)
@@ -311,16 +331,20 @@ class HybridIndex:
             postings = build_postings(doc_offsets, token_ids, stats, k1, b, tile_docs)
         if isinstance(postings, DevicePostings):
             self.vocab_size = postings.vocab_size
-            self.tile_docs, self.n_tiles = postings.tile_docs, postings.n_tiles
-            self.post, self.tile_base, self.blk_off = postings.data, postings.tile_base, postings.blk_off
+            self.tile_docs, self.n_tiles, self.n_freq = postings.tile_docs, postings.n_tiles, postings.n_freq
+            self.post, self.tile_base, self.dir = postings.data, postings.tile_base, postings.dir
+            self.term_slot, self.rare_off = postings.term_slot, postings.rare_off
             if forward_index:
                 self.fwd_off, self.fwd_data = postings.fwd_off, postings.fwd_data
         elif postings is not None:
             self.vocab_size = postings.vocab_size
-            self.tile_docs, self.n_tiles = postings.tile_docs, postings.n_tiles
+            self.tile_docs, self.n_tiles, self.n_freq = postings.tile_docs, postings.n_tiles, postings.n_freq
             self.post = torch.from_numpy(postings.data.view(np.int64)).to(self.device)
             self.tile_base = torch.from_numpy(postings.tile_base.view(np.int64)).to(self.device)
-            self.blk_off = torch.from_numpy(postings.blk_off.view(np.int32)).to(self.device)
+            d_ = postings.dir if postings.dir.size else np.zeros(1, dtype=np.uint32)
+            self.dir = torch.from_numpy(d_.view(np.int32)).to(self.device)
+            self.term_slot = torch.from_numpy(postings.term_slot).to(self.device)
+            self.rare_off = torch.from_numpy(postings.rare_off.view(np.int64)).to(self.device)
             if self.post.numel() == 0:
                 self.post = torch.zeros(2, dtype=torch.int64, device=self.device)
             if forward_index and postings.fwd_off is not None:
@@ -340,10 +364,12 @@ class HybridIndex:
 
         desc = IndexDesc(self.n_docs, self.row_offset, self.dim, self.dim_pad,
                          self.emb.data_ptr(), self.emb_bf16.data_ptr() if self.emb_bf16 is not None else None,
-                         self.max_row_norm, self.vocab_size, self.tile_docs, self.n_tiles,
+                         self.max_row_norm, self.vocab_size, self.tile_docs, self.n_tiles, self.n_freq,
                          self.post.data_ptr() if self.post is not None else None,
                          self.tile_base.data_ptr() if self.tile_base is not None else None,
-                         self.blk_off.data_ptr() if self.blk_off is not None else None,
+                         self.dir.data_ptr() if self.dir is not None else None,
+                         self.term_slot.data_ptr() if self.term_slot is not None else None,
+                         self.rare_off.data_ptr() if self.rare_off is not None else None,
                          self.fwd_off.data_ptr() if self.fwd_off is not None else None,
                          self.fwd_data.data_ptr() if self.fwd_data is not None else None,
                          self.n_reviews.data_ptr() if self.n_reviews is not None else None,
@@ -352,6 +378,14 @@ class HybridIndex:
         h = C.c_void_p(0)
         check(self.lib.rr_index_create(C.byref(h), C.byref(desc), self.device.index or 0))
         self._h = h
+
+    def index_bytes(self) -> Dict[str, int]:
+        """Bytes of the BM25 index in HBM: postings (both regions), metadata that locates them (tile bases, tile
+        directory of the frequent terms, term slots, rare-list offsets) and the forward index."""
+        def nb(t):
+            return 0 if t is None else int(t.numel()) * t.element_size()
+        return {"postings": nb(self.post), "directory": nb(self.tile_base) + nb(self.dir) + nb(self.term_slot) + nb(self.rare_off),
+                "forward": nb(self.fwd_off) + nb(self.fwd_data), "n_freq": int(self.n_freq), "n_tiles": int(self.n_tiles)}
 
     def view(self) -> "HybridIndex":
         """A second handle over the SAME device buffers with its own scratch memory, so that two batches can be in
@@ -429,6 +463,16 @@ class HybridIndex:
         check(self.lib.rr_dense_topk(self._h, _ptr(q), B, pool, mode, _ptr(idx), _ptr(sims), _ptr(cnt), _stream()))
         return idx, sims, cnt
 
+    def debug_bf16_scores(self, q, row0: int, n_rows: int) -> torch.Tensor:
+        """float32[B, n_rows]: the raw tensor-core (bf16 x bf16 -> fp32) scores of rows row0 .. row0+n_rows, B <= 128."""
+        q = self._dev(q, torch.float32)
+        if q.dim() == 1:
+            q = q[None, :]
+        out = torch.full((int(q.shape[0]), int(n_rows)), float("nan"), dtype=torch.float32, device=self.device)
+        check(self.lib.rr_dense_debug_bf16_scores(self._h, _ptr(q), int(q.shape[0]), int(row0), int(n_rows), _ptr(out),
+                                                  _stream()))
+        return out
+
     def dense_stats(self) -> dict:
         st = _lib.DenseStats()
         check(self.lib.rr_dense_last_stats(self._h, C.byref(st)))
@@ -466,6 +510,10 @@ class HybridIndex:
             return None if x is None else self._dev(x, dt)
         rerank, best, gate = opt(rerank, torch.float32), opt(best, torch.float32), opt(gate, torch.float32)
         count = opt(count, torch.int32)
+        # tuple fields are device pointers for the kernel: anything else (NumPy, CPU tensor, strided view, wrong dtype)
+        # is converted here rather than handed over as a raw pointer
+        dense, bm25 = self._dev(dense, torch.float32), self._dev(bm25, torch.float32)
+        n, avg, grow = self._dev(n, torch.float64), self._dev(avg, torch.float64), self._dev(grow, torch.int64)
         check(self.lib.rr_fuse_topk(C.byref(p), B, n_in, _ptr(count), _ptr(dense), _ptr(bm25), _ptr(n), _ptr(avg),
                                     _ptr(grow), _ptr(rerank), _ptr(best), _ptr(gate), _ptr(rows), _ptr(final),
                                     _ptr(pos), _ptr(comp), self.device.index or 0, _stream()))
@@ -494,6 +542,11 @@ class HybridIndex:
         """K4 over tuples received from `n_shards` row shards (cross-shard merge + fusion).  The field
         tensors are views into one exchange buffer; shard s's [B, per_shard] block of a field starts
         s*shard_stride_bytes after the field's base."""
+        for name, t, dt in (("dense", dense, torch.float32), ("bm25", bm25, torch.float32), ("n", n, torch.float64),
+                            ("avg", avg, torch.float64), ("grow", grow, torch.int64)):
+            # views into the exchange buffer: must already be device memory of this index (no silent host pointers)
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.device == self.device and t.is_contiguous()):
+                raise RRError(f"fuse_sharded: `{name}` must be a contiguous CUDA tensor on {self.device}")
         p = fusion.to_c()
         if out is not None:
             rows, final, flags = out
@@ -543,7 +596,8 @@ class HybridIndex:
         n_unc = unc.sum()                                        # enqueued on the same stream, read in result()
         done = torch.cuda.Event()
         done.record()
-        return PendingSearch(self, q, term_ids, n_terms, fusion, mode, rows, final, unc, n_unc, done)
+        return PendingSearch(self, q, term_ids, n_terms, fusion, mode, rows, final, unc, n_unc, done,
+                             torch.cuda.current_stream())
 
     def hybrid_search_host(self, q: np.ndarray, term_ids: Optional[np.ndarray], n_terms: Optional[np.ndarray],
                            fusion: Fusion, mode: int = _lib.RR_DENSE_AUTO, out_rows: Optional[np.ndarray] = None,
@@ -568,9 +622,10 @@ class HybridIndex:
 class PendingSearch:
     """A hybrid search in flight (HybridIndex.hybrid_search_begin)."""
 
-    def __init__(self, ix, q, term_ids, n_terms, fusion, mode, rows, final, unc, n_unc, done):
+    def __init__(self, ix, q, term_ids, n_terms, fusion, mode, rows, final, unc, n_unc, done, stream):
         self.ix, self.q, self.term_ids, self.n_terms, self.fusion, self.mode = ix, q, term_ids, n_terms, fusion, mode
         self.rows, self.final, self.unc, self.n_unc, self.done = rows, final, unc, n_unc, done
+        self.stream = stream            # the stream the search was enqueued on: its outputs live (allocator-wise) there
         self.repeated = 0
 
     def result(self) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -581,13 +636,20 @@ class PendingSearch:
             nf = int(self.n_unc.item())
             self.repeated = nf
             if nf > 0:
-                idx = torch.nonzero(self.unc, as_tuple=False).view(-1)
-                r2, f2 = self.ix.hybrid_search(self.q[idx].contiguous(),
-                                               None if self.term_ids is None else self.term_ids[idx].contiguous(),
-                                               None if self.n_terms is None else self.n_terms[idx].contiguous(),
-                                               self.fusion, self.mode)
-                self.rows[idx] = r2
-                self.final[idx] = f2
+                # the repeat and the scatter run on the stream the token was created on, whatever is current now
+                with torch.cuda.stream(self.stream):
+                    idx = torch.nonzero(self.unc, as_tuple=False).view(-1)
+                    r2, f2 = self.ix.hybrid_search(self.q[idx].contiguous(),
+                                                   None if self.term_ids is None else self.term_ids[idx].contiguous(),
+                                                   None if self.n_terms is None else self.n_terms[idx].contiguous(),
+                                                   self.fusion, self.mode)
+                    self.rows[idx] = r2
+                    self.final[idx] = f2
+                self.stream.synchronize()
+            cur = torch.cuda.current_stream()
+            if cur != self.stream:          # the caller reads the outputs on its own stream
+                self.rows.record_stream(cur)
+                self.final.record_stream(cur)
         return self.rows, self.final
 
 

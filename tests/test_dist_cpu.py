@@ -124,6 +124,13 @@ GRID_WORKER = textwrap.dedent('''
         want_rows = torch.arange(B)[:, None] * 10 + torch.arange(3)[None, :]
         assert torch.equal(rows, want_rows), rows
         assert torch.allclose(final, torch.arange(B)[:, None].float() + torch.arange(3)[None, :].float() / 100)
+        # odd (B/Q)*k: the gathered byte rows must stay 8-byte aligned (ADVICE r01: stride not divisible by 8)
+        class F5:
+            k, pool = 5, 5
+        q2 = torch.arange(2, dtype=torch.float32)[:, None].repeat(1, 4)
+        rows, final = grid.search(q2, None, None, F5())
+        assert torch.equal(rows, torch.arange(2)[:, None] * 10 + torch.arange(5)[None, :]), rows
+        assert torch.allclose(final, torch.arange(2)[:, None].float() + torch.arange(5)[None, :].float() / 100)
     dist.barrier()
     dist.destroy_process_group()
     print(f"rank {rank} grid ok", flush=True)

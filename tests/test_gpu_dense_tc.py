@@ -69,3 +69,26 @@ def test_near_duplicates_fall_back_to_exact_and_stay_exact():
     np.testing.assert_array_equal(i1, i2)
     np.testing.assert_array_equal(s1, s2)
     ix.close()
+
+
+def test_bf16_scores_within_1e3_of_exact_before_rescoring():
+    """north_star: "dense cosine scores must match within 1e-3 absolute before rescoring".  The raw tensor-core scores
+    (rr_dense_debug_bf16_scores: tcgen05 bf16 x bf16 -> fp32, what the threshold filter sees) against the exact fp32
+    similarities on configs[1]-shaped data (384-d unit rows, recipe of SURVEY 8d)."""
+    import torch
+    import review_recommender_b200 as rr
+    n, d, b = 200_000, 384, 96
+    emb = rr.synth.embeddings(n, d)
+    q = rr.synth.queries(b, d)
+    ix = rr.engine.HybridIndex(emb, device="cuda:0")
+    worst = 0.0
+    for row0, rows in ((0, 148 * 256), (150_016, 30_000), (n - 256 - (n - 256) % 256, 256 + (n - 256) % 256)):
+        got = ix.debug_bf16_scores(q, row0, rows).cpu().numpy()
+        assert not np.isnan(got).any(), "every row of the range must have been scored"
+        want = (emb[row0:row0 + rows] @ q.T).T
+        worst = max(worst, float(np.max(np.abs(got - want))))
+    assert worst <= 1e-3, worst
+    # and the certification margin the library actually uses is a proven bound, looser than the stated tolerance
+    _, _, _ = ix.dense_topk(q, 150, rr._lib.RR_DENSE_TENSOR)
+    assert ix.dense_stats()["eps"] >= worst
+    ix.close()

@@ -1,5 +1,5 @@
 """BM25 index construction on the GPU (rr_bm25_gpu_build_*) against the host C++ builder: statistics, forward index,
-tile-blocked postings, tile bases and block offsets must be IDENTICAL (bit for bit), including out-of-vocabulary
+postings of both regions, tile bases, term classes, tile directory and rare-list offsets must be IDENTICAL (bit for bit), including out-of-vocabulary
 token ids, empty documents, odd posting counts per tile (alignment padding) and trailing empty tiles."""
 import numpy as np
 import pytest
@@ -51,7 +51,10 @@ def test_gpu_builder_equals_host_builder(case):
     dp = gb.finish(dev_stats)
     assert dp.n_tiles == hp.n_tiles
     np.testing.assert_array_equal(dp.tile_base.cpu().numpy().view(np.uint64), hp.tile_base)
-    np.testing.assert_array_equal(dp.blk_off.cpu().numpy().view(np.uint32), hp.blk_off)
+    assert dp.n_freq == hp.n_freq
+    np.testing.assert_array_equal(dp.term_slot.cpu().numpy(), hp.term_slot)
+    np.testing.assert_array_equal(dp.rare_off.cpu().numpy().view(np.uint64), hp.rare_off)
+    np.testing.assert_array_equal(dp.dir.cpu().numpy().view(np.uint32)[:hp.dir.size], hp.dir)
     np.testing.assert_array_equal(dp.fwd_off.cpu().numpy().view(np.uint64), hp.fwd_off)
     n_f = int(hp.fwd_off[-1])
     np.testing.assert_array_equal(dp.fwd_data.cpu().numpy().view(np.uint64)[:n_f], hp.fwd_data)

@@ -28,10 +28,10 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(rr._lib.SIGNATURES), declared ^ set(rr._lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.rr_abi_version() == 2
+    assert lib.rr_abi_version() == 3
 
 
-@pytest.mark.parametrize("n,v,tile", [(37, 50, 16), (3000, 400, 256), (5000, 2000, 16384)])
+@pytest.mark.parametrize("n,v,tile", [(37, 50, 16), (3000, 400, 256), (5000, 2000, 16384), (9000, 5000, 64)])
 def test_builder_matches_oracle(lib, n, v, tile):
     offs, toks = rr.synth.corpus_tokens(n, v)
     csr = BM25OkapiCSR(offs, toks, v)
@@ -44,23 +44,45 @@ def test_builder_matches_oracle(lib, n, v, tile):
     assert hp.n_tiles == (n + tile - 1) // tile
     docs = (hp.data & np.uint64(0xFFFFFFFF)).astype(np.int64)
     imp = (hp.data >> np.uint64(32)).astype(np.uint32).view(np.float32)
-    stride = v + 1
+    # term classes: frequent <=> local df >= RR_DIR_MIN_PER_TILE * n_tiles; slots are term-ascending
+    theta = lib.rr_bm25_dir_threshold(hp.n_tiles)
+    assert theta == 8 * hp.n_tiles
+    freq = np.nonzero(csr.df >= theta)[0]
+    assert hp.n_freq == len(freq)
+    np.testing.assert_array_equal(hp.term_slot[freq], np.arange(len(freq)))
+    assert np.all(hp.term_slot[csr.df < theta] == -1)
+    stride = hp.n_freq + 1
     seen = 0
     for t in range(hp.n_tiles):
         base = int(hp.tile_base[t])
         assert base % 2 == 0
-        off = hp.blk_off[t * stride:(t + 1) * stride].astype(np.int64)
+        off = hp.dir[t * stride:(t + 1) * stride].astype(np.int64)
         assert off[0] == 0 and np.all(np.diff(off) >= 0)
-        for term in np.nonzero(np.diff(off))[0]:
-            lo, hi = base + off[term], base + off[term + 1]
+        for slot in np.nonzero(np.diff(off))[0]:
+            term = int(freq[slot])
+            lo, hi = base + off[slot], base + off[slot + 1]
             d = docs[lo:hi]
             assert np.all(np.diff(d) > 0) and d[0] >= t * tile and d[-1] < min(n, (t + 1) * tile)
-            odocs, ocontrib = csr.impacts(int(term))
+            odocs, ocontrib = csr.impacts(term)
             sel = (odocs >= t * tile) & (odocs < (t + 1) * tile)
             np.testing.assert_array_equal(d, odocs[sel])
             np.testing.assert_array_equal(imp[lo:hi], ocontrib[sel].astype(np.float32))
             seen += hi - lo
+    # rare terms: one term-major, doc-ascending list each, behind the frequent region
+    rare_base = int(hp.tile_base[hp.n_tiles])
+    assert rare_base % 2 == 0 and hp.rare_off[0] == 0
+    for term in np.nonzero(csr.df < theta)[0]:
+        lo, hi = rare_base + int(hp.rare_off[term]), rare_base + int(hp.rare_off[term + 1])
+        assert hi - lo == csr.df[term]
+        if hi > lo:
+            odocs, ocontrib = csr.impacts(int(term))
+            np.testing.assert_array_equal(docs[lo:hi], odocs)
+            np.testing.assert_array_equal(imp[lo:hi], ocontrib.astype(np.float32))
+            seen += hi - lo
+    for term in freq:
+        assert hp.rare_off[term] == hp.rare_off[term + 1]
     assert seen == csr.post_doc.shape[0]
+    assert hp.data.size == rare_base + (int(hp.rare_off[-1]) + 1) // 2 * 2
 
 
 def test_sharded_stats_reduce_to_global(lib):

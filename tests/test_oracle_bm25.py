@@ -54,3 +54,25 @@ def test_csr_twin_is_bit_identical(seed, n, v):
     for _ in range(10):
         q = [int(x) for x in rng.integers(0, len(vocab), size=int(rng.integers(1, 8)))]
         np.testing.assert_array_equal(csr.get_scores(q), bm.get_scores([vocab[i] for i in q]))
+
+
+def test_pin_against_the_real_rank_bm25_when_installed(fx):
+    """Flips oracle.bm25_okapi from "parity unpinned" to pinned wherever the real package exists (it is absent from
+    the reference tree, its requirements.txt and this image): bit-for-bit on the reference's fixture corpus, the
+    negative-idf corpus and random Zipf corpora -- construction statistics and get_scores."""
+    rank_bm25 = pytest.importorskip("rank_bm25")
+    from pathlib import Path
+    if Path(rank_bm25.__file__).resolve().is_relative_to(Path(__file__).resolve().parent.parent):
+        pytest.skip("`rank_bm25` resolves to this repo's drop-in shim, not the third-party package")
+    rng = np.random.default_rng(123)
+    corpora = [fx["fixture_corpus"], fx["neg_corpus"]]
+    for n, v in ((60, 15), (800, 120)):
+        corpora.append([[f"w{int(t)}" for t in rng.zipf(1.3, size=int(rng.integers(1, 40))) % v] for _ in range(n)])
+    for corpus in corpora:
+        real, mine = rank_bm25.BM25Okapi(corpus), BM25Okapi(corpus)
+        assert real.avgdl == mine.avgdl and real.average_idf == mine.average_idf and real.corpus_size == mine.corpus_size
+        assert list(real.idf.items()) == list(mine.idf.items())                  # values AND dict order
+        vocab = list(mine.idf)
+        for _ in range(20):
+            q = [vocab[int(i)] for i in rng.integers(0, len(vocab), size=int(rng.integers(1, 9)))] + ["<unknown>"]
+            np.testing.assert_array_equal(real.get_scores(q), mine.get_scores(q))

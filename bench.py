@@ -66,9 +66,10 @@ def parse_args():
     ap.add_argument("--cpu-workers", type=int, default=0, help="worker processes of the CPU arm (0 = all host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sparse-queries", type=int, default=32, help="queries of the BM25 get_scores sweep")
-    ap.add_argument("--in-flight", type=int, default=1,
-                    help="batches in flight in the device-resident loop (2 = consecutive steps alternate between two "
-                         "handles / CUDA streams over the same index, so one step's tail overlaps the next step's GEMM)")
+    ap.add_argument("--in-flight", type=int, default=0,
+                    help="batches in flight (2 = consecutive steps alternate between two handles / CUDA streams over the "
+                         "same index, so one step's latency-bound tail -- selection, exchange, host wait -- runs under the next "
+                         "step's GEMM).  0 = auto: 1 on a single GPU (power-capped GEMM: measured +0.6 %), 2 on several")
     ap.add_argument("--synth", default="recipe", choices=["recipe", "device"],
                     help="recipe = the SURVEY 8d NumPy recipe, generated per 1 M-row chunk on the host (default; the only "
                          "mode with id_parity); device = same distributions drawn with torch generators in HBM (fast set-up "
@@ -440,7 +441,9 @@ def main():
     Q = args.query_groups
     if Q < 1 or world % Q:
         raise SystemExit("--query-groups must divide the number of GPUs")
-    searcher = rr.dist.GridSearcher(None, Q) if world > 1 else None      # creates the process sub-groups (collective)
+    if args.in_flight <= 0:
+        args.in_flight = 2 if (world > 1 and Q == 1) else 1
+    searcher = rr.dist.GridSearcher(None, Q, lanes=args.in_flight if Q == 1 else 1) if world > 1 else None   # creates the process sub-groups (collective)
     qg, shard, R = rr.dist.GridSearcher.layout(rank, world, Q)
     row0 = N * shard // R
     n_local = N * (shard + 1) // R - row0
@@ -514,7 +517,15 @@ def main():
     pending = collections.deque()
     last = [None]
 
+    pipelined = searcher is not None and Q == 1 and args.in_flight > 1
+
     def step_device():
+        if pipelined:
+            # row-sharded, batches in flight: enqueue this step, then complete the oldest one still pending
+            pending.append(searcher.begin(q_dev, qt_dev, nt_dev, fusion, mode=args.dense_mode))
+            if len(pending) >= args.in_flight:
+                last[0] = pending.popleft().result()
+            return last[0]
         if searcher is not None:
             last[0] = searcher.search(q_dev, qt_dev, nt_dev, fusion, mode=args.dense_mode)
             return last[0]
@@ -627,6 +638,23 @@ def main():
     bqt = batch_dev[nb_q:nb_q + nb_t].view(torch.int32).view(B, L)
     bnt = batch_dev[nb_q + nb_t:].view(torch.int32)
 
+    # multi-GPU ingest is double-buffered: batch i+1 is copied to rank 0's HBM and broadcast (on the default stream)
+    # while batch i is still being searched on its lane; results of batch i-1 are read back meanwhile
+    ingest = [(batch_dev, bq, bqt, bnt)]
+    for _ in range(args.in_flight - 1 if pipelined else 0):
+        bd = torch.empty_like(batch_pin, device=dev)
+        ingest.append((bd, bd[:nb_q].view(torch.float32).view(B, D), bd[nb_q:nb_q + nb_t].view(torch.int32).view(B, L),
+                       bd[nb_q + nb_t:].view(torch.int32)))
+    e2e_pending = collections.deque()
+    e2e_no = [0]
+
+    def finish_e2e(tok):
+        r, f = tok.result()
+        if rank == 0:
+            rows_pin.copy_(r, non_blocking=True)
+            final_pin.copy_(f, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
     def step_e2e():
         if searcher is None:
             ix.hybrid_search_host(q_pin.numpy(), qt_pin.numpy(), nt_pin.numpy(), fusion, mode=args.dense_mode,
@@ -634,21 +662,34 @@ def main():
             return
         # the query batch (vectors | term ids | term counts, one packed buffer) enters on rank 0 and is broadcast
         # ONCE; results are read back on rank 0
+        bd, xq, xqt, xnt = ingest[e2e_no[0] % len(ingest)]
+        e2e_no[0] += 1
         if rank == 0:
-            batch_dev.copy_(batch_pin, non_blocking=True)
-        dist.broadcast(batch_dev, 0)
-        r, f = searcher.search(bq, bqt, bnt, fusion, mode=args.dense_mode)
+            bd.copy_(batch_pin, non_blocking=True)
+        dist.broadcast(bd, 0)
+        if pipelined:
+            e2e_pending.append(searcher.begin(xq, xqt, xnt, fusion, mode=args.dense_mode))
+            if len(e2e_pending) >= args.in_flight:
+                finish_e2e(e2e_pending.popleft())
+            return
+        r, f = searcher.search(xq, xqt, xnt, fusion, mode=args.dense_mode)
         if rank == 0:
             rows_pin.copy_(r, non_blocking=True)
             final_pin.copy_(f, non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
+    def drain_e2e():
+        while e2e_pending:
+            finish_e2e(e2e_pending.popleft())
+
     for _ in range(min(2, args.warmup)):
         step_e2e()
+    drain_e2e()
     sync_all()
     e0.record()
     for _ in range(args.steps):
         step_e2e()
+    drain_e2e()
     e1.record()
     sync_all()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
@@ -738,7 +779,7 @@ def main():
         "config": {"workload": cfg["workload"], "docs": N, "docs_per_gpu": n_local, "dim": D, "vocab": V, "batch": B,
                    "query_terms": L, "k": K, "pool": fusion.pool, "weights": wts, "parallelism": f"row-sharded x{R}" + (f", query groups x{Q}" if Q > 1 else ""),
                    "l2": "inputs larger than L2 (bf16 corpus shard read every step)",
-                   "dense_path": dstats, "setup_s": setup_s, "index_build_s": build_s, "batches_in_flight": len(lanes)},
+                   "dense_path": dstats, "setup_s": setup_s, "index_build_s": build_s, "batches_in_flight": args.in_flight if searcher is not None else len(lanes)},
         "roofline": roofline, "kernels": kernels, "profiled_ms_per_step": profiled_ms_per_step, "sparse": sparse,
         "cpu_baseline": cpu_base,
         "clocks": {"sm_mhz": clock_info.get("sm_mhz"), "sm_max_mhz": clock_info.get("sm_max_mhz"),

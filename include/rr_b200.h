@@ -177,6 +177,10 @@ int rr_bm25_candidates(rr_index*, const int32_t* d_term_ids, const int32_t* d_n_
 #define RR_DENSE_TENSOR 2
 int rr_dense_topk(rr_index*, const float* d_q, int32_t B, int32_t pool, int32_t mode,
                   int64_t* d_idx, float* d_sims, int32_t* d_count, rr_stream);
+/* Same without any host synchronisation: queries whose pool the tensor path could not prove exact are NOT redone;
+ * d_uncertified int32[B] says which (1 = best-effort, repeat through rr_dense_topk; 0 = final). */
+int rr_dense_topk_deferred(rr_index*, const float* d_q, int32_t B, int32_t pool, int32_t mode,
+                           int64_t* d_idx, float* d_sims, int32_t* d_count, int32_t* d_uncertified, rr_stream);
 
 /* Test / debug entry of the shortlist stage: the raw bf16 x bf16 -> fp32 tensor-core scores (tcgen05.mma, exactly what
  * the threshold filter compares) of rows [row0, row0+n_rows) for B <= 128 queries, d_out float[B, n_rows].  row0 must be
@@ -230,11 +234,15 @@ int rr_fuse_topk(const rr_fusion_params*, int32_t B, int32_t n_in, const int32_t
  * (optional) is then set to 1 when some shard sent all m of its tuples and its weakest one still
  * reaches the merged pool's cut-off, i.e. that shard may hold further pool members and the query has
  * to be repeated with per_shard = pool; 0 means the merged pool is provably the exact global pool.
- * A shard block whose first global row is -2 (rr_shard_tuples: dense result not certified) also sets it. */
+ * A shard block whose first global row is -2 (rr_shard_tuples: dense result not certified) also sets it.
+ * d_gate / d_best (optional, NULL = 1.0 / 0.0): the per-candidate gate factor and best-review similarity
+ * (raw when best_is_raw) as two more float fields of the tuples, laid out like d_dense -- run_search's `_gate`
+ * and `_best` columns (app/app_product_search.py:285-310) in a row-sharded search. */
 int rr_fuse_topk_sharded(const rr_fusion_params*, int32_t B, int32_t n_shards, int32_t per_shard,
                          int64_t shard_stride_bytes,
                          const float* d_dense, const float* d_bm25, const double* d_n_reviews,
                          const double* d_avg_stars, const int64_t* d_global_row,
+                         const float* d_gate, const float* d_best,
                          int64_t* d_top_row, float* d_top_final, int32_t* d_incomplete, int device, rr_stream);
 
 /* Row-shard half of a distributed search with NO host synchronisation: the shard's exact top-m by dense

@@ -78,7 +78,8 @@ SIGNATURES = {
     "rr_fuse_topk": (C.c_int, [C.POINTER(FusionParams), C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                _P, _P, _P, _P, C.c_int, _P]),
     "rr_fuse_topk_sharded": (C.c_int, [C.POINTER(FusionParams), C.c_int32, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P,
-                                       _P, _P, _P, _P, _P, C.c_int, _P]),
+                                       _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "rr_dense_topk_deferred": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "rr_struct_sizes": (None, [_P]),
     "rr_profile_enable": (C.c_int, [C.c_int]),
     "rr_profile_collect": (C.c_int, [_P, _P, C.c_int32]),

@@ -97,11 +97,14 @@ extern "C" int rr_profile_collect(double* h_ms, int64_t* h_launches, int32_t n_c
 // ---------------------------------------------------------------------------------------------
 // handle
 // ---------------------------------------------------------------------------------------------
+static std::atomic<uint64_t> g_buf_generation{1};     // bumped whenever any scratch buffer moves (captured graphs hold pointers)
+
 struct DeviceBuf {
     void* p = nullptr;
     size_t cap = 0;
     int ensure(size_t bytes) {
         if (bytes <= cap) return RR_OK;
+        g_buf_generation.fetch_add(1);
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
         const size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
         cudaError_t e = cudaMalloc(&p, want);
@@ -130,6 +133,10 @@ struct rr_index {
     cudaEvent_t fence = nullptr;
     cudaStream_t fence_stream = nullptr;
     bool fence_armed = false;
+    // small-batch host searches replay a captured CUDA graph (one launch instead of ~20 latency-bound ones)
+    struct GraphEntry { uint64_t key; uint64_t generation; int seen; cudaGraphExec_t exec; };
+    std::vector<GraphEntry> graphs;
+    cudaStream_t capture_stream = nullptr;
 };
 
 namespace {
@@ -198,6 +205,8 @@ extern "C" void rr_index_destroy(rr_index* ix) {
     ix->staging.release();
     ix->rtab.release();
     rr_tc_destroy(ix->tc);
+    for (auto& g : ix->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (ix->capture_stream) cudaStreamDestroy(ix->capture_stream);
     if (ix->fence) cudaEventDestroy(ix->fence);
     delete ix;
 }
@@ -336,6 +345,19 @@ extern "C" int rr_dense_topk(rr_index* ix, const float* d_q, int32_t B, int32_t 
     return dense_topk_locked(ix, d_q, B, pool, mode, d_idx, d_sims, d_count, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int rr_dense_topk_deferred(rr_index* ix, const float* d_q, int32_t B, int32_t pool, int32_t mode,
+                                      int64_t* d_idx, float* d_sims, int32_t* d_count, int32_t* d_uncertified,
+                                      rr_stream stream) {
+    if (!ix || !d_q || !d_idx || !d_sims || !d_uncertified || B < 0 || pool <= 0)
+        return rr_fail(RR_EINVAL, "rr_dense_topk_deferred: bad argument");
+    if (pool > 8192) return rr_fail(RR_EINVAL, "rr_dense_topk_deferred: pool larger than 8192 is not supported");
+    if (B == 0) return RR_OK;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    RR_CUDA(cudaSetDevice(ix->device));
+    ScratchFence fence(ix, static_cast<cudaStream_t>(stream));
+    return dense_topk_locked(ix, d_q, B, pool, mode, d_idx, d_sims, d_count, static_cast<cudaStream_t>(stream), d_uncertified);
+}
+
 extern "C" int rr_dense_debug_bf16_scores(rr_index* ix, const float* d_q, int32_t B, int64_t row0, int32_t n_rows,
                                           float* d_out, rr_stream stream) {
     if (!ix || !d_q || !d_out) return rr_fail(RR_EINVAL, "rr_dense_debug_bf16_scores: null argument");
@@ -365,14 +387,15 @@ extern "C" int rr_fuse_topk(const rr_fusion_params* p, int32_t B, int32_t n_in, 
 extern "C" int rr_fuse_topk_sharded(const rr_fusion_params* p, int32_t B, int32_t n_shards, int32_t per_shard,
                                     int64_t shard_stride_bytes, const float* d_dense, const float* d_bm25,
                                     const double* d_n_reviews, const double* d_avg_stars, const int64_t* d_global_row,
+                                    const float* d_gate, const float* d_best,
                                     int64_t* d_top_row, float* d_top_final, int32_t* d_incomplete, int device,
                                     rr_stream stream) {
     if (n_shards <= 0 || per_shard <= 0 || (shard_stride_bytes & 7))
         return rr_fail(RR_EINVAL, "rr_fuse_topk_sharded: bad shard geometry");
     RR_CUDA(cudaSetDevice(device));
     return rr_launch_fuse(p, B, n_shards * per_shard, n_shards, shard_stride_bytes, nullptr, d_dense, d_bm25,
-                          d_n_reviews, d_avg_stars, d_global_row, nullptr, nullptr, nullptr, d_top_row, d_top_final,
-                          nullptr, nullptr, d_incomplete, static_cast<cudaStream_t>(stream));
+                          d_n_reviews, d_avg_stars, d_global_row, nullptr, d_best, d_gate, d_top_row, d_top_final,
+                          nullptr, nullptr, d_incomplete, static_cast<cudaStream_t>(stream), 1);
 }
 
 extern "C" int rr_shard_tuples(rr_index* ix, const float* d_q, const int32_t* d_term_ids, const int32_t* d_n_terms,
@@ -556,8 +579,69 @@ extern "C" int rr_hybrid_search_host(rr_index* ix, const float* h_q, const int32
         RR_CUDA(cudaMemcpyAsync(d_t, h_term_ids, t_bytes, cudaMemcpyHostToDevice, s));
         RR_CUDA(cudaMemcpyAsync(d_n, h_n_terms, n_bytes, cudaMemcpyHostToDevice, s));
     }
-    RR_TRY(hybrid_locked(ix, d_q, have_terms ? d_t : nullptr, have_terms ? d_n : nullptr, B, l_max, fp, dense_mode,
-                         d_r, d_f, s));
+    // Small batches on the exact path (the single-query shape Streamlit issues, app/app_product_search.py:245-261)
+    // are launch-latency bound: ~20 dependent launches of a few microseconds each.  The second call with the same
+    // shape captures the device work into a CUDA graph (on a private stream: the caller's may be the legacy default
+    // stream, which cannot be captured); later calls replay it with one launch.  Buffers the graph points into are
+    // the handle's staging / scratch buffers; any reallocation invalidates the graphs (generation counter).
+    bool done = false;
+    const bool exact = dense_mode == RR_DENSE_EXACT ||
+                       (dense_mode == RR_DENSE_AUTO && !(rr_tc_supported(ix->cc_major, ix->cc_minor) && ix->d.d_emb_bf16 != nullptr &&
+                                                         rr_tc_can_handle(ix->d.dim_pad, fp->pool) && B >= 32 && ix->d.n_docs >= 65536));
+    if (B <= 8 && exact && !g_prof_on.load(std::memory_order_relaxed) && !getenv("RR_NO_GRAPHS")) {
+        uint64_t key = 1469598103934665603ull;
+        auto mix = [&key](const void* p, size_t n) {
+            const unsigned char* c = static_cast<const unsigned char*>(p);
+            for (size_t i = 0; i < n; ++i) { key ^= c[i]; key *= 1099511628211ull; }
+        };
+        const int32_t shape[4] = {B, l_max, have_terms ? 1 : 0, dense_mode};
+        mix(shape, sizeof(shape));
+        mix(fp, sizeof(*fp));
+        rr_index::GraphEntry* ent = nullptr;
+        for (auto& g : ix->graphs) if (g.key == key) { ent = &g; break; }
+        if (!ent) {
+            if (ix->graphs.size() >= 16) {
+                for (auto& g : ix->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+                ix->graphs.clear();
+            }
+            ix->graphs.push_back({key, 0, 0, nullptr});
+            ent = &ix->graphs.back();
+        }
+        const uint64_t gen = g_buf_generation.load();
+        if (ent->exec && ent->generation != gen) { cudaGraphExecDestroy(ent->exec); ent->exec = nullptr; ent->seen = 1; }
+        if (!ent->exec && ent->seen == 1) {
+            // warm (buffers allocated, attributes set by the previous call): capture
+            if (!ix->capture_stream) cudaStreamCreateWithFlags(&ix->capture_stream, cudaStreamNonBlocking);
+            cudaGraph_t graph = nullptr;
+            if (ix->capture_stream && cudaStreamBeginCapture(ix->capture_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int rc = hybrid_locked(ix, d_q, have_terms ? d_t : nullptr, have_terms ? d_n : nullptr, B, l_max, fp,
+                                             dense_mode, d_r, d_f, ix->capture_stream);
+                const cudaError_t e = cudaStreamEndCapture(ix->capture_stream, &graph);
+                if (rc == RR_OK && e == cudaSuccess && graph && g_buf_generation.load() == gen &&
+                    cudaGraphInstantiate(&ent->exec, graph, 0) == cudaSuccess) {
+                    ent->generation = gen;
+                } else {
+                    ent->exec = nullptr;
+                    ent->seen = -1;                 // this shape cannot be captured: stay on the plain path
+                    cudaGetLastError();
+                }
+                if (graph) cudaGraphDestroy(graph);
+            } else {
+                ent->seen = -1;
+                cudaGetLastError();
+            }
+        }
+        if (ent->exec) {
+            RR_CUDA(cudaGraphLaunch(ent->exec, s));
+            rr_count_launch();
+            done = true;
+        } else if (ent->seen == 0) {
+            ent->seen = 1;
+        }
+    }
+    if (!done)
+        RR_TRY(hybrid_locked(ix, d_q, have_terms ? d_t : nullptr, have_terms ? d_n : nullptr, B, l_max, fp, dense_mode,
+                             d_r, d_f, s));
     RR_CUDA(cudaMemcpyAsync(h_top_row, d_r, r_bytes, cudaMemcpyDeviceToHost, s));
     RR_CUDA(cudaMemcpyAsync(h_top_final, d_f, f_bytes, cudaMemcpyDeviceToHost, s));
     RR_CUDA(cudaStreamSynchronize(s));

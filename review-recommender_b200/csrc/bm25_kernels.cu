@@ -76,7 +76,9 @@ struct Bm25Args {
     const uint64_t* tile_base;        // [n_tiles+1]
     const uint32_t* dir;              // [n_tiles, n_freq+1]
     const int32_t* term_slot;         // [V]
-    const uint32_t* rtab;             // [B, l_max, n_tiles+1] rare-list tile bounds of this batch (relative to the rare region)
+    const uint32_t* rtab;             // [B, l_max, n_tiles+1] rare-list tile bounds of this batch (relative to the rare
+                                      // region), or NULL: every CTA searches its own bounds (small batches)
+    const unsigned long long* rare_off;   // [V+1]
     int V, T, n_freq, n_tiles, tile0;
     long long n_docs;
     const int32_t* q_terms;
@@ -86,6 +88,26 @@ struct Bm25Args {
     long long ld_out;
     int stage_units, n_stages;
 };
+
+// warp-cooperative 32-ary lower bound: first index in [0, n) whose doc id is >= target (3 round trips for 16 k entries)
+__device__ __forceinline__ uint32_t warp_lower_bound(const uint2* __restrict__ list, uint32_t n, uint32_t target, int lane) {
+    uint32_t lo = 0, hi = n;
+    while (hi > lo) {
+        const uint32_t span = hi - lo;
+        if (span <= 32u) {
+            const bool less = lo + (uint32_t)lane < hi && __ldg(&list[lo + lane].x) < target;
+            return lo + (uint32_t)__popc(__ballot_sync(0xffffffffu, less));
+        }
+        const uint32_t step = (span + 31u) >> 5;
+        const uint32_t p = min(hi - 1u, lo + (uint32_t)(lane + 1) * step - 1u);
+        const bool less = __ldg(&list[p].x) < target;
+        const uint32_t c = (uint32_t)__popc(__ballot_sync(0xffffffffu, less));
+        const uint32_t nlo = min(hi, lo + c * step);
+        hi = c >= 32u ? hi : min(hi, lo + (c + 1u) * step);
+        lo = nlo;
+    }
+    return lo;
+}
 
 __global__ void __launch_bounds__(BM25_THREADS, 4)
 bm25_tile_scores_kernel(const Bm25Args a) {
@@ -135,12 +157,30 @@ bm25_tile_scores_kernel(const Bm25Args a) {
                     const uint32_t* r = a.rtab + ((long long)q * a.l_max + l) * (a.n_tiles + 1) + tile;
                     lo = base + r[0];
                     hi = base + r[1];
+                } else {
+                    lo = ~0ull;                       // rare term, bounds searched below by a warp
+                    hi = (unsigned long long)(uint32_t)t;
                 }
             }
             s_lo[tid] = lo;
             s_hi[tid] = hi;
         }
         __syncthreads();
+        if (a.rtab == nullptr) {
+            // small batches: no pre-pass; every warp resolves the rare terms l = warp, warp + 9, ... of this CTA
+            for (int l = warp; l < nl; l += BM25_THREADS / 32) {
+                if (s_lo[l] != ~0ull) continue;
+                const int t = (int)s_hi[l];
+                const unsigned long long b0 = a.rare_off[t], b1 = a.rare_off[t + 1];
+                const unsigned long long base = a.tile_base[a.n_tiles] + b0;
+                const uint2* list = reinterpret_cast<const uint2*>(a.postings) + base;
+                const uint32_t n = (uint32_t)(b1 - b0);
+                const uint32_t r0 = warp_lower_bound(list, n, doc0u, lane);
+                const uint32_t r1 = tile + 1 < a.n_tiles ? warp_lower_bound(list, n, doc0u + (uint32_t)a.T, lane) : n;
+                if (lane == 0) { s_lo[l] = base + r0; s_hi[l] = base + r1; }
+            }
+            __syncthreads();
+        }
         if (producer) {
             // ===== producer warp (one lane issues): chunk c of term l -> ring stage, up to NS chunks ahead =====
             if (lane == 0) {
@@ -350,6 +390,7 @@ int rr_launch_bm25_tile_scores(const rr_index_desc* d, const int32_t* d_terms, c
         RR_CUDA(cudaFuncSetAttribute(bm25_tile_scores_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         optin.done(smem, dev);
     }
+    if (B < 8) d_rtab = nullptr;          // small batches: the CTAs search their own rare-list bounds (one launch less)
     if (d_rtab != nullptr) {
         const long long total = (long long)B * l_max * (d->n_tiles + 1);
         RrProfScope prof(RR_PROF_MISC, stream);
@@ -361,7 +402,7 @@ int rr_launch_bm25_tile_scores(const rr_index_desc* d, const int32_t* d_terms, c
     }
     Bm25Args a;
     a.postings = reinterpret_cast<const uint4*>(d->d_postings); a.tile_base = d->d_tile_base; a.dir = d->d_dir;
-    a.term_slot = d->d_term_slot; a.rtab = d_rtab; a.V = d->vocab_size; a.T = T; a.n_freq = d->n_freq; a.n_tiles = d->n_tiles;
+    a.term_slot = d->d_term_slot; a.rtab = d_rtab; a.rare_off = reinterpret_cast<const unsigned long long*>(d->d_rare_off); a.V = d->vocab_size; a.T = T; a.n_freq = d->n_freq; a.n_tiles = d->n_tiles;
     a.n_docs = d->n_docs; a.q_terms = d_terms; a.q_len = d_nterms; a.l_max = l_max; a.out = d_out; a.ld_out = ld_out;
     a.stage_units = SU; a.n_stages = NS;
     // grid: query fastest, so that the CTAs sharing a tile (and the segments of common terms) are co-resident

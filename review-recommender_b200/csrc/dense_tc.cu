@@ -889,8 +889,18 @@ void rr_tc_destroy(rr_tc_state* s) {
     delete s;
 }
 
-// corpus prefix growth per segment: x4, or x2 when 8*k' keys would not fit one selection
-static int KP_growth(int kp) { return kp * 2 * TC_GROWTH <= TC_SORT_MAX ? TC_GROWTH : 2; }
+// Corpus prefix growth per segment.  A segment brings ~ (growth-1)*k' new candidates per query, so fewer, longer
+// segments trade selection launches (latency-bound: ~60 us each for 4096 queries) against the size of each selection.
+// Default: as large as keeps (growth+2)*k' keys -- the expected candidates plus head-room -- inside half of one
+// selection's capacity, between 2 and 8 (r01 used a fixed 4: 8 segments at 10 M rows, 7 on a 1.25 M-row shard;
+// now 5 and 4).  RR_TC_GROWTH overrides (2..16).
+static int KP_growth(int kp) {
+    const char* env = getenv("RR_TC_GROWTH");
+    int g = env ? atoi(env) : 0;
+    if (g < 2 || g > 16) g = std::min(8, std::max(2, TC_SORT_MAX / 2 / std::max(kp, 1) - 2));
+    while (g > 2 && (long long)kp * (g + 2) > TC_SORT_MAX) --g;
+    return g;
+}
 
 static int shortlist_size(int pool) {
     const char* env = getenv("RR_TC_SHORTLIST_FACTOR");
@@ -1002,8 +1012,12 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
     }
 
     const int n_dt = (int)((d->n_docs + TC_BN - 1) / TC_BN);
-    // first segment: tau = -inf, everything passes -> at most one tile per CTA and a sortable total
-    const int seg0_tiles = std::max(1, std::min(reps_min, (TC_SORT_MAX - KP) / TC_BN));
+    // first segment: tau = -inf, everything passes (256 keys per tile and query go through the selection), so it is
+    // sized to bring about as many keys as a later segment is expected to, (growth-1)*k'.  Limits: every (CTA, query,
+    // half) sub-list must hold all the tiles its CTA scans (cap_sub / 128 of them), the total must stay sortable.
+    const int seg0_want = ((growth - 1) * KP + TC_BN - 1) / TC_BN;
+    const int seg0_tiles = std::max(1, std::min(seg0_want, std::min(reps_min * std::max(1, cap_sub / (TC_BN / 2)),
+                                                                    (TC_SORT_MAX - KP) / TC_BN)));
     int n_segments = 0;
     int dt_lo = 0;
     while (dt_lo < n_dt) {

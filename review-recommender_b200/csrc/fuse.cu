@@ -43,6 +43,8 @@ struct FuseArgs {
     const float* rerank;
     const float* best;
     const float* gate;
+    int extras_by_slot;      // 1: best / gate are fields of the input tuples (sharded layout, indexed like dense);
+                             // 0: given in pool order [B, pool]
     long long* top_row;
     float* top_final;
     int32_t* top_pos;
@@ -118,6 +120,8 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
     float* s_dense = reinterpret_cast<float*>(s_prior + a.p.pool);
     float* s_bm25 = s_dense + a.p.pool;
     float* s_final = s_bm25 + a.p.pool;
+    float* s_best = s_final + a.p.pool;
+    float* s_gate = s_best + a.p.pool;
     __shared__ double red_d[32];
     __shared__ float red_f[32];
     __shared__ int red_i[32];
@@ -185,6 +189,10 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
         s_bm25[i] = a.bm25 ? a.bm25[at(s, 4)] : 0.f;
         s_n[i] = a.n ? a.n[at(s, 8)] : 0.0;
         s_avg[i] = a.avg ? a.avg[at(s, 8)] : nan64();
+        // optional per-candidate columns: tuple fields (sharded) or pool-order arrays
+        const long long e = a.extras_by_slot ? at(s, 4) : (long long)b * a.p.pool + i;
+        s_best[i] = a.best ? a.best[e] : 0.f;
+        s_gate[i] = a.gate ? a.gate[e] : 1.0f;
     }
     __syncthreads();
     // keep the slot of every pool position (val is reused by the second sort)
@@ -221,9 +229,8 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
     bool e_zero = false;
     const bool best_raw = a.best != nullptr && a.p.best_is_raw;
     if (best_raw) {
-        const long long e0 = (long long)b * a.p.pool;
         float lo = INFINITY, hi = -INFINITY; int bad = 0;
-        for (int i = tid; i < P; i += FUSE_THREADS) { const float x = a.best[e0 + i]; if (x != x) bad = 1; lo = fminf(lo, x); hi = fmaxf(hi, x); }
+        for (int i = tid; i < P; i += FUSE_THREADS) { const float x = s_best[i]; if (x != x) bad = 1; lo = fminf(lo, x); hi = fmaxf(hi, x); }
         lo = block_reduce<float>(lo, [](float x, float y) { return fminf(x, y); }, red_f);
         hi = block_reduce<float>(hi, [](float x, float y) { return fmaxf(x, y); }, red_f);
         bad = block_reduce<int>(bad, [](int x, int y) { return x | y; }, red_i);
@@ -332,7 +339,7 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
         // best-review term (float32 column)
         float be;
         {
-            be = a.best ? a.best[ex0 + i] : 0.f;
+            be = s_best[i];
             if (best_raw) be = e_zero ? 0.f : __fdiv_rn(__fsub_rn(be, emm_lo), emm_div);
             acc64 = __dadd_rn(acc64, (double)__fmul_rn(wbest32, be));
         }
@@ -340,7 +347,7 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
         const double ramp = fmin(fmax(__ddiv_rn(n, trust_den), 0.0), 1.0);
         const double satv = fmin(1.0, __ddiv_rn(l1, sat_den));
         const float trust = (float)__dadd_rn(__dmul_rn(0.6, ramp), __dmul_rn(0.4, satv));
-        const float gate = a.gate ? a.gate[ex0 + i] : 1.0f;
+        const float gate = s_gate[i];
         if (a.p.use_trust) fin = __fmul_rn(fin, trust);
         fin = __fmul_rn(fin, gate);
         s_final[i] = fin;
@@ -395,13 +402,13 @@ int rr_launch_fuse(const rr_fusion_params* p, int B, int n_in, int n_shards, int
                    const float* d_bm25, const double* d_n, const double* d_avg, const int64_t* d_grow,
                    const float* d_rerank, const float* d_best, const float* d_gate, int64_t* d_top_row,
                    float* d_top_final, int32_t* d_top_pos, float* d_components, int32_t* d_incomplete,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, int extras_by_slot) {
     if (!p || B < 0 || !d_dense || !d_grow || !d_top_row || !d_top_final)
         return rr_fail(RR_EINVAL, "rr_fuse_topk: null argument");
     if (p->pool <= 0 || p->pool > FUSE_MAX_POOL) return rr_fail(RR_EINVAL, "rr_fuse_topk: pool must be in 1..%d", FUSE_MAX_POOL);
     if (n_in <= 0 || n_in > FUSE_MAX_IN) return rr_fail(RR_EINVAL, "rr_fuse_topk: n_in must be in 1..%d", FUSE_MAX_IN);
     if (p->k <= 0) return rr_fail(RR_EINVAL, "rr_fuse_topk: k must be positive");
-    if ((d_rerank || d_best || d_gate) && n_in != p->pool)
+    if ((d_rerank || ((d_best || d_gate) && !extras_by_slot)) && n_in != p->pool)
         return rr_fail(RR_EINVAL, "rr_fuse_topk: rerank/best/gate are given in pool order and need n_in == pool");
     if (B == 0) return RR_OK;
     FuseArgs a;
@@ -412,13 +419,21 @@ int rr_launch_fuse(const rr_fusion_params* p, int B, int n_in, int n_shards, int
     a.top_row = reinterpret_cast<long long*>(d_top_row); a.top_final = d_top_final; a.top_pos = d_top_pos;
     a.components = d_components;
     a.incomplete = d_incomplete;
+    a.extras_by_slot = extras_by_slot;
     const int n_pad_in = next_pow2(n_in), n_pad_pool = next_pow2(p->pool);
     const int n_pad = n_pad_in > n_pad_pool ? n_pad_in : n_pad_pool;
-    const size_t smem = (size_t)n_pad * 8 + (size_t)(n_pad + (n_pad & 1)) * 4 + (size_t)p->pool * (8 * 3 + 4 * 3) + 16;
-    // ~21 KB of static shared memory on top: opt in whenever the sum may pass the 48 KB default
-    if (smem > 24 * 1024)
-        RR_CUDA(cudaFuncSetAttribute(fuse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RR_CUDA(cudaFuncSetAttribute(fuse_topk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    const size_t smem = (size_t)n_pad * 8 + (size_t)(n_pad + (n_pad & 1)) * 4 + (size_t)p->pool * (8 * 3 + 4 * 5) + 16;
+    // ~21 KB of static shared memory on top: opt in for the largest request seen so far on this device (set once per
+    // size class, never while a stream of this thread is being captured into a graph by a warm caller)
+    static RrSmemOptIn optin;
+    int dev = 0;
+    const size_t want = smem > 24 * 1024 ? smem : 1;
+    if (optin.needed(want, &dev)) {
+        if (smem > 24 * 1024)
+            RR_CUDA(cudaFuncSetAttribute(fuse_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RR_CUDA(cudaFuncSetAttribute(fuse_topk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        optin.done(want, dev);
+    }
     {
         RrProfScope prof(RR_PROF_FUSE, stream);
         fuse_topk_kernel<<<B, FUSE_THREADS, smem, stream>>>(a, n_pad_in, n_pad_pool);

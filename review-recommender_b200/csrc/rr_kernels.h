@@ -54,7 +54,7 @@ int rr_launch_fuse(const rr_fusion_params* p, int B, int n_in, int n_shards, int
                    const float* d_bm25, const double* d_n, const double* d_avg, const int64_t* d_grow,
                    const float* d_rerank, const float* d_best, const float* d_gate, int64_t* d_top_row,
                    float* d_top_final, int32_t* d_top_pos, float* d_components, int32_t* d_incomplete,
-                   cudaStream_t stream);
+                   cudaStream_t stream, int extras_by_slot = 0);
 
 // dense_tc.cu (tcgen05 shortlist path)
 struct rr_tc_plan;

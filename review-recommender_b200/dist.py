@@ -30,7 +30,8 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
-TUPLE_BYTES = 32   # int64 row + float64 n + float64 avg + float32 dense + float32 bm25
+TUPLE_BYTES = 32          # int64 row + float64 n + float64 avg + float32 dense + float32 bm25
+TUPLE_BYTES_EXTRAS = 40   # + float32 gate factor + float32 raw best-review similarity
 
 
 def all_reduce_stats(stats, group=None, device="cpu"):
@@ -49,15 +50,20 @@ def all_reduce_stats(stats, group=None, device="cpu"):
 
 
 def pack_tuples(world: int, grow: torch.Tensor, n: torch.Tensor, avg: torch.Tensor, dense: torch.Tensor,
-                bm25: torch.Tensor) -> torch.Tensor:
+                bm25: torch.Tensor, gate: Optional[torch.Tensor] = None, best: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[B, pool] field tensors -> uint8 [world, (B/world)*pool*32]: block g holds, for the query
-    slice owned by rank g, the five fields back to back (rows, n, avg, dense, bm25)."""
+    slice owned by rank g, the five fields back to back (rows, n, avg, dense, bm25); with the optional per-candidate
+    columns of run_search (gate factor, raw best-review similarity; both or neither) the tuple is 40 bytes."""
     B = grow.shape[0]
     assert B % world == 0, "pad the batch to a multiple of the world size"
+    assert (gate is None) == (best is None)
 
     def blk(t):
         return t.contiguous().view(world, -1).view(torch.uint8)
-    return torch.cat([blk(grow), blk(n), blk(avg), blk(dense), blk(bm25)], dim=1).contiguous()
+    fields = [blk(grow), blk(n), blk(avg), blk(dense), blk(bm25)]
+    if gate is not None:
+        fields += [blk(gate), blk(best)]
+    return torch.cat(fields, dim=1).contiguous()
 
 
 def exchange(send: torch.Tensor, group=None) -> torch.Tensor:
@@ -67,13 +73,15 @@ def exchange(send: torch.Tensor, group=None) -> torch.Tensor:
     return recv
 
 
-def field_views(recv: torch.Tensor, per_rank_queries: int, pool: int):
+def field_views(recv: torch.Tensor, per_rank_queries: int, pool: int, with_extras: bool = False):
     """Views of the received buffer: for each field the [bytes] tensor starting at shard 0's block of
     that field; shard s's block of the same field starts `stride` bytes later."""
     bp = per_rank_queries * pool
     flat = recv.view(-1)
-    stride = bp * TUPLE_BYTES
+    stride = bp * (TUPLE_BYTES_EXTRAS if with_extras else TUPLE_BYTES)
     off = {"grow": 0, "n": bp * 8, "avg": bp * 16, "dense": bp * 24, "bm25": bp * 28}
+    if with_extras:
+        off.update(gate=bp * 32, best=bp * 36)
     return {k: flat[v:] for k, v in off.items()}, stride
 
 
@@ -100,30 +108,106 @@ def local_pool(pool: int, world: int) -> int:
     return min(pool, max(16, m))
 
 
+class _Lane:
+    """One batch in flight: its own handle over the shared index tensors (own scratch), its own stream, buffers."""
+
+    def __init__(self, ix, stream):
+        self.ix, self.stream = ix, stream
+        self.send = None
+        self.flags_host = None
+
+
+class PendingShardedSearch:
+    """A sharded search in flight (ShardedSearcher.begin).  `result()` must be called on every rank, in the order
+    the searches were begun (its second round, when needed, is collective)."""
+
+    def __init__(self, searcher, lane, args, rows, final, flags_host, done):
+        self.s, self.lane, self.args = searcher, lane, args
+        self.rows, self.final, self.flags_host, self.done = rows, final, flags_host, done
+        self.repeated = 0
+
+    def result(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.done is None:
+            return self.rows, self.final
+        self.done.synchronize()             # the ONE host wait of a search: which queries need the second round
+        self.done = None
+        q, term_ids, n_terms, fusion, mode = self.args
+        idx = torch.nonzero(self.flags_host, as_tuple=False).view(-1)
+        nf = int(idx.numel())
+        self.repeated = self.s.last_repeated = nf
+        lane, G = self.lane, self.s.world
+        with torch.cuda.stream(lane.stream):
+            if nf > 0:
+                # a shard may hold more pool members than it sent, or could not certify its tensor-path result:
+                # repeat those queries with m = pool through the synchronous entry points (always exact)
+                idx = idx.to(self.rows.device)
+                pad = (-nf) % G
+                if pad:
+                    idx = torch.cat([idx, idx[:1].expand(pad)])
+                r2, f2, _ = self.s._round(lane, q[idx].contiguous(),
+                                          None if term_ids is None else term_ids[idx].contiguous(),
+                                          None if n_terms is None else n_terms[idx].contiguous(), fusion, mode,
+                                          fusion.pool, deferred=False)
+                self.rows = self.rows.clone()
+                self.final = self.final.clone()
+                self.rows[idx[:nf]] = r2[:nf]
+                self.final[idx[:nf]] = f2[:nf]
+                lane.stream.synchronize()
+        cur = torch.cuda.current_stream()
+        if cur != lane.stream:
+            self.rows.record_stream(cur)
+            self.final.record_stream(cur)
+        return self.rows, self.final
+
+
 class ShardedSearcher:
-    """Hybrid search over a row-sharded corpus; call `search` collectively on every rank.
+    """Hybrid search over a row-sharded corpus; call `search` (or `begin` / `result`) collectively on every rank.
 
     Two-round distributed top-pool.  Round 1: every shard sends its local exact top-m (m = local_pool,
     e.g. 48 of pool 150 on 8 shards), so the per-query work on a shard (shortlist selection, exact
     rescoring, candidate BM25) shrinks with the shard.  The owner merges G*m tuples and PROVES the
     result: a shard whose m-th similarity is below the merged pool's cut-off cannot hold another pool
     member.  Queries that fail the proof (rows clustered on one shard) are repeated with m = pool,
-    which is always exact.  Results are therefore identical to the single-GPU search."""
+    which is always exact.  Results are therefore identical to the single-GPU search.
 
-    def __init__(self, index, group=None, round1_pool: Optional[int] = None):
+    Batches in flight.  `begin()` enqueues round 1 of a batch -- shortlist GEMM, selection, rescoring, candidate BM25,
+    all-to-all, merge + fusion, result all-gather, flag read-back into pinned memory -- on one of `lanes` CUDA streams
+    (each with its own scratch handle over the same index tensors) WITHOUT any host wait; `token.result()` waits for
+    that batch only.  With two lanes the tail of batch i (latency-bound selection / exchange / host wait) runs under
+    the GEMM of batch i+1; a serving loop is `t1 = begin(b1); t2 = begin(b2); r1 = t1.result(); t3 = begin(b3); ...`.
+    Optional per-candidate columns of run_search (app/app_product_search.py:285-310): `extras(cand_local_rows,
+    q) -> (gate f32[B, m] | None, best_raw f32[B, m] | None)` is evaluated on every shard for its own candidates and
+    rides in the tuples (gate factor and raw best-review similarity are per-candidate quantities)."""
+
+    def __init__(self, index, group=None, round1_pool: Optional[int] = None, lanes: int = 1, extras=None):
         self.ix = index
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.round1_pool = round1_pool
         self.last_repeated = 0
+        self.extras = extras
+        self.n_lanes = max(1, int(lanes))
+        self._lanes = None
+        self._next = 0
 
-    def _merge(self, recv: torch.Tensor, fusion, m: int, B: int):
+    def _lane_list(self):
+        if self._lanes is None or self._lanes[0].ix is not self.ix:
+            if self.n_lanes == 1:
+                lanes = [_Lane(self.ix, None)]                  # runs on the caller's current stream
+            else:
+                # every lane has its own stream, so the caller's stream stays free for the next batch's ingest
+                lanes = [_Lane(self.ix if i == 0 else self.ix.view(), torch.cuda.Stream(device=self.ix.device))
+                         for i in range(self.n_lanes)]
+            self._lanes = lanes
+        return self._lanes
+
+    def _merge(self, lane, recv: torch.Tensor, fusion, m: int, B: int, with_extras: bool):
         """Owner side of a round: K4 over the G*m received tuples of this rank's B/G queries, then ONE all-gather
         of a byte buffer [rows int64[Bg,k] | final f32[Bg,k] | flags int32[Bg]] (the kernel writes into views of it)."""
-        ix, G = self.ix, self.world
+        ix, G = lane.ix, self.world
         k, Bg = fusion.k, B // G
-        views, stride = field_views(recv, Bg, m)
+        views, stride = field_views(recv, Bg, m, with_extras)
         o_final, o_flags = Bg * k * 8, Bg * k * 12
         nbytes = (Bg * k * 12 + Bg * 4 + 7) // 8 * 8                       # rows of the gathered buffer stay 8-byte aligned
         mine = torch.empty(nbytes, dtype=torch.uint8, device=recv.device)
@@ -131,7 +215,7 @@ class ShardedSearcher:
         final = mine[o_final:o_flags].view(torch.float32).view(Bg, k)
         flags = mine[o_flags:o_flags + Bg * 4].view(torch.int32)
         ix.fuse_sharded(fusion, G, m, stride, Bg, views["dense"], views["bm25"], views["n"], views["avg"], views["grow"],
-                        out=(rows, final, flags))
+                        out=(rows, final, flags), gate=views.get("gate"), best=views.get("best"))
         out = torch.empty((G, mine.numel()), dtype=torch.uint8, device=mine.device)
         dist.all_gather_into_tensor(out.view(-1), mine, group=self.group)
         all_rows = out[:, :o_final].view(torch.int64).reshape(B, k)
@@ -139,48 +223,81 @@ class ShardedSearcher:
         all_flags = out[:, o_flags:o_flags + Bg * 4].view(torch.int32).reshape(B)
         return all_rows, all_final, all_flags
 
-    def _round(self, q, term_ids, n_terms, fusion, mode, m, deferred: bool):
+    def _round(self, lane, q, term_ids, n_terms, fusion, mode, m, deferred: bool):
         """deferred=True: no host synchronisation anywhere (queries the tensor path cannot certify come back
         flagged); deferred=False: rr_dense_topk redoes uncertified queries exactly before the exchange."""
-        ix, G = self.ix, self.world
+        ix, G = lane.ix, self.world
         B = int(q.shape[0])
-        if deferred:
+        with_extras = self.extras is not None
+        if deferred and not with_extras:
             send = ix.shard_tuples(q, term_ids, n_terms, m, G, mode)
         else:
-            cand, dense, _cnt = ix.dense_topk(q, m, mode)
+            if deferred:
+                cand, dense, _cnt, unc = ix.dense_topk(q, m, mode, want_uncertified=True)
+            else:
+                cand, dense, _cnt = ix.dense_topk(q, m, mode)
+                unc = None
             bm25, n, avg, grow = ix.candidate_tuples(term_ids, n_terms, cand)
-            send = pack_tuples(G, grow, n, avg, dense, bm25)
-        return self._merge(exchange(send, self.group), fusion, m, B)
+            if unc is not None:
+                grow = torch.where(unc[:, None] != 0, torch.full_like(grow, -2), grow)
+            gate = best = None
+            if with_extras:
+                gate, best = self.extras(cand, q)
+                gate = torch.ones_like(dense) if gate is None else gate.to(torch.float32)
+                best = torch.zeros_like(dense) if best is None else best.to(torch.float32)
+            send = pack_tuples(G, grow, n, avg, dense, bm25, gate, best)
+        return self._merge(lane, exchange(send, self.group), fusion, m, B, with_extras)
+
+    def begin(self, q: torch.Tensor, term_ids: Optional[torch.Tensor], n_terms: Optional[torch.Tensor], fusion,
+              mode: int = 0) -> PendingShardedSearch:
+        """Enqueue round 1 of a batch (q float32[B, D] identical on every rank, B % world == 0) without a host wait."""
+        G = self.world
+        B, pool = int(q.shape[0]), fusion.pool
+        if B % G:
+            raise ValueError("batch size must be a multiple of the world size")
+        m = min(self.round1_pool or local_pool(pool, G), pool)
+        lanes = self._lane_list()
+        lane = lanes[self._next % len(lanes)]
+        self._next += 1
+        cur = torch.cuda.current_stream()
+        if lane.stream is None:
+            lane_stream = cur
+        else:
+            lane_stream = lane.stream
+            lane_stream.wait_stream(cur)                       # the inputs were produced on the caller's stream
+        run = _Lane(lane.ix, lane_stream)
+        with torch.cuda.stream(lane_stream):
+            rows, final, flags = self._round(run, q, term_ids, n_terms, fusion, mode, m, deferred=True)
+            if lane.flags_host is None or lane.flags_host.numel() != B:
+                lane.flags_host = torch.empty(B, dtype=torch.int32).pin_memory()
+            lane.flags_host.copy_(flags, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(lane_stream)
+        return PendingShardedSearch(self, run, (q, term_ids, n_terms, fusion, mode), rows, final, lane.flags_host, done)
 
     def search(self, q: torch.Tensor, term_ids: Optional[torch.Tensor], n_terms: Optional[torch.Tensor], fusion,
                mode: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
         """q float32[B, D] (identical on every rank, B % world == 0) -> (global rows int64[B, k],
         final float32[B, k]) on every rank."""
-        G = self.world
-        B, pool = int(q.shape[0]), fusion.pool
-        if B % G:
-            raise ValueError("batch size must be a multiple of the world size")
-        m = self.round1_pool or local_pool(pool, G)
-        m = min(m, pool)
-        rows, final, flags = self._round(q, term_ids, n_terms, fusion, mode, m, deferred=True)
-        # the ONE host synchronisation of a search: which queries need the second round (a shard may hold more
-        # pool members than it sent, or could not certify its tensor-path result)
-        idx = torch.nonzero(flags, as_tuple=False).view(-1)
-        nf = int(idx.numel())
-        self.last_repeated = nf
-        if nf > 0:
-            pad = (-nf) % G
-            if pad:
-                idx = torch.cat([idx, idx[:1].expand(pad)])
-            r2, f2, _ = self._round(q[idx].contiguous(),
-                                    None if term_ids is None else term_ids[idx].contiguous(),
-                                    None if n_terms is None else n_terms[idx].contiguous(), fusion, mode, pool,
-                                    deferred=False)
-            rows = rows.clone()
-            final = final.clone()
-            rows[idx[:nf]] = r2[:nf]
-            final[idx[:nf]] = f2[:nf]
-        return rows, final
+        return self.begin(q, term_ids, n_terms, fusion, mode).result()
+
+
+def make_extras(gate_ix=None, review_ix=None, groups_per_query=None, gate_penalty: float = 0.5):
+    """`extras` callback of ShardedSearcher for run_search's per-candidate columns (app/app_product_search.py:285-310),
+    evaluated by every shard on ITS OWN candidates (local rows):
+      gate  `engine.GateIndex` over the shard's product texts + one gate-group list per query (drop_in.build_gate_groups)
+      best  `engine.ReviewIndex` over the reviews of the shard's products: raw best-review similarity, min-max
+            normalised after the cross-shard merge by K4 (Fusion.best_is_raw = True)
+    The reference's `max_rows` cap on scanned reviews (:343-346) is defined over the reviews of the WHOLE pool and is
+    not applied here: use it only where the cap does not bind (its default, 300 000 rows, rarely does)."""
+    def extras(cand: torch.Tensor, q: torch.Tensor):
+        gate = best = None
+        if gate_ix is not None and groups_per_query is not None:
+            gate = gate_ix.factors(groups_per_query, cand, gate_penalty)
+        if review_ix is not None:
+            best, _ = review_ix.best(q, cand, max_rows=None, as_numpy=False)
+        return gate, best
+    return extras
 
 
 class GridSearcher:
@@ -193,7 +310,7 @@ class GridSearcher:
 
     Collective construction: every rank of `dist.group.WORLD` must create the searcher (it creates the sub-groups)."""
 
-    def __init__(self, index, query_groups: int = 1, round1_pool: Optional[int] = None):
+    def __init__(self, index, query_groups: int = 1, round1_pool: Optional[int] = None, lanes: int = 1, extras=None):
         self.world = dist.get_world_size()
         self.rank = dist.get_rank()
         self.Q = int(query_groups)
@@ -211,8 +328,15 @@ class GridSearcher:
             if s == self.s:
                 self.col_group = grp
         self.ix = index
-        self.inner = ShardedSearcher(index, group=self.row_group, round1_pool=round1_pool) if self.R > 1 else None
+        self.inner = (ShardedSearcher(index, group=self.row_group, round1_pool=round1_pool, lanes=lanes, extras=extras)
+                      if self.R > 1 else None)
         self.last_repeated = 0
+
+    def begin(self, q, term_ids, n_terms, fusion, mode: int = 0):
+        """Batches in flight (plain row sharding only, Q = 1): see ShardedSearcher.begin."""
+        if self.Q != 1 or self.inner is None:
+            raise ValueError("begin() needs plain row sharding (query_groups = 1, world > 1)")
+        return self.inner.begin(q, term_ids, n_terms, fusion, mode)
 
     @staticmethod
     def layout(rank: int, world: int, query_groups: int) -> Tuple[int, int, int]:

@@ -449,8 +449,9 @@ class HybridIndex:
         return out
 
     # ---- dense -----------------------------------------------------------------------------
-    def dense_topk(self, q, pool: int, mode: int = _lib.RR_DENSE_AUTO):
-        """(idx int64[B, pool] local rows, sims float32[B, pool], count int32[B])."""
+    def dense_topk(self, q, pool: int, mode: int = _lib.RR_DENSE_AUTO, want_uncertified: bool = False):
+        """(idx int64[B, pool] local rows, sims float32[B, pool], count int32[B]).  want_uncertified=True: no host
+        synchronisation, a fourth tensor int32[B] marks the queries whose pool is not proven exact (not redone)."""
         q = self._dev(q, torch.float32)
         if q.dim() == 1:
             q = q[None, :]
@@ -460,6 +461,11 @@ class HybridIndex:
         idx = torch.empty((B, pool), dtype=torch.int64, device=self.device)
         sims = torch.empty((B, pool), dtype=torch.float32, device=self.device)
         cnt = torch.empty((B,), dtype=torch.int32, device=self.device)
+        if want_uncertified:
+            unc = torch.empty((B,), dtype=torch.int32, device=self.device)
+            check(self.lib.rr_dense_topk_deferred(self._h, _ptr(q), B, pool, mode, _ptr(idx), _ptr(sims), _ptr(cnt),
+                                                  _ptr(unc), _stream()))
+            return idx, sims, cnt, unc
         check(self.lib.rr_dense_topk(self._h, _ptr(q), B, pool, mode, _ptr(idx), _ptr(sims), _ptr(cnt), _stream()))
         return idx, sims, cnt
 
@@ -538,7 +544,8 @@ class HybridIndex:
         return send
 
     def fuse_sharded(self, fusion: Fusion, n_shards: int, per_shard: int, shard_stride_bytes: int, B: int,
-                     dense, bm25, n, avg, grow, out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
+                     dense, bm25, n, avg, grow, out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None,
+                     gate=None, best=None):
         """K4 over tuples received from `n_shards` row shards (cross-shard merge + fusion).  The field
         tensors are views into one exchange buffer; shard s's [B, per_shard] block of a field starts
         s*shard_stride_bytes after the field's base."""
@@ -555,8 +562,8 @@ class HybridIndex:
             final = torch.empty((B, fusion.k), dtype=torch.float32, device=self.device)
             flags = torch.zeros((B,), dtype=torch.int32, device=self.device)
         check(self.lib.rr_fuse_topk_sharded(C.byref(p), B, n_shards, per_shard, shard_stride_bytes, _ptr(dense),
-                                            _ptr(bm25), _ptr(n), _ptr(avg), _ptr(grow), _ptr(rows), _ptr(final),
-                                            _ptr(flags), self.device.index or 0, _stream()))
+                                            _ptr(bm25), _ptr(n), _ptr(avg), _ptr(grow), _ptr(gate), _ptr(best), _ptr(rows),
+                                            _ptr(final), _ptr(flags), self.device.index or 0, _stream()))
         return rows, final, flags
 
     # ---- one-shot ------------------------------------------------------------------------------

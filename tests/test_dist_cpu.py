@@ -66,6 +66,18 @@ WORKER = textwrap.dedent('''
         ref_idx, ref_sims = cosine_topk_canonical(q[gq], full_emb, pool)
         assert np.array_equal(rows[order], ref_idx), (rank, b)
         assert np.allclose(scores[order], ref_sims, atol=1e-6)
+    # ---- 40-byte tuples: gate factor and raw best-review similarity ride along (run_search :285-310) ------------
+    gate = ((grow % 7) / 7.0).astype(np.float32); best = ((grow % 11) / 11.0).astype(np.float32)
+    send2 = rr.dist.pack_tuples(world, t(grow), t(n), t(avg), t(dense), t(bm25), t(gate), t(best))
+    assert send2.shape == (world, Bg * pool * rr.dist.TUPLE_BYTES_EXTRAS)
+    recv2 = rr.dist.exchange(send2)
+    views2, stride2 = rr.dist.field_views(recv2, Bg, pool, with_extras=True)
+    assert stride2 == Bg * pool * rr.dist.TUPLE_BYTES_EXTRAS
+    for s_ in range(world):
+        g_ = views2["grow"][s_ * stride2: s_ * stride2 + Bg * pool * 8].view(torch.int64).numpy()
+        ga = views2["gate"][s_ * stride2: s_ * stride2 + Bg * pool * 4].view(torch.float32).numpy()
+        be = views2["best"][s_ * stride2: s_ * stride2 + Bg * pool * 4].view(torch.float32).numpy()
+        assert np.array_equal(ga, ((g_ % 7) / 7.0).astype(np.float32)) and np.array_equal(be, ((g_ % 11) / 11.0).astype(np.float32))
     dist.barrier()
     dist.destroy_process_group()
     print(f"rank {rank} ok", flush=True)

@@ -69,10 +69,60 @@ WORKER = textwrap.dedent('''
             assert torch.equal(rows, r1), (mode, int((rows != r1).sum()))
             assert torch.equal(final, f1), mode
             whole.close()
-    # ---- row shards x query groups: same answers for every layout ------------------------------------------
+    # ---- batches in flight: two lanes, results identical to the one-at-a-time search ----------------------------
     qd, qtd, ntd = torch.from_numpy(q).to(dev), torch.from_numpy(qt).to(dev), torch.from_numpy(nt).to(dev)
-    plain = rr.dist.ShardedSearcher(ix)
-    ref_rows, ref_final = plain.search(qd, qtd, ntd, fusion, mode=rr._lib.RR_DENSE_TENSOR)
+    one = rr.dist.ShardedSearcher(ix)
+    ref_rows, ref_final = one.search(qd, qtd, ntd, fusion, mode=rr._lib.RR_DENSE_TENSOR)
+    two = rr.dist.ShardedSearcher(ix, lanes=2)
+    perm = torch.arange(B - 1, -1, -1, device=dev)
+    batches = [(qd, qtd, ntd), (qd[perm].contiguous(), qtd[perm].contiguous(), ntd[perm].contiguous())] * 3
+    tokens, outs = [], []
+    for bq, bt, bn in batches:
+        tokens.append(two.begin(bq, bt, bn, fusion, mode=rr._lib.RR_DENSE_TENSOR))
+        if len(tokens) == 2:
+            outs.append(tokens.pop(0).result())
+    outs += [t.result() for t in tokens]
+    torch.cuda.synchronize(dev)
+    for i, (r_, f_) in enumerate(outs):
+        want_r, want_f = (ref_rows, ref_final) if i % 2 == 0 else (ref_rows[perm], ref_final[perm])
+        assert torch.equal(r_, want_r) and torch.equal(f_, want_f), ("lanes", i)
+    print(f"rank {rank} two lanes ok", flush=True)
+
+    # ---- gate and best-review columns ride in the tuples (run_search :285-310) ----------------------------------
+    from tests.golden_worlds import make_gate_texts, GATE_QUERIES
+    texts = make_gate_texts(N, full.doc_offsets, full.token_ids)
+    skus = syn.skus(N)
+    rngr = np.random.default_rng(21)
+    M = 3 * N // 10
+    rev_prod = rngr.integers(0, N, size=M)
+    rev_emb = rngr.standard_normal((M, D)).astype(np.float32)
+    rev_skus = [skus[i] for i in rev_prod]
+    Bx = 16 * max(world, 1)
+    qx = q[:Bx]
+    qtx, ntx = qt[:Bx], nt[:Bx]
+    groups = [rr.drop_in.build_gate_groups(GATE_QUERIES[i % len(GATE_QUERIES)]) for i in range(Bx)]
+    fx = rr.engine.Fusion(k=20, rerank_k=0, w_dense=0.45, w_bm25=0.15, w_rerank=0.0, w_prior=0.10, w_best=0.30, best_is_raw=True)
+    g_loc = rr.engine.GateIndex(texts[row0:row1], rr.drop_in.GATE_FIXED_GROUPS, device=dev)
+    r_loc = rr.engine.ReviewIndex(rev_emb, rev_skus, skus[row0:row1], device=dev)
+    sx = rr.dist.ShardedSearcher(ix, extras=rr.dist.make_extras(g_loc, r_loc, groups, 0.5))
+    rows_x, final_x = sx.search(torch.from_numpy(qx).to(dev), torch.from_numpy(qtx).to(dev), torch.from_numpy(ntx).to(dev),
+                                fx, mode=rr._lib.RR_DENSE_EXACT)
+    if rank == 0:
+        whole = rr.engine.HybridIndex(full.emb, full.doc_offsets, full.token_ids, V, full.n_reviews, full.avg_stars, device=dev)
+        g_all = rr.engine.GateIndex(texts, rr.drop_in.GATE_FIXED_GROUPS, device=dev)
+        r_all = rr.engine.ReviewIndex(rev_emb, rev_skus, skus, device=dev)
+        cand, dense, cnt = whole.dense_topk(qx, fx.pool, rr._lib.RR_DENSE_EXACT)
+        bm25, n_, avg_, grow_ = whole.candidate_tuples(qtx, ntx, cand)
+        gate = g_all.factors(groups, cand, 0.5)
+        best, _ = r_all.best(qx, cand, max_rows=None, as_numpy=False)
+        w_rows, w_final, _, _ = whole.fuse(fx, dense, bm25, n_, avg_, grow_, count=cnt, best=best, gate=gate)
+        assert torch.equal(rows_x, w_rows), int((rows_x != w_rows).sum())
+        assert torch.equal(final_x, w_final)
+        assert float(gate.min()) < 1.0 and float(best.max()) > 0.0, "the extras must actually matter in this case"
+        whole.close()
+    print(f"rank {rank} extras ok", flush=True)
+
+    # ---- row shards x query groups: same answers for every layout ------------------------------------------
     for Q in [x for x in (2, 4) if world % x == 0]:
         grid = rr.dist.GridSearcher(None, Q)
         g, s, R = rr.dist.GridSearcher.layout(rank, world, Q)
@@ -125,4 +175,4 @@ def _run_world(tmp_path, world):
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-4000:]
     for k in range(world):
-        assert f"rank {k} ok" in r.stdout
+        assert f"rank {k} ok" in r.stdout and f"rank {k} two lanes ok" in r.stdout and f"rank {k} extras ok" in r.stdout

@@ -70,10 +70,11 @@ def parse_args():
                     help="batches in flight (2 = consecutive steps alternate between two handles / CUDA streams over the "
                          "same index, so one step's latency-bound tail -- selection, exchange, host wait -- runs under the next "
                          "step's GEMM).  0 = auto: 1 on a single GPU (power-capped GEMM: measured +0.6 %), 2 on several")
-    ap.add_argument("--synth", default="recipe", choices=["recipe", "device"],
+    ap.add_argument("--synth", default="recipe", choices=["recipe", "device", "clustered"],
                     help="recipe = the SURVEY 8d NumPy recipe, generated per 1 M-row chunk on the host (default; the only "
                          "mode with id_parity); device = same distributions drawn with torch generators in HBM (fast set-up "
-                         "for profiling runs, not comparable with the oracle)")
+                         "for profiling runs, not comparable with the oracle); clustered = device generators, 2000 tight "
+                         "clusters (in-cluster cosine ~0.6), queries drawn from the clusters: robustness workload")
     ap.add_argument("--parity-queries", type=int, default=32,
                     help="queries of the batch that are also answered by the CPU oracle (oracle/sharded.py) -> id_parity")
     ap.add_argument("--synth-workers", type=int, default=0, help="host threads generating recipe chunks (0 = all cores)")
@@ -213,7 +214,30 @@ def run_reference(args, cfg):
 # ------------------------------------------------------------------------------------------------
 # device-side synthetic corpus (same distributions as synth.py, generated in HBM)
 # ------------------------------------------------------------------------------------------------
-def device_shard(cfg, row0: int, n: int, dev):
+CLUSTERS, CLUSTER_COS = 2000, 0.6
+
+
+def cluster_centres(D: int, dev):
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(777)
+    c = torch.randn((CLUSTERS, D), generator=g, device=dev, dtype=torch.float32)
+    return c / torch.linalg.vector_norm(c, dim=1, keepdim=True)
+
+
+def clustered_rows(n: int, D: int, seed: int, dev):
+    """Rows of a catalogue made of 2000 tight clusters (robustness workload): centre + sigma * noise, normalised, with
+    sigma chosen so that two rows of one cluster have cosine ~ 0.6 (1 / (1 + sigma^2 D) = 0.6)."""
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    sigma = ((1.0 / CLUSTER_COS - 1.0) / D) ** 0.5
+    assign = torch.randint(0, CLUSTERS, (n,), generator=g, device=dev)
+    x = cluster_centres(D, dev)[assign] + sigma * torch.randn((n, D), generator=g, device=dev, dtype=torch.float32)
+    return x / torch.linalg.vector_norm(x, dim=1, keepdim=True)
+
+
+def device_shard(cfg, row0: int, n: int, dev, clustered: bool = False):
     import torch
     import review_recommender_b200 as rr
     syn = rr.synth
@@ -227,8 +251,11 @@ def device_shard(cfg, row0: int, n: int, dev):
         take = min(syn.CHUNK - within, row0 + n - r)
         g = torch.Generator(device=dev)
         g.manual_seed(1000 + chunk)
-        x = torch.randn((within + take, D), generator=g, device=dev, dtype=torch.float32)[within:]
-        x /= torch.linalg.vector_norm(x, dim=1, keepdim=True).clamp_min(1e-12)
+        if clustered:
+            x = clustered_rows(within + take, D, 1000 + chunk, dev)[within:]
+        else:
+            x = torch.randn((within + take, D), generator=g, device=dev, dtype=torch.float32)[within:]
+            x /= torch.linalg.vector_norm(x, dim=1, keepdim=True).clamp_min(1e-12)
         emb[r - row0:r - row0 + take] = x
         del x
         g.manual_seed(3000 + chunk)
@@ -463,7 +490,9 @@ def main():
             oracle = ShardedOracle(q_np[sample], qt_np[sample], V, fusion.pool)
         emb, offs, toks, nrev, avg = recipe_shard(cfg, row0, n_local, dev, oracle, args.synth_workers)
     else:
-        emb, offs, toks, nrev, avg = device_shard(cfg, row0, n_local, dev)
+        emb, offs, toks, nrev, avg = device_shard(cfg, row0, n_local, dev, clustered=args.synth == "clustered")
+        if args.synth == "clustered":
+            q_np = clustered_rows(B, D, 2000, dev).cpu().numpy()
     # global BM25 statistics (every query group holds the whole corpus: reduce inside the row group)
     tok_counts = torch.tensor([int(offs[-1].item())], dtype=torch.int64, device=dev)
     pos0 = 0
@@ -516,6 +545,7 @@ def main():
     step_no = [0]
     pending = collections.deque()
     last = [None]
+    repeated = [0]
 
     pipelined = searcher is not None and Q == 1 and args.in_flight > 1
 
@@ -534,12 +564,16 @@ def main():
         with torch.cuda.stream(st):
             pending.append(h.hybrid_search_begin(q_dev, qt_dev, nt_dev, fusion, mode=args.dense_mode))
         if len(pending) >= len(lanes):
-            last[0] = pending.popleft().result()
+            tok = pending.popleft()
+            last[0] = tok.result()
+            repeated[0] = tok.repeated
         return last[0]
 
     def drain():
         while pending:
-            last[0] = pending.popleft().result()
+            tok = pending.popleft()
+            last[0] = tok.result()
+            repeated[0] = tok.repeated
         for _, st in lanes[1:]:
             torch.cuda.current_stream().wait_stream(st)
         return last[0]
@@ -774,12 +808,14 @@ def main():
     line = {
         "metric": cfg.get("metric", METRIC), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic" + (" (SURVEY 8d NumPy recipe)" if args.synth == "recipe" else " (device generators)"),
+        "dtype": "bf16", "data": "synthetic" + {"recipe": " (SURVEY 8d NumPy recipe)", "device": " (device generators)",
+                                "clustered": " (device generators, 2000 clusters with in-cluster cosine 0.6: robustness workload)"}[args.synth],
         "dtype_note": "bf16 tensor-core shortlist (fp32 accumulate), exact f32 rescoring, f32/f64 fusion as the reference",
         "config": {"workload": cfg["workload"], "docs": N, "docs_per_gpu": n_local, "dim": D, "vocab": V, "batch": B,
                    "query_terms": L, "k": K, "pool": fusion.pool, "weights": wts, "parallelism": f"row-sharded x{R}" + (f", query groups x{Q}" if Q > 1 else ""),
                    "l2": "inputs larger than L2 (bf16 corpus shard read every step)",
-                   "dense_path": dstats, "setup_s": setup_s, "index_build_s": build_s, "batches_in_flight": args.in_flight if searcher is not None else len(lanes)},
+                   "dense_path": dstats, "repeated_queries_last_step": int(repeated[0] if searcher is None else searcher.inner.last_repeated if searcher.inner is not None else 0),
+                   "setup_s": setup_s, "index_build_s": build_s, "batches_in_flight": args.in_flight if searcher is not None else len(lanes)},
         "roofline": roofline, "kernels": kernels, "profiled_ms_per_step": profiled_ms_per_step, "sparse": sparse,
         "cpu_baseline": cpu_base,
         "clocks": {"sm_mhz": clock_info.get("sm_mhz"), "sm_max_mhz": clock_info.get("sm_max_mhz"),

@@ -333,8 +333,8 @@ int rr_gate_fixed_bitmaps(const uint8_t* d_text, const int64_t* d_text_off, cons
 int64_t rr_launch_count(int reset);
 typedef struct rr_dense_stats {
     int32_t path;            /* 1 exact, 2 tensor */
-    int32_t n_uncertified;   /* queries redone on the exact path */
-    int32_t n_overflow;      /* queries whose candidate buffer overflowed */
+    int32_t n_uncertified;   /* queries the first tensor pass could not certify (redone: second pass, then exact path) */
+    int32_t n_overflow;      /* of those, queries the second tensor pass (4x shortlist) handed to the exact fp32 path */
     int32_t shortlist;       /* k' */
     int32_t n_segments;
     float   eps;             /* bf16 score error bound used for certification */

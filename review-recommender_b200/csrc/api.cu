@@ -240,11 +240,17 @@ extern "C" int rr_bm25_get_scores(rr_index* ix, const int32_t* d_term_ids, const
     ScratchFence fence(ix, s);
     const size_t per_q = rr_bm25_rtab_bytes(1, l_max, ix->d.n_tiles);
     const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, ((size_t)256 << 20) / std::max<size_t>(per_q, 1)));
-    RR_TRY(ix->rtab.ensure(per_q * (size_t)chunk));
+    {
+        const void* before = ix->rtab.p;
+        RR_TRY(ix->rtab.ensure(256 + per_q * (size_t)chunk));     // [work counters | rare-bound table]
+        if (ix->rtab.p != before) RR_CUDA(cudaMemsetAsync(ix->rtab.p, 0, 256, s));   // the kernel re-arms them itself afterwards
+    }
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = std::min(chunk, B - b0);
         RR_TRY(rr_launch_bm25_tile_scores(&ix->d, d_term_ids + (int64_t)b0 * l_max, d_n_terms + b0, nb, l_max,
-                                          d_out + (int64_t)b0 * ld_out, ld_out, static_cast<uint32_t*>(ix->rtab.p), s));
+                                          d_out + (int64_t)b0 * ld_out, ld_out,
+                                          reinterpret_cast<uint32_t*>(static_cast<char*>(ix->rtab.p) + 256),
+                                          static_cast<unsigned*>(ix->rtab.p), s));
     }
     return RR_OK;
 }

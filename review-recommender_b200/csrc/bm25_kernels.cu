@@ -31,6 +31,7 @@
 //      bit-identical to the tile kernel at those docs.  Also gathers n_reviews / avg_stars /
 //      global row so that the fusion kernel gets complete tuples, optionally straight into the
 //      all-to-all send buffer of a sharded search.
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
@@ -238,6 +239,170 @@ bm25_tile_scores_kernel(const Bm25Args a) {
     for (int i = (n4 << 2) + tid; i < tile_n; i += BM25_CONSUMERS) dst[i] = acc[i];
 }
 
+// Persistent variant (query term lists of at most 64 terms): CTAs stay resident and pull (query, tile) items from a
+// global counter.  The producer warp works one item AHEAD of the consumers: while they still accumulate / write out
+// item k it has already looked up the segment bounds of item k+1 (double-buffered in shared memory) and keeps the ring
+// full with its first chunks, so the directory round trips, the accumulator zero-fill and the write-out of one item
+// overlap with the posting stream of the next -- the per-CTA prologue that the one-shot kernel above pays per item
+// (4-5 dependent global loads, ~30 % of a 4-term item's lifetime) is hidden, and there are no waves to quantise.
+__global__ void __launch_bounds__(BM25_THREADS, 3)
+bm25_tile_scores_persistent_kernel(const Bm25Args a, int n_items, int B, unsigned* __restrict__ counter) {
+    extern __shared__ __align__(16) unsigned char bm25_smem[];
+    float* acc = reinterpret_cast<float*>(bm25_smem);
+    uint4* ring = reinterpret_cast<uint4*>(bm25_smem + (size_t)a.T * sizeof(float));
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)a.n_stages * a.stage_units);
+    uint64_t* empty = full + BM25_MAX_STAGES;
+    __shared__ unsigned long long s_lo[2][BM25_MAXL], s_hi[2][BM25_MAXL];
+    __shared__ int s_item[2], s_nl[2];
+    __shared__ uint64_t bfull[2], bempty[2];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool producer = warp == BM25_CONSUMERS / 32;
+    const int SU = a.stage_units, NS = a.n_stages;
+    if (tid == 0) {
+        for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], BM25_CONSUMERS / 32); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], BM25_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int stage = 0;
+    uint32_t phase = 0;
+
+    if (producer) {
+        for (int k = 0;; ++k) {
+            const int buf = k & 1;
+            mbar_wait(&bempty[buf], (uint32_t)(((k >> 1) & 1) ^ 1));       // consumers are done with item k-2's bounds
+            int item = 0;
+            if (lane == 0) item = (int)atomicAdd(counter, 1u);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= n_items) {
+                if (lane == 0) {
+                    s_item[buf] = -1;
+                    mbar_arrive(&bfull[buf]);
+                    // the last CTA to run dry re-arms the two counters for the next launch (no memset per call)
+                    if (atomicAdd(counter + 1, 1u) == gridDim.x - 1) { counter[0] = 0u; counter[1] = 0u; __threadfence(); }
+                }
+                break;
+            }
+            const int q = item % B, tile = a.tile0 + item / B;
+            int L = a.q_len[q];
+            if (L > a.l_max) L = a.l_max;
+            if (L > BM25_MAXL) L = BM25_MAXL;
+            const uint32_t doc0u = (uint32_t)((long long)tile * a.T);
+            for (int l = lane; l < L; l += 32) {
+                const int t = a.q_terms[(long long)q * a.l_max + l];
+                unsigned long long lo = 0, hi = 0;
+                if (t >= 0 && t < a.V) {
+                    const int slot = a.term_slot[t];
+                    if (slot >= 0) {
+                        const unsigned long long base = a.tile_base[tile];
+                        const uint32_t* d = a.dir + (long long)tile * (a.n_freq + 1) + slot;
+                        lo = base + d[0];
+                        hi = base + d[1];
+                    } else if (a.rtab != nullptr) {
+                        const unsigned long long base = a.tile_base[a.n_tiles];
+                        const uint32_t* r = a.rtab + ((long long)q * a.l_max + l) * (a.n_tiles + 1) + tile;
+                        lo = base + r[0];
+                        hi = base + r[1];
+                    } else {
+                        lo = ~0ull;
+                        hi = (unsigned long long)(uint32_t)t;
+                    }
+                }
+                s_lo[buf][l] = lo;
+                s_hi[buf][l] = hi;
+            }
+            __syncwarp();
+            if (a.rtab == nullptr) {
+                for (int l = 0; l < L; ++l) {
+                    if (s_lo[buf][l] != ~0ull) continue;
+                    const int t = (int)s_hi[buf][l];
+                    const unsigned long long b0 = a.rare_off[t], b1 = a.rare_off[t + 1];
+                    const unsigned long long base = a.tile_base[a.n_tiles] + b0;
+                    const uint2* list = reinterpret_cast<const uint2*>(a.postings) + base;
+                    const uint32_t n = (uint32_t)(b1 - b0);
+                    const uint32_t r0 = warp_lower_bound(list, n, doc0u, lane);
+                    const uint32_t r1 = tile + 1 < a.n_tiles ? warp_lower_bound(list, n, doc0u + (uint32_t)a.T, lane) : n;
+                    __syncwarp();
+                    if (lane == 0) { s_lo[buf][l] = base + r0; s_hi[buf][l] = base + r1; }
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) {
+                s_item[buf] = item;
+                s_nl[buf] = L;
+                mbar_arrive(&bfull[buf]);                                    // bounds of item k are published
+                for (int l = 0; l < L; ++l) {
+                    const unsigned long long lo = s_lo[buf][l], hi = s_hi[buf][l];
+                    if (hi <= lo) continue;
+                    const unsigned long long u0 = lo >> 1, u1 = (hi + 1) >> 1;
+                    for (unsigned long long u = u0; u < u1; u += (unsigned long long)SU) {
+                        const uint32_t n = (uint32_t)min((unsigned long long)SU, u1 - u);
+                        mbar_wait(&empty[stage], phase ^ 1u);
+                        mbar_expect_tx(&full[stage], n * 16u);
+                        bulk_g2s(ring + (size_t)stage * SU, a.postings + u, n * 16u, &full[stage]);
+                        if (++stage == NS) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    for (int k = 0;; ++k) {
+        const int buf = k & 1;
+        // own accumulator slots: written out by this thread at the end of the previous item, zeroed by it now
+        for (int i = tid; i < a.T / 4; i += BM25_CONSUMERS) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_wait(&bfull[buf], (uint32_t)((k >> 1) & 1));
+        const int item = s_item[buf];
+        if (item < 0) break;
+        const int nl = s_nl[buf];
+        const int q = item % B, tile = a.tile0 + item / B;
+        const long long doc0 = (long long)tile * a.T;
+        const uint32_t doc0u = (uint32_t)doc0;
+        const int tile_n = (int)min((long long)a.T, a.n_docs - doc0);
+        for (int l = 0; l < nl; ++l) {
+            const unsigned long long lo = s_lo[buf][l], hi = s_hi[buf][l];
+            if (hi <= lo) continue;
+            consumer_barrier();                 // accumulators zeroed / all adds of the previous term are done
+            const uint32_t n_post = (uint32_t)(hi - lo);
+            const int odd = (int)(lo & 1ull);
+            const uint32_t n_units = (uint32_t)(((hi + 1) >> 1) - (lo >> 1));
+            for (uint32_t c0 = 0; c0 < n_units; c0 += (uint32_t)SU) {
+                const uint32_t n = min((uint32_t)SU, n_units - c0);
+                mbar_wait(&full[stage], phase);
+                const uint4* src = ring + (size_t)stage * SU;
+                for (uint32_t u = (uint32_t)tid; u < n; u += BM25_CONSUMERS) {
+                    const uint4 p = src[u];
+                    const int r0 = (int)(2u * (c0 + u)) - odd;
+                    if ((uint32_t)r0 < n_post) {
+                        const uint32_t d = p.x - doc0u;
+                        acc[d] = __fadd_rn(acc[d], __uint_as_float(p.y));
+                    }
+                    if ((uint32_t)(r0 + 1) < n_post) {
+                        const uint32_t d = p.z - doc0u;
+                        acc[d] = __fadd_rn(acc[d], __uint_as_float(p.w));
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);
+                if (++stage == NS) { stage = 0; phase ^= 1u; }
+            }
+        }
+        consumer_barrier();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bempty[buf]);            // the producer may reuse this bounds buffer
+        float* dst = a.out + (long long)q * a.ld_out + doc0;
+        const int n4 = tile_n >> 2;
+        for (int i = tid; i < n4; i += BM25_CONSUMERS) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(acc)[i];
+        // a ragged tail (last tile only) is written by the owners of the covering float4 slots
+        for (int i = (n4 << 2) + tid; i < tile_n; i += BM25_CONSUMERS) dst[i] = acc[i];
+        if ((tile_n & 3) != 0) consumer_barrier();           // tail elements are read by other threads than their zero-fillers
+    }
+}
+
 // Where tile i starts in the list of every RARE term of the batch: rtab[(q*l_max + l)*(n_tiles+1) + i] = number of
 // postings of the term with doc < i*T (i = n_tiles: the list length).  One thread per (query, term slot, tile).
 __global__ void __launch_bounds__(256)
@@ -375,7 +540,7 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
 }
 
 int rr_launch_bm25_tile_scores(const rr_index_desc* d, const int32_t* d_terms, const int32_t* d_nterms, int B, int l_max,
-                               float* d_out, int64_t ld_out, uint32_t* d_rtab, cudaStream_t stream) {
+                               float* d_out, int64_t ld_out, uint32_t* d_rtab, unsigned* d_counter, cudaStream_t stream) {
     if (B <= 0 || d->n_tiles <= 0) return RR_OK;
     const int T = d->tile_docs;
     // ring geometry: NSTAGE chunks of STAGE_UNITS 16-byte units in flight per CTA (defaults: 4 x 4 KB)
@@ -405,6 +570,30 @@ int rr_launch_bm25_tile_scores(const rr_index_desc* d, const int32_t* d_terms, c
     a.term_slot = d->d_term_slot; a.rtab = d_rtab; a.rare_off = reinterpret_cast<const unsigned long long*>(d->d_rare_off); a.V = d->vocab_size; a.T = T; a.n_freq = d->n_freq; a.n_tiles = d->n_tiles;
     a.n_docs = d->n_docs; a.q_terms = d_terms; a.q_len = d_nterms; a.l_max = l_max; a.out = d_out; a.ld_out = ld_out;
     a.stage_units = SU; a.n_stages = NS;
+    if (l_max <= BM25_MAXL && d_counter != nullptr && !getenv("RR_BM25_ONE_SHOT")) {
+        static RrSmemOptIn optin_p;
+        if (optin_p.needed(smem, &dev)) {
+            RR_CUDA(cudaFuncSetAttribute(bm25_tile_scores_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RR_CUDA(cudaFuncSetAttribute(bm25_tile_scores_persistent_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            optin_p.done(smem, dev);
+        }
+        int per_sm = 0, sms = 148;
+        RR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bm25_tile_scores_persistent_kernel, BM25_THREADS, smem));
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        per_sm = std::max(per_sm, 1);
+        // items: (query, tile), query fastest, so that the CTAs sharing a tile (and the segments of common terms) run together
+        const long long tiles_per_launch = std::max<long long>(1, std::min<long long>(d->n_tiles, 0x7fffffffll / std::max(B, 1)));
+        for (long long t0 = 0; t0 < d->n_tiles; t0 += tiles_per_launch) {
+            const int nt = (int)std::min<long long>(tiles_per_launch, d->n_tiles - t0);
+            const int n_items = nt * B;
+            a.tile0 = (int)t0;
+            RrProfScope prof(RR_PROF_BM25_TILE, stream);      // d_counter = {next item, CTAs finished}: zero on entry, re-armed by the kernel
+            bm25_tile_scores_persistent_kernel<<<(unsigned)std::min<long long>(n_items, (long long)per_sm * sms), BM25_THREADS, smem, stream>>>(
+                a, n_items, B, d_counter);
+            RR_LAUNCH_CHECK();
+        }
+        return RR_OK;
+    }
     // grid: query fastest, so that the CTAs sharing a tile (and the segments of common terms) are co-resident
     for (int t0 = 0; t0 < d->n_tiles; t0 += 65535) {
         a.tile0 = t0;

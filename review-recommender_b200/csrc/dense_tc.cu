@@ -862,7 +862,8 @@ struct Buf {
 struct rr_tc_state {
     CUtensorMap tmap_c;
     const void* tmap_c_base = nullptr;
-    Buf q_bf16, qnorm, cand_keys, cand_cnt, kept_keys, kept_cnt, tau, overflow, rows, exact, flags, fb_q, fb_idx, fb_sims, fb_cnt;
+    Buf q_bf16, qnorm, cand_keys, cand_cnt, kept_keys, kept_cnt, tau, overflow, rows, exact, flags;
+    Buf fb_q[2], fb_idx[2], fb_sims[2], fb_cnt[2], fb_flag[2];     // per fallback depth
     int* h_nflag = nullptr;   // pinned: [0] read-back of the synchronous path, [1] of the last deferred call
     bool attr_set = false;
     // Shortlist feedback.  How many rows lie within the certification margin of the pool-th score depends on the data
@@ -882,7 +883,8 @@ bool rr_tc_supported(int cc_major, int) { return cc_major == 10; }
 void rr_tc_destroy(rr_tc_state* s) {
     if (!s) return;
     for (Buf* b : {&s->q_bf16, &s->qnorm, &s->cand_keys, &s->cand_cnt, &s->kept_keys, &s->kept_cnt, &s->tau, &s->overflow,
-                   &s->rows, &s->exact, &s->flags, &s->fb_q, &s->fb_idx, &s->fb_sims, &s->fb_cnt})
+                   &s->rows, &s->exact, &s->flags, &s->fb_q[0], &s->fb_idx[0], &s->fb_sims[0], &s->fb_cnt[0], &s->fb_flag[0],
+                   &s->fb_q[1], &s->fb_idx[1], &s->fb_sims[1], &s->fb_cnt[1], &s->fb_flag[1]})
         b->release();
     if (s->h_nflag) cudaFreeHost(s->h_nflag);
     if (s->deferred_done) cudaEventDestroy(s->deferred_done);
@@ -898,7 +900,7 @@ static int KP_growth(int kp) {
     const char* env = getenv("RR_TC_GROWTH");
     int g = env ? atoi(env) : 0;
     if (g < 2 || g > 16) g = std::min(8, std::max(2, TC_SORT_MAX / 2 / std::max(kp, 1) - 2));
-    while (g > 2 && (long long)kp * (g + 2) > TC_SORT_MAX) --g;
+    while (g > 2 && (long long)kp * (g + g / 2 + 2) > TC_SORT_MAX) --g;
     return g;
 }
 
@@ -922,7 +924,8 @@ bool rr_tc_can_handle(int dim_pad, int pool) {
 
 int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, const float* d_q, int32_t B,
                      int32_t pool, int64_t* d_idx, float* d_sims, int32_t* d_count, rr_dense_stats* stats,
-                     rr_exact_fn exact_fn, void* exact_ctx, int32_t* d_uncertified, cudaStream_t s) {
+                     rr_exact_fn exact_fn, void* exact_ctx, int32_t* d_uncertified, cudaStream_t s, int kp_override,
+                     int depth) {
     if (d->dim_pad > TC_MAX_KB_STREAMED * TC_BK)
         return rr_fail(RR_EUNSUPPORTED, "tensor path supports dim <= %d in this build", TC_MAX_KB_STREAMED * TC_BK);
     if (shortlist_size(pool) > TC_SORT_MAX / 4)
@@ -938,7 +941,8 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
         st->feedback(st->h_nflag[1], st->deferred_batch);          // outcome of the previous sync-free call
         st->deferred_pending = false;
     }
-    const int KP = std::min(TC_SORT_MAX / 4, (int)((std::ceil(shortlist_size(pool) * st->boost) + 31) / 32) * 32);
+    const int KP = kp_override > 0 ? kp_override
+                                   : std::min(TC_SORT_MAX / 4, (int)((std::ceil(shortlist_size(pool) * st->boost) + 31) / 32) * 32);
     const int growth = KP_growth(KP);
     if (!st->attr_set) {
         RR_CUDA(cudaFuncSetAttribute(tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
@@ -1047,7 +1051,9 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
             // kept list plus ~ (growth-1)*k' expected passes (2x head-room; more is flagged as overflow
             // and that query is redone exactly)
             // (kept k' + (growth-1) k' expected passes) with 50 % head-room
-            const int expect = dt_lo == 0 ? (dt_hi - dt_lo) * TC_BN + KP : KP * (growth + 2);
+            // (a prefix that under-represents the rest of the corpus -- duplicates, rows sorted by category -- lets more
+            // rows pass than (growth-1)*k': the head-room is 50 % of that plus k', r02 probe: 25 % was not enough)
+            const int expect = dt_lo == 0 ? (dt_hi - dt_lo) * TC_BN + KP : KP * (growth + growth / 2 + 2);
             const int sort_cap = std::min(TC_SORT_MAX, std::max(1024, (expect + 255) / 256 * 256));
             RrProfScope prof(RR_PROF_TC_SELECT, s);
             if (sort_cap <= 2048) {
@@ -1106,30 +1112,43 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
     RR_CUDA(cudaMemcpyAsync(st->h_nflag, n_flagged, sizeof(int), cudaMemcpyDeviceToHost, s));
     RR_CUDA(cudaStreamSynchronize(s));
     const int nf = *st->h_nflag;
-    st->feedback(nf, B);
-    if (stats) {
+    if (depth == 0) st->feedback(nf, B);
+    if (stats && depth == 0) {
         stats->path = 2; stats->n_uncertified = nf; stats->n_overflow = 0; stats->shortlist = KP;
         stats->n_segments = n_segments; stats->eps = eps_rel;
     }
     if (nf > 0) {
-        // redo the uncertified queries on the exact fp32 path
-        RR_TRY(st->fb_q.ensure(sizeof(float) * (size_t)nf * d->dim));
-        RR_TRY(st->fb_idx.ensure(sizeof(long long) * (size_t)nf * pool));
-        RR_TRY(st->fb_sims.ensure(sizeof(float) * (size_t)nf * pool));
-        RR_TRY(st->fb_cnt.ensure(sizeof(int32_t) * (size_t)nf));
-        tc_gather_queries_kernel<<<nf, 128, 0, s>>>(d_q, flagged, d->dim, static_cast<float*>(st->fb_q.p));
+        // Uncertified queries (rows denser than the margin around the pool-th score, candidate overflow): first a SECOND
+        // TENSOR PASS over the corpus for those queries only, with a 4x longer shortlist -- one bf16 sweep for up to 128
+        // queries costs less than the fp32 GEMV does for 8 -- and only what still cannot be proven goes to the exact
+        // fp32 path.  Results never depend on bf16 either way.
+        Buf &fq = st->fb_q[depth], &fi = st->fb_idx[depth], &fs = st->fb_sims[depth], &fc = st->fb_cnt[depth], &ff = st->fb_flag[depth];
+        RR_TRY(fq.ensure(sizeof(float) * (size_t)nf * d->dim));
+        RR_TRY(fi.ensure(sizeof(long long) * (size_t)nf * pool));
+        RR_TRY(fs.ensure(sizeof(float) * (size_t)nf * pool));
+        RR_TRY(fc.ensure(sizeof(int32_t) * (size_t)nf));
+        RR_TRY(ff.ensure(sizeof(int) * (size_t)nf));
+        RR_CUDA(cudaMemcpyAsync(ff.p, flagged, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToDevice, s));
+        const int* my_flags = static_cast<const int*>(ff.p);
+        tc_gather_queries_kernel<<<nf, 128, 0, s>>>(d_q, my_flags, d->dim, static_cast<float*>(fq.p));
         RR_LAUNCH_CHECK();
-        RR_TRY(exact_fn(exact_ctx, static_cast<const float*>(st->fb_q.p), nf, pool, static_cast<int64_t*>(st->fb_idx.p),
-                        static_cast<float*>(st->fb_sims.p), static_cast<int32_t*>(st->fb_cnt.p), s));
-        tc_scatter_results_kernel<<<nf, 128, 0, s>>>(flagged, pool, static_cast<const long long*>(st->fb_idx.p),
-                                                     static_cast<const float*>(st->fb_sims.p),
-                                                     static_cast<const int32_t*>(st->fb_cnt.p),
+        const int KP2 = std::min(TC_SORT_MAX / 4, KP * 4);
+        if (depth == 0 && KP2 > KP && !getenv("RR_TC_NO_SECOND_PASS")) {
+            RR_TRY(rr_tc_dense_topk(state, d, sm_count, static_cast<const float*>(fq.p), nf, pool, static_cast<int64_t*>(fi.p),
+                                    static_cast<float*>(fs.p), static_cast<int32_t*>(fc.p), nullptr, exact_fn, exact_ctx, nullptr,
+                                    s, KP2, 1));
+            if (stats) stats->n_overflow = *st->h_nflag;          // queries the second pass still had to hand to the exact path
+        } else {
+            RR_TRY(exact_fn(exact_ctx, static_cast<const float*>(fq.p), nf, pool, static_cast<int64_t*>(fi.p),
+                            static_cast<float*>(fs.p), static_cast<int32_t*>(fc.p), s));
+        }
+        tc_scatter_results_kernel<<<nf, 128, 0, s>>>(my_flags, pool, static_cast<const long long*>(fi.p),
+                                                     static_cast<const float*>(fs.p), static_cast<const int32_t*>(fc.p),
                                                      reinterpret_cast<long long*>(d_idx), d_sims, d_count);
         RR_LAUNCH_CHECK();
     }
     return RR_OK;
 }
-
 // Debug / test entry: the raw bf16 x bf16 -> fp32 tensor-core scores of rows [row0, row0 + n_rows) for up to 128
 // queries, exactly as tc_filter_kernel sees them (tau = -inf, every score is kept), so that the stated tolerance of
 // the shortlist stage ("within 1e-3 absolute before rescoring") can be asserted against the exact similarities.

@@ -16,7 +16,8 @@ bool rr_tc_supported(int cc_major, int cc_minor);
 bool rr_tc_can_handle(int dim_pad, int pool);
 int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, const float* d_q, int32_t B,
                      int32_t pool, int64_t* d_idx, float* d_sims, int32_t* d_count, rr_dense_stats* stats,
-                     rr_exact_fn exact, void* exact_ctx, int32_t* d_uncertified, cudaStream_t stream);
+                     rr_exact_fn exact, void* exact_ctx, int32_t* d_uncertified, cudaStream_t stream, int kp_override = 0,
+                     int depth = 0);
 // d_uncertified == NULL: synchronous -- the stream is synchronised once and uncertified queries are redone through
 // `exact` before returning.  d_uncertified != NULL (int32[B]): nothing is read back, the mask says which queries'
 // results are not proven exact.

@@ -9,7 +9,7 @@
 // bm25_kernels.cu
 size_t rr_bm25_rtab_bytes(int B, int l_max, int n_tiles);
 int rr_launch_bm25_tile_scores(const rr_index_desc* d, const int32_t* d_terms, const int32_t* d_nterms, int B, int l_max,
-                               float* d_out, int64_t ld_out, uint32_t* d_rtab, cudaStream_t stream);
+                               float* d_out, int64_t ld_out, uint32_t* d_rtab, unsigned* d_counter, cudaStream_t stream);
 // V = 0: no BM25 terms (scores are zero), the metadata gather still runs
 int rr_launch_bm25_candidates(const rr_index_desc* d, int V, const int32_t* d_terms, const int32_t* d_nterms,
                               int B, int l_max, const int64_t* d_cand, int pool, float* d_bm25, double* d_n_out,

@@ -147,7 +147,7 @@ class PendingShardedSearch:
                 r2, f2, _ = self.s._round(lane, q[idx].contiguous(),
                                           None if term_ids is None else term_ids[idx].contiguous(),
                                           None if n_terms is None else n_terms[idx].contiguous(), fusion, mode,
-                                          fusion.pool, deferred=False)
+                                          fusion.pool, deferred=False, which=idx)
                 self.rows = self.rows.clone()
                 self.final = self.final.clone()
                 self.rows[idx[:nf]] = r2[:nf]
@@ -175,9 +175,10 @@ class ShardedSearcher:
     (each with its own scratch handle over the same index tensors) WITHOUT any host wait; `token.result()` waits for
     that batch only.  With two lanes the tail of batch i (latency-bound selection / exchange / host wait) runs under
     the GEMM of batch i+1; a serving loop is `t1 = begin(b1); t2 = begin(b2); r1 = t1.result(); t3 = begin(b3); ...`.
-    Optional per-candidate columns of run_search (app/app_product_search.py:285-310): `extras(cand_local_rows,
-    q) -> (gate f32[B, m] | None, best_raw f32[B, m] | None)` is evaluated on every shard for its own candidates and
-    rides in the tuples (gate factor and raw best-review similarity are per-candidate quantities)."""
+    Optional per-candidate columns of run_search (app/app_product_search.py:285-310): `extras(cand_local_rows, q,
+    which) -> (gate f32[b, m] | None, best_raw f32[b, m] | None)` is evaluated on every shard for its own candidates
+    and rides in the tuples (gate factor and raw best-review similarity are per-candidate quantities); `which` is None
+    for the whole batch or the batch positions (LongTensor[b]) of the queries a second round repeats."""
 
     def __init__(self, index, group=None, round1_pool: Optional[int] = None, lanes: int = 1, extras=None):
         self.ix = index
@@ -223,7 +224,7 @@ class ShardedSearcher:
         all_flags = out[:, o_flags:o_flags + Bg * 4].view(torch.int32).reshape(B)
         return all_rows, all_final, all_flags
 
-    def _round(self, lane, q, term_ids, n_terms, fusion, mode, m, deferred: bool):
+    def _round(self, lane, q, term_ids, n_terms, fusion, mode, m, deferred: bool, which=None):
         """deferred=True: no host synchronisation anywhere (queries the tensor path cannot certify come back
         flagged); deferred=False: rr_dense_topk redoes uncertified queries exactly before the exchange."""
         ix, G = lane.ix, self.world
@@ -242,7 +243,7 @@ class ShardedSearcher:
                 grow = torch.where(unc[:, None] != 0, torch.full_like(grow, -2), grow)
             gate = best = None
             if with_extras:
-                gate, best = self.extras(cand, q)
+                gate, best = self.extras(cand, q, which)
                 gate = torch.ones_like(dense) if gate is None else gate.to(torch.float32)
                 best = torch.zeros_like(dense) if best is None else best.to(torch.float32)
             send = pack_tuples(G, grow, n, avg, dense, bm25, gate, best)
@@ -290,10 +291,11 @@ def make_extras(gate_ix=None, review_ix=None, groups_per_query=None, gate_penalt
             normalised after the cross-shard merge by K4 (Fusion.best_is_raw = True)
     The reference's `max_rows` cap on scanned reviews (:343-346) is defined over the reviews of the WHOLE pool and is
     not applied here: use it only where the cap does not bind (its default, 300 000 rows, rarely does)."""
-    def extras(cand: torch.Tensor, q: torch.Tensor):
+    def extras(cand: torch.Tensor, q: torch.Tensor, which=None):
         gate = best = None
         if gate_ix is not None and groups_per_query is not None:
-            gate = gate_ix.factors(groups_per_query, cand, gate_penalty)
+            groups = groups_per_query if which is None else [groups_per_query[int(i)] for i in which.tolist()]
+            gate = gate_ix.factors(groups, cand, gate_penalty)
         if review_ix is not None:
             best, _ = review_ix.best(q, cand, max_rows=None, as_numpy=False)
         return gate, best

@@ -214,7 +214,7 @@ def run_reference(args, cfg):
 # ------------------------------------------------------------------------------------------------
 # device-side synthetic corpus (same distributions as synth.py, generated in HBM)
 # ------------------------------------------------------------------------------------------------
-CLUSTERS, CLUSTER_COS = 2000, 0.6
+CLUSTERS, CLUSTER_COS = int(os.environ.get("RR_BENCH_CLUSTERS", "2000")), 0.6
 
 
 def cluster_centres(D: int, dev):

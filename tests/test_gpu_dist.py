@@ -88,38 +88,64 @@ WORKER = textwrap.dedent('''
         assert torch.equal(r_, want_r) and torch.equal(f_, want_f), ("lanes", i)
     print(f"rank {rank} two lanes ok", flush=True)
 
-    # ---- gate and best-review columns ride in the tuples (run_search :285-310) ----------------------------------
+    # ---- gate and best-review columns ride in the tuples (run_search :285-310): a sharded run_search with snippets
+    # and gates on must return what the single-GPU SearchEngine.run_search returns ---------------------------------
+    import pandas as pd
     from tests.golden_worlds import make_gate_texts, GATE_QUERIES
-    texts = make_gate_texts(N, full.doc_offsets, full.token_ids)
-    skus = syn.skus(N)
+    N2, D2, V2 = 20_000, 64, 1500
+    w2 = syn.make_corpus(N2, D2, V2)
+    texts = make_gate_texts(N2, w2.doc_offsets, w2.token_ids)
+    skus2 = syn.skus(N2)
     rngr = np.random.default_rng(21)
-    M = 3 * N // 10
-    rev_prod = rngr.integers(0, N, size=M)
-    rev_emb = rngr.standard_normal((M, D)).astype(np.float32)
-    rev_skus = [skus[i] for i in rev_prod]
-    Bx = 16 * max(world, 1)
-    qx = q[:Bx]
-    qtx, ntx = qt[:Bx], nt[:Bx]
-    groups = [rr.drop_in.build_gate_groups(GATE_QUERIES[i % len(GATE_QUERIES)]) for i in range(Bx)]
-    fx = rr.engine.Fusion(k=20, rerank_k=0, w_dense=0.45, w_bm25=0.15, w_rerank=0.0, w_prior=0.10, w_best=0.30, best_is_raw=True)
-    g_loc = rr.engine.GateIndex(texts[row0:row1], rr.drop_in.GATE_FIXED_GROUPS, device=dev)
-    r_loc = rr.engine.ReviewIndex(rev_emb, rev_skus, skus[row0:row1], device=dev)
-    sx = rr.dist.ShardedSearcher(ix, extras=rr.dist.make_extras(g_loc, r_loc, groups, 0.5))
-    rows_x, final_x = sx.search(torch.from_numpy(qx).to(dev), torch.from_numpy(qtx).to(dev), torch.from_numpy(ntx).to(dev),
-                                fx, mode=rr._lib.RR_DENSE_EXACT)
-    if rank == 0:
-        whole = rr.engine.HybridIndex(full.emb, full.doc_offsets, full.token_ids, V, full.n_reviews, full.avg_stars, device=dev)
-        g_all = rr.engine.GateIndex(texts, rr.drop_in.GATE_FIXED_GROUPS, device=dev)
-        r_all = rr.engine.ReviewIndex(rev_emb, rev_skus, skus, device=dev)
-        cand, dense, cnt = whole.dense_topk(qx, fx.pool, rr._lib.RR_DENSE_EXACT)
-        bm25, n_, avg_, grow_ = whole.candidate_tuples(qtx, ntx, cand)
-        gate = g_all.factors(groups, cand, 0.5)
-        best, _ = r_all.best(qx, cand, max_rows=None, as_numpy=False)
-        w_rows, w_final, _, _ = whole.fuse(fx, dense, bm25, n_, avg_, grow_, count=cnt, best=best, gate=gate)
-        assert torch.equal(rows_x, w_rows), int((rows_x != w_rows).sum())
-        assert torch.equal(final_x, w_final)
-        assert float(gate.min()) < 1.0 and float(best.max()) > 0.0, "the extras must actually matter in this case"
-        whole.close()
+    M = 3 * N2
+    rev_prod = rngr.integers(0, N2, size=M)
+    rev_emb = rngr.standard_normal((M, D2)).astype(np.float32)
+    rev_skus = [skus2[i] for i in rev_prod]
+    Bx = 8 * world
+    qx = syn.queries(Bx, D2)
+    qt2 = syn.query_terms(Bx, 3, w2.doc_offsets, w2.token_ids, V2)
+    query_strs = [" ".join(f"t{int(t) + 1}" for t in qt2[i]) + " " + GATE_QUERIES[i % len(GATE_QUERIES)] for i in range(Bx)]
+    toks = [rr.drop_in.tokenize_query(s) for s in query_strs]
+    ids = [[(int(t[1:]) - 1 if t[0] == "t" and t[1:].isdigit() and int(t[1:]) <= V2 else -1) for t in tk] for tk in toks]
+    tid, ntm = rr.engine.HybridIndex.pack_terms(ids)
+    groups = [rr.drop_in.build_gate_groups(s) for s in query_strs]
+    kw = dict(k=20, rerank_k=0, w_dense=0.45, w_bm25=0.15, w_rerank=0.0, w_prior=0.10, w_best=0.30, prior_C=20.0, min_reviews=8)
+    fx = rr.engine.Fusion(driver="streamlit", best_is_raw=True, **kw)
+    a0, a1 = N2 * rank // world, N2 * (rank + 1) // world
+    o2 = w2.doc_offsets[a0:a1 + 1] - w2.doc_offsets[a0]
+    t2 = w2.token_ids[w2.doc_offsets[a0]:w2.doc_offsets[a1]]
+    st2 = rr.engine.BM25Stats.local(o2, t2, V2, token_pos0=int(w2.doc_offsets[a0]))
+    rr.dist.all_reduce_stats(st2, device=dev)
+    st2.finalize()
+    ixx = rr.engine.HybridIndex(w2.emb[a0:a1], o2, t2, V2, w2.n_reviews[a0:a1], w2.avg_stars[a0:a1], device=dev,
+                                row_offset=a0, stats=st2)
+    g_loc = rr.engine.GateIndex(texts[a0:a1], rr.drop_in.GATE_FIXED_GROUPS, device=dev)
+    r_loc = rr.engine.ReviewIndex(rev_emb, rev_skus, skus2[a0:a1], device=dev)
+    for r1x in (None, 8):                      # 8: too few tuples in round 1 -> the second round must carry the extras too
+        sx = rr.dist.ShardedSearcher(ixx, round1_pool=r1x, extras=rr.dist.make_extras(g_loc, r_loc, groups, 0.5))
+        rows_x, final_x = sx.search(torch.from_numpy(qx).to(dev), torch.from_numpy(tid).to(dev), torch.from_numpy(ntm).to(dev),
+                                    fx, mode=rr._lib.RR_DENSE_EXACT)
+        if r1x == 8:
+            assert sx.last_repeated > 0
+        if rank == 0:
+            meta = pd.DataFrame({"sku": skus2, "n_reviews": w2.n_reviews.astype(np.float64), "avg_stars": w2.avg_stars,
+                                 "agg_text": texts})
+            reviews = pd.DataFrame({"sku": rev_skus, "text": [f"review {j}" for j in range(M)],
+                                    "stars": (rev_prod % 5 + 1).astype(np.float64), "embedding": list(rev_emb)})
+            table = dict(zip(query_strs, qx))
+            se = rr.drop_in.SearchEngine(meta, w2.emb, syn.corpus_as_lists(w2.doc_offsets, w2.token_ids), skus2,
+                                         encode=lambda s_: table[s_], reviews=reviews, device=str(dev))
+            res = se.run_search_batch(query_strs, use_snips=True, max_scan=10**9, gate_penalty=0.5, **kw)
+            rows_h, final_h = rows_x.cpu().numpy(), final_x.cpu().numpy()
+            n_gated = n_best = 0
+            for i, (top, snips, dbg) in enumerate(res):
+                assert top["sku"].tolist() == [skus2[r] for r in rows_h[i]], ("extras", r1x, i)
+                assert np.array_equal(top["_final"].values.astype(np.float32), final_h[i]), ("extras final", r1x, i)
+                n_gated += int((top["_gate"].values < 1.0).sum())
+                n_best += int((top["_best"].values > 0.0).sum())
+            assert n_gated > 0 and n_best > 0, "the extras must actually matter in this case"
+            se.ix.close()
+    ixx.close()
     print(f"rank {rank} extras ok", flush=True)
 
     # ---- row shards x query groups: same answers for every layout ------------------------------------------

@@ -892,14 +892,14 @@ void rr_tc_destroy(rr_tc_state* s) {
 }
 
 // Corpus prefix growth per segment.  A segment brings ~ (growth-1)*k' new candidates per query, so fewer, longer
-// segments trade selection launches (latency-bound: ~60 us each for 4096 queries) against the size of each selection.
-// Default: as large as keeps (growth+2)*k' keys -- the expected candidates plus head-room -- inside half of one
-// selection's capacity, between 2 and 8 (r01 used a fixed 4: 8 segments at 10 M rows, 7 on a 1.25 M-row shard;
-// now 5 and 4).  RR_TC_GROWTH overrides (2..16).
+// segments trade selection launches against the size of each selection.  Measured in r02 (10 M x 384, B = 4096):
+// growth 8 (5 segments instead of 8 on one GPU, 5 instead of 7 on a 1.25 M-row shard) is no faster on one GPU and
+// 3 % SLOWER on eight (3.67 vs 3.57 ms / step): the selections get bigger as fast as they get fewer.  Growth 16
+// overflows the selection capacity.  Default 4, RR_TC_GROWTH overrides (2..16).
 static int KP_growth(int kp) {
     const char* env = getenv("RR_TC_GROWTH");
     int g = env ? atoi(env) : 0;
-    if (g < 2 || g > 16) g = std::min(8, std::max(2, TC_SORT_MAX / 2 / std::max(kp, 1) - 2));
+    if (g < 2 || g > 16) g = TC_GROWTH;
     while (g > 2 && (long long)kp * (g + g / 2 + 2) > TC_SORT_MAX) --g;
     return g;
 }

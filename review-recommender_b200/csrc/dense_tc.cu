@@ -367,6 +367,228 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
+// the same GEMM + filter on CTA PAIRS (tcgen05.mma.cta_group::2)
+// ---------------------------------------------------------------------------------------------
+// One-CTA tiles are co-limited by the SM's ingress from L2: a 256-doc x 384-d corpus tile is 196 KB per 3072 tensor
+// clocks = the 64 B/clk an SM can take in, which is why the one-CTA kernel tops out at ~80-89 % tensor activity and
+// loses efficiency as the clock rises (r02: 60 % of the tensor peak at 1965 MHz on a 1.25 M-row shard).  A CTA pair
+// (two SMs of one TPC, cluster of 2) computes a 256-query x 256-doc tile per instruction: each CTA keeps ITS 128
+// queries resident and streams only HALF of every corpus tile (128 docs); the pair's MMA reads both halves.  Per-SM
+// ingress halves, the accumulator layout per CTA (128 lanes x 256 columns) and hence the whole epilogue are unchanged.
+//   - both CTAs issue TMA for their half (cp.async.bulk.tensor .cta_group::2, completion counted on the LEADER's
+//     mbarrier), the leader's single MMA thread issues tcgen05.mma.cta_group::2 and commits with a multicast arrive
+//     to both CTAs' "stage empty" / "accumulator full" barriers; both CTAs' epilogue threads arrive on the leader's
+//     "accumulator empty" barrier.
+constexpr int TC2_STAGES = 6;
+constexpr int TC2_B_KB_BYTES = (TC_BN / 2) * TC_BK * 2;      // 16 KB: this CTA's half of a corpus k-block
+constexpr int TC2_SMEM_TOTAL = TC_SMEM_Q + TC2_STAGES * TC2_B_KB_BYTES + TC_SMEM_BAR + 1024;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t cta_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t leader_bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_512_pair(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512_pair(uint32_t addr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(addr) : "memory");
+}
+// commit of the pair's MMAs: arrive on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// D[tmem] (+)= A * B^T over the pair: M = 256 (128 rows per CTA), N = 256 (128 docs per CTA), K = 16
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+constexpr uint32_t kInstrDescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                                    ((uint32_t)((2 * TC_BM) >> 4) << 24);
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c_half,
+                      const TcFilterArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;                                  // [6 x 16 KB] this CTA's 128 queries, resident
+    uint8_t* sB = smem + TC_SMEM_Q;                      // [TC2_STAGES x 16 KB] this CTA's half of the corpus k-blocks
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_SMEM_Q + TC2_STAGES * TC2_B_KB_BYTES);
+    uint64_t* full = bars;                    // [TC2_STAGES]  used in the LEADER: both CTAs' TMA -> MMA
+    uint64_t* empty = bars + 8;               // [TC2_STAGES]  per CTA: MMA (multicast commit) -> this CTA's TMA
+    uint64_t* tfull = bars + 16;              // [2]           per CTA: MMA (multicast commit) -> this CTA's epilogue
+    uint64_t* tempty = tfull + 2;             // [2]           used in the LEADER: both CTAs' epilogues -> MMA
+    uint64_t* qfull = tempty + 2;             // [1]           used in the LEADER
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cta = blockIdx.x;                          // pairs: (2p, 2p+1) share j0 and own adjacent query tiles
+    const int qt = a.qt0 + cta % a.n_qt;
+    const int j0 = cta / a.n_qt;
+    const int span = a.dt_hi - a.dt_lo;
+    const int n_tiles = j0 < span ? (span - j0 + a.reps - 1) / a.reps : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_c_half);
+        for (int i = 0; i < TC2_STAGES; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * TC_EPI_THREADS); }
+        mbar_init(qfull, 2);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_512_pair(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();                                   // barriers of BOTH CTAs are initialised before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (one thread per CTA): its queries once, then its half of every corpus k-block =====
+        if (lane == 0 && n_tiles > 0) {
+            const uint32_t qfull_leader = mapa_cluster(smem_u32(qfull), 0);
+            if (leader) mbar_expect_tx(qfull, (uint32_t)(2 * a.n_kb * TC_Q_KB_BYTES));
+            else mbar_arrive_remote(qfull_leader);
+            for (int kb = 0; kb < a.n_kb; ++kb) tma_load_2d_pair(&tmap_q, qfull_leader, sQ + kb * TC_Q_KB_BYTES, kb * TC_BK, qt * TC_BM);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int dt = a.dt_lo + j0 + t * a.reps;
+                for (int kb = 0; kb < a.n_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    const uint32_t full_leader = mapa_cluster(smem_u32(&full[stage]), 0);
+                    if (leader) mbar_expect_tx(&full[stage], (uint32_t)(2 * TC2_B_KB_BYTES));
+                    else mbar_arrive_remote(full_leader);
+                    tma_load_2d_pair(&tmap_c_half, full_leader, sB + stage * TC2_B_KB_BYTES, kb * TC_BK,
+                                     dt * TC_BN + (int)rank * (TC_BN / 2));
+                    if (++stage == TC2_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the LEADER CTA issues for the pair =====
+        if (leader && lane == 0 && n_tiles > 0) {
+            mbar_wait(qfull, 0u);
+            tc_fence_after();
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int as = t & 1;
+                const uint32_t aphase = (uint32_t)((t >> 1) & 1);
+                mbar_wait(&tempty[as], aphase ^ 1u);       // both epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_BN);
+                for (int kb = 0; kb < a.n_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(sQ + kb * TC_Q_KB_BYTES);
+                    const uint64_t db = umma_desc_sw128(sB + stage * TC2_B_KB_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k)
+                        umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kInstrDescPair, (uint32_t)((kb | k) != 0));
+                    umma_commit_pair(&empty[stage]);
+                    if (++stage == TC2_STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit_pair(&tfull[as]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): identical to tc_filter_kernel, the drain signal goes to the leader =====
+        const int ew = (warp - 4) & 3;
+        const int half = (warp - 4) >> 2;
+        const int q = qt * TC_BM + ew * 32 + lane;
+        const bool active = q < a.B;
+        const float tau = active ? a.tau[q] : INFINITY;
+        const int sub = j0 * 2 + half;
+        unsigned long long* my_keys = a.cand_keys + ((size_t)(active ? q : 0) * a.n_sub + sub) * a.cap_sub;
+        unsigned cnt = 0;
+        const unsigned cap = (unsigned)a.cap_sub;
+        const uint32_t tempty_leader0 = mapa_cluster(smem_u32(&tempty[0]), 0);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int as = t & 1;
+            const uint32_t aphase = (uint32_t)((t >> 1) & 1);
+            const int dt = a.dt_lo + j0 + t * a.reps;
+            const long long doc_base = (long long)dt * TC_BN;
+            const uint32_t doc_base_u = (uint32_t)doc_base;
+            const int n_valid = (int)min((long long)TC_BN, a.n_docs - doc_base);
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * TC_BN + half * (TC_BN / 2));
+#pragma unroll 1
+            for (int chunk = 0; chunk < TC_BN / 64; chunk += 2) {
+                uint32_t v[2][32];
+                tmem_ld_x32(taddr0 + (uint32_t)(chunk * 32), v[0]);
+                tmem_ld_x32(taddr0 + (uint32_t)(chunk * 32 + 32), v[1]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float m8[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float m = __uint_as_float(v[h][8 * g]);
+#pragma unroll
+                        for (int e = 1; e < 8; ++e) m = fmaxf(m, __uint_as_float(v[h][8 * g + e]));
+                        m8[g] = m;
+                    }
+                    const float m32 = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+                    if (active && m32 >= tau) {
+                        const int c0 = half * (TC_BN / 2) + (chunk + h) * 32;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (m8[g] >= tau) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const uint32_t sb = v[h][8 * g + e];
+                                    const int col = c0 + 8 * g + e;
+                                    const bool pass = __uint_as_float(sb) >= tau && col < n_valid;
+                                    st_pred_v2(my_keys + cnt, sb, doc_base_u + (uint32_t)col, pass && cnt < cap);
+                                    cnt += pass ? 1u : 0u;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_remote(tempty_leader0 + (uint32_t)(as * 8));
+        }
+        if (active) a.cand_cnt[(size_t)q * a.n_sub + sub] = cnt;
+    }
+    tc_fence_before();
+    cluster_sync_all();                                   // both CTAs are done with TMEM and with each other's barriers
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_512_pair(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // per-query selection
 // ---------------------------------------------------------------------------------------------
 __device__ void bitonic_keys_desc(unsigned long long* key, int n_pad) {
@@ -860,8 +1082,9 @@ struct Buf {
 }  // namespace
 
 struct rr_tc_state {
-    CUtensorMap tmap_c;
+    CUtensorMap tmap_c, tmap_c_half;      // corpus rows in boxes of 256 (one-CTA tiles) / 128 (this CTA's half of a pair's tile)
     const void* tmap_c_base = nullptr;
+    bool pair_attr_set = false;
     Buf q_bf16, qnorm, cand_keys, cand_cnt, kept_keys, kept_cnt, tau, overflow, rows, exact, flags;
     Buf fb_q[2], fb_idx[2], fb_sims[2], fb_cnt[2], fb_flag[2];     // per fallback depth
     int* h_nflag = nullptr;   // pinned: [0] read-back of the synchronous path, [1] of the last deferred call
@@ -956,31 +1179,46 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
     }
     if (st->tmap_c_base != d->d_emb_bf16) {
         RR_TRY(make_tmap_bf16_rows(&st->tmap_c, d->d_emb_bf16, (uint64_t)d->n_docs, (uint64_t)d->dim_pad, TC_BN));
+        RR_TRY(make_tmap_bf16_rows(&st->tmap_c_half, d->d_emb_bf16, (uint64_t)d->n_docs, (uint64_t)d->dim_pad, TC_BN / 2));
         st->tmap_c_base = d->d_emb_bf16;
     }
-    const int n_qt = (B + TC_BM - 1) / TC_BM;
+    // CTA pairs (tcgen05 cta_group::2): resident query tiles only (dim_pad <= 384), and enough query tiles that padding
+    // their number to an even one does not waste much (an odd tile out of >= 8 costs < 13 %)
+    const int n_qt_real = (B + TC_BM - 1) / TC_BM;
+    const char* pair_env = getenv("RR_TC_PAIR");
+    const bool use_pair = !(pair_env && pair_env[0] == '0') && d->dim_pad <= TC_MAX_KB * TC_BK &&
+                          (n_qt_real >= 8 || (n_qt_real >= 2 && n_qt_real % 2 == 0));
+    const int n_qt = use_pair ? (n_qt_real + 1) / 2 * 2 : n_qt_real;
     const int B_pad = n_qt * TC_BM;
+    if (use_pair && !st->pair_attr_set) {
+        RR_CUDA(cudaFuncSetAttribute(tc_filter_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_TOTAL));
+        st->pair_attr_set = true;
+    }
+    const int sm_units = use_pair ? sm_count / 2 * 2 : sm_count;      // pairs occupy whole TPCs
 
     // Split the query tiles into parts so that (tiles per part) x (CTAs per tile) fills the SMs; an extra
     // part re-reads the corpus from HBM, so it has to buy at least 5 % more SM occupancy.
     int best_parts = 0;
     double best_cost = 1e30;
-    for (int parts = 1; parts <= 8 && parts <= n_qt; ++parts) {
+    const int unit = use_pair ? 2 : 1;                 // query tiles are dealt to the parts in units of `unit`
+    const int n_units = n_qt / unit;
+    auto part_tiles = [&](int parts, int p) { return unit * (n_units / parts + (p < n_units % parts ? 1 : 0)); };
+    for (int parts = 1; parts <= 8 && parts <= n_units; ++parts) {
         double cost = 0;
         bool ok = true;
         for (int p = 0; p < parts; ++p) {
-            const int nq = n_qt / parts + (p < n_qt % parts ? 1 : 0);
-            if (nq > sm_count) { ok = false; break; }
-            cost += 1.0 / (double)(sm_count / nq);
+            const int nq = part_tiles(parts, p);
+            if (nq > sm_units) { ok = false; break; }
+            cost += 1.0 / (double)(sm_units / nq);
         }
         if (ok && cost < best_cost * 0.95) { best_cost = cost; best_parts = parts; }
     }
     if (best_parts == 0) return rr_fail(RR_EUNSUPPORTED, "batch too large for the tensor path (%d query tiles)", n_qt);
-    int reps_max = 1, reps_min = sm_count;
+    int reps_max = 1, reps_min = sm_units;
     for (int p = 0; p < best_parts; ++p) {
-        const int nq = n_qt / best_parts + (p < n_qt % best_parts ? 1 : 0);
-        reps_max = std::max(reps_max, sm_count / nq);
-        reps_min = std::min(reps_min, sm_count / nq);
+        const int nq = part_tiles(best_parts, p);
+        reps_max = std::max(reps_max, sm_units / nq);
+        reps_min = std::min(reps_min, sm_units / nq);
     }
     const int n_sub = 2 * reps_max;                                              // one sub-list per (CTA, column half)
     if (n_sub > TC_MAX_SUB) return rr_fail(RR_EUNSUPPORTED, "too many SMs for the candidate sub-list table");
@@ -1029,10 +1267,10 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
                                      : (int)std::min<long long>(n_dt, (long long)dt_lo * growth);
         int qt0 = 0;
         for (int p = 0; p < best_parts; ++p) {
-            const int nq = n_qt / best_parts + (p < n_qt % best_parts ? 1 : 0);
+            const int nq = part_tiles(best_parts, p);
             TcFilterArgs a;
             a.n_docs = d->n_docs; a.n_kb = d->dim_pad / TC_BK; a.B = B; a.qt0 = qt0; a.n_qt = nq;
-            a.reps = std::max(1, std::min(sm_count / nq, dt_hi - dt_lo));
+            a.reps = std::max(1, std::min(sm_units / nq, dt_hi - dt_lo));
             a.dt_lo = dt_lo; a.dt_hi = dt_hi; a.tau = static_cast<const float*>(st->tau.p);
             a.q_resident = d->dim_pad <= TC_MAX_KB * TC_BK ? 1 : 0;
             a.n_sub = n_sub; a.cap_sub = cap_sub;
@@ -1040,7 +1278,10 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
             a.cand_cnt = static_cast<unsigned*>(st->cand_cnt.p);
             {
                 RrProfScope prof(RR_PROF_TC_FILTER, s);
-                tc_filter_kernel<<<nq * a.reps, TC_THREADS, TC_SMEM_TOTAL, s>>>(tmap_q, st->tmap_c, a);
+                if (use_pair)
+                    tc_filter_pair_kernel<<<nq * a.reps, TC_THREADS, TC2_SMEM_TOTAL, s>>>(tmap_q, st->tmap_c_half, a);
+                else
+                    tc_filter_kernel<<<nq * a.reps, TC_THREADS, TC_SMEM_TOTAL, s>>>(tmap_q, st->tmap_c, a);
             }
             RR_LAUNCH_CHECK();
             qt0 += nq;

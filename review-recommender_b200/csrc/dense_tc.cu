@@ -192,6 +192,7 @@ struct TcFilterArgs {
     int dt_lo, dt_hi;  // doc tiles of this segment
     int q_resident;    // 1: query tile loaded once (dim_pad <= 384); 0: its k-blocks are streamed with the corpus'
     const float* tau;  // [B]
+    int pair_stages;   // tc_filter_pair_kernel: depth of the corpus ring
     int n_sub, cap_sub;              // sub-lists per query (2 per scanning CTA) and slots per sub-list
     unsigned long long* cand_keys;   // [B, n_sub, cap_sub]
     unsigned* cand_cnt;              // [B, n_sub]
@@ -379,9 +380,9 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 //     mbarrier), the leader's single MMA thread issues tcgen05.mma.cta_group::2 and commits with a multicast arrive
 //     to both CTAs' "stage empty" / "accumulator full" barriers; both CTAs' epilogue threads arrive on the leader's
 //     "accumulator empty" barrier.
-constexpr int TC2_STAGES = 6;
+constexpr int TC2_MAX_STAGES = 8;
 constexpr int TC2_B_KB_BYTES = (TC_BN / 2) * TC_BK * 2;      // 16 KB: this CTA's half of a corpus k-block
-constexpr int TC2_SMEM_TOTAL = TC_SMEM_Q + TC2_STAGES * TC2_B_KB_BYTES + TC_SMEM_BAR + 1024;
+constexpr int tc2_smem_total(int stages) { return TC_SMEM_Q + 1024 + stages * TC2_B_KB_BYTES + 1024; }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -398,7 +399,11 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t cta_addr, uint32_t ran
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics (.release at CTA scope), like a local arrive: r02 ncu showed `.release.cluster` fencing every
+    // epilogue thread's candidate stores to global memory per tile (ERRBAR + arrive = the hottest epilogue lines), which made
+    // the epilogue slower than the MMA.  What the MMA thread needs ordered is the TMEM read, which tcgen05.wait::ld +
+    // tcgen05.fence::before_thread_sync have already completed.
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t leader_bar, void* dst, int c0, int c1) {
     asm volatile(
@@ -437,8 +442,9 @@ tc_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = smem;                                  // [6 x 16 KB] this CTA's 128 queries, resident
-    uint8_t* sB = smem + TC_SMEM_Q;                      // [TC2_STAGES x 16 KB] this CTA's half of the corpus k-blocks
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_SMEM_Q + TC2_STAGES * TC2_B_KB_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_SMEM_Q);      // 1 KB of barriers
+    uint8_t* sB = smem + TC_SMEM_Q + 1024;               // [stages x 16 KB] this CTA's half of the corpus k-blocks
+    const int TC2_STAGES = a.pair_stages;
     uint64_t* full = bars;                    // [TC2_STAGES]  used in the LEADER: both CTAs' TMA -> MMA
     uint64_t* empty = bars + 8;               // [TC2_STAGES]  per CTA: MMA (multicast commit) -> this CTA's TMA
     uint64_t* tfull = bars + 16;              // [2]           per CTA: MMA (multicast commit) -> this CTA's epilogue
@@ -459,7 +465,9 @@ tc_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_c_half);
         for (int i = 0; i < TC2_STAGES; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * TC_EPI_THREADS); }
+        // accumulator-empty: one arrive per epilogue WARP of both CTAs (r02: one remote arrive per thread -- 512 per tile on one
+        // barrier word across the cluster -- made the pair kernel 1.6x slower than the one-CTA kernel)
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * (TC_EPI_THREADS / 32)); }
         mbar_init(qfull, 2);
         fence_barrier_init();
     }
@@ -576,7 +584,8 @@ tc_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 }
             }
             tc_fence_before();
-            mbar_arrive_remote(tempty_leader0 + (uint32_t)(as * 8));
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(tempty_leader0 + (uint32_t)(as * 8));
         }
         if (active) a.cand_cnt[(size_t)q * a.n_sub + sub] = cnt;
     }
@@ -1191,9 +1200,11 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
     const int n_qt = use_pair ? (n_qt_real + 1) / 2 * 2 : n_qt_real;
     const int B_pad = n_qt * TC_BM;
     if (use_pair && !st->pair_attr_set) {
-        RR_CUDA(cudaFuncSetAttribute(tc_filter_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_TOTAL));
+        RR_CUDA(cudaFuncSetAttribute(tc_filter_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_total(TC2_MAX_STAGES)));
         st->pair_attr_set = true;
     }
+    const char* ps_env = getenv("RR_TC_PAIR_STAGES");
+    const int pair_stages = std::max(2, std::min(TC2_MAX_STAGES, ps_env ? atoi(ps_env) : 8));
     const int sm_units = use_pair ? sm_count / 2 * 2 : sm_count;      // pairs occupy whole TPCs
 
     // Split the query tiles into parts so that (tiles per part) x (CTAs per tile) fills the SMs; an extra
@@ -1273,13 +1284,13 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
             a.reps = std::max(1, std::min(sm_units / nq, dt_hi - dt_lo));
             a.dt_lo = dt_lo; a.dt_hi = dt_hi; a.tau = static_cast<const float*>(st->tau.p);
             a.q_resident = d->dim_pad <= TC_MAX_KB * TC_BK ? 1 : 0;
-            a.n_sub = n_sub; a.cap_sub = cap_sub;
+            a.n_sub = n_sub; a.cap_sub = cap_sub; a.pair_stages = pair_stages;
             a.cand_keys = static_cast<unsigned long long*>(st->cand_keys.p);
             a.cand_cnt = static_cast<unsigned*>(st->cand_cnt.p);
             {
                 RrProfScope prof(RR_PROF_TC_FILTER, s);
                 if (use_pair)
-                    tc_filter_pair_kernel<<<nq * a.reps, TC_THREADS, TC2_SMEM_TOTAL, s>>>(tmap_q, st->tmap_c_half, a);
+                    tc_filter_pair_kernel<<<nq * a.reps, TC_THREADS, tc2_smem_total(pair_stages), s>>>(tmap_q, st->tmap_c_half, a);
                 else
                     tc_filter_kernel<<<nq * a.reps, TC_THREADS, TC_SMEM_TOTAL, s>>>(tmap_q, st->tmap_c, a);
             }

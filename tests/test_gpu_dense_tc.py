@@ -92,3 +92,25 @@ def test_bf16_scores_within_1e3_of_exact_before_rescoring():
     _, _, _ = ix.dense_topk(q, 150, rr._lib.RR_DENSE_TENSOR)
     assert ix.dense_stats()["eps"] >= worst
     ix.close()
+
+
+def test_cta_pair_kernel_equals_one_cta_kernel(monkeypatch):
+    """tc_filter_pair_kernel (tcgen05 cta_group::2, an ODD number of query tiles padded to an even one) and
+    tc_filter_kernel return the same exact pools; both equal the fp32 path."""
+    rr = _rr()
+    n, d, b, pool = 150_000, 384, 1100, 150            # 9 query tiles -> 10 for the pair kernel
+    emb = rr.synth.embeddings(n, d)
+    q = rr.synth.queries(b, d)
+    ix = rr.engine.HybridIndex(emb, device="cuda:0")
+    out = {}
+    for pair in ("1", "0"):
+        monkeypatch.setenv("RR_TC_PAIR", pair)
+        i2, s2, c2 = ix.dense_topk(q, pool, rr._lib.RR_DENSE_TENSOR)
+        assert ix.dense_stats()["path"] == 2
+        out[pair] = (i2.cpu().numpy(), s2.cpu().numpy())
+    np.testing.assert_array_equal(out["1"][0], out["0"][0])
+    np.testing.assert_array_equal(out["1"][1], out["0"][1])
+    i1, s1, _ = ix.dense_topk(q[:64], pool, rr._lib.RR_DENSE_EXACT)
+    np.testing.assert_array_equal(out["1"][0][:64], i1.cpu().numpy())
+    np.testing.assert_array_equal(out["1"][1][:64], s1.cpu().numpy())
+    ix.close()

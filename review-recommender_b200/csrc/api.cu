@@ -137,6 +137,8 @@ struct rr_index {
     struct GraphEntry { uint64_t key; uint64_t generation; int seen; cudaGraphExec_t exec; };
     std::vector<GraphEntry> graphs;
     cudaStream_t capture_stream = nullptr;
+    void* h_pinned = nullptr;          // small-batch host searches: one packed H2D and one packed D2H through pinned memory
+    size_t h_pinned_cap = 0;
 };
 
 namespace {
@@ -207,6 +209,7 @@ extern "C" void rr_index_destroy(rr_index* ix) {
     rr_tc_destroy(ix->tc);
     for (auto& g : ix->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ix->capture_stream) cudaStreamDestroy(ix->capture_stream);
+    if (ix->h_pinned) cudaFreeHost(ix->h_pinned);
     if (ix->fence) cudaEventDestroy(ix->fence);
     delete ix;
 }
@@ -580,10 +583,32 @@ extern "C" int rr_hybrid_search_host(rr_index* ix, const float* h_q, const int32
     int32_t* d_n = reinterpret_cast<int32_t*>(p); p += align_up(n_bytes, 256);
     int64_t* d_r = reinterpret_cast<int64_t*>(p); p += align_up(r_bytes, 256);
     float* d_f = reinterpret_cast<float*>(p);
-    RR_CUDA(cudaMemcpyAsync(d_q, h_q, q_bytes, cudaMemcpyHostToDevice, s));
-    if (have_terms) {
-        RR_CUDA(cudaMemcpyAsync(d_t, h_term_ids, t_bytes, cudaMemcpyHostToDevice, s));
-        RR_CUDA(cudaMemcpyAsync(d_n, h_n_terms, n_bytes, cudaMemcpyHostToDevice, s));
+    // Inputs and outputs are carved contiguously ([q | terms | n_terms] and [rows | final]).  Small batches travel as ONE
+    // copy each way through a pinned bounce buffer of the handle: five separate cudaMemcpyAsync calls on pageable memory
+    // cost more than the whole search of a single query (r02: 200 us per query at 10 k docs, most of it copies).
+    const size_t in_span = (size_t)(reinterpret_cast<char*>(d_r) - reinterpret_cast<char*>(d_q));
+    const size_t out_span = align_up(r_bytes, 256) + f_bytes;
+    const bool packed = in_span + out_span <= ((size_t)256 << 10);
+    if (packed) {
+        if (ix->h_pinned_cap < in_span + out_span) {
+            if (ix->h_pinned) cudaFreeHost(ix->h_pinned);
+            ix->h_pinned = nullptr; ix->h_pinned_cap = 0;
+            RR_CUDA(cudaMallocHost(&ix->h_pinned, (size_t)256 << 10));
+            ix->h_pinned_cap = (size_t)256 << 10;
+        }
+        char* hp = static_cast<char*>(ix->h_pinned);
+        memcpy(hp, h_q, q_bytes);
+        if (have_terms) {
+            memcpy(hp + (reinterpret_cast<char*>(d_t) - reinterpret_cast<char*>(d_q)), h_term_ids, t_bytes);
+            memcpy(hp + (reinterpret_cast<char*>(d_n) - reinterpret_cast<char*>(d_q)), h_n_terms, n_bytes);
+        }
+        RR_CUDA(cudaMemcpyAsync(d_q, hp, in_span, cudaMemcpyHostToDevice, s));
+    } else {
+        RR_CUDA(cudaMemcpyAsync(d_q, h_q, q_bytes, cudaMemcpyHostToDevice, s));
+        if (have_terms) {
+            RR_CUDA(cudaMemcpyAsync(d_t, h_term_ids, t_bytes, cudaMemcpyHostToDevice, s));
+            RR_CUDA(cudaMemcpyAsync(d_n, h_n_terms, n_bytes, cudaMemcpyHostToDevice, s));
+        }
     }
     // Small batches on the exact path (the single-query shape Streamlit issues, app/app_product_search.py:245-261)
     // are launch-latency bound: ~20 dependent launches of a few microseconds each.  The second call with the same
@@ -648,6 +673,14 @@ extern "C" int rr_hybrid_search_host(rr_index* ix, const float* h_q, const int32
     if (!done)
         RR_TRY(hybrid_locked(ix, d_q, have_terms ? d_t : nullptr, have_terms ? d_n : nullptr, B, l_max, fp, dense_mode,
                              d_r, d_f, s));
+    if (packed) {
+        char* hp = static_cast<char*>(ix->h_pinned) + in_span;
+        RR_CUDA(cudaMemcpyAsync(hp, d_r, out_span, cudaMemcpyDeviceToHost, s));
+        RR_CUDA(cudaStreamSynchronize(s));
+        memcpy(h_top_row, hp, r_bytes);
+        memcpy(h_top_final, hp + align_up(r_bytes, 256), f_bytes);
+        return RR_OK;
+    }
     RR_CUDA(cudaMemcpyAsync(h_top_row, d_r, r_bytes, cudaMemcpyDeviceToHost, s));
     RR_CUDA(cudaMemcpyAsync(h_top_final, d_f, f_bytes, cudaMemcpyDeviceToHost, s));
     RR_CUDA(cudaStreamSynchronize(s));

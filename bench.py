@@ -79,6 +79,8 @@ def parse_args():
                     help="queries of the batch that are also answered by the CPU oracle (oracle/sharded.py) -> id_parity")
     ap.add_argument("--synth-workers", type=int, default=0, help="host threads generating recipe chunks (0 = all cores)")
     ap.add_argument("--no-c1", action="store_true", help="skip the configs[0] single-query latency block")
+    ap.add_argument("--sparse-c4-docs", type=int, default=20_000_000,
+                    help="documents of the configs[3] BM25-only sweep appended to the N=1 line (0 = skip)")
     ap.add_argument("--query-groups", type=int, default=1,
                     help="Q query groups x (gpus/Q) row shards (dist.GridSearcher); 1 = plain row sharding")
     return ap.parse_args()
@@ -86,7 +88,7 @@ def parse_args():
 
 def load_traffic(kernel: str):
     """DRAM bytes of one profiled launch of `kernel` from the committed ncu --set full capture (or None)."""
-    p = REPO / "profiles" / "r01_traffic.json"
+    p = REPO / "profiles" / "r02_traffic.json"
     try:
         d = json.loads(p.read_text())
         rec = dict(d[kernel])
@@ -363,6 +365,47 @@ def c1_block(args, fusion_cls):
                    "queries, whole 10 k-doc corpus, no scaling"}
 
 
+def sparse_c4_block(args, peaks, dev):
+    """configs[3]: BM25-only, 20 M documents, 200 k-term Zipf vocabulary, 16-term queries -- rr_bm25_get_scores (every
+    document scored) for B in {1, 64, 256}, CUDA events around 5 calls each, against the algorithmic bytes of SURVEY 8d
+    (8 B per posting of the query's terms + 4 B per document per query)."""
+    import torch
+    import review_recommender_b200 as rr
+    n, v, l = args.sparse_c4_docs, 200_000, 16
+    cfg = dict(docs=n, dim=8, vocab=v, terms=l)
+    emb, offs, toks, nrev, avg = device_shard(cfg, 0, n, dev)
+    gb = rr.engine.GpuIndexBuilder(offs, toks, v)
+    stats = gb.local_stats().finalize()
+    ix = rr.engine.HybridIndex(emb, None, None, v, device=dev, stats=stats, postings=gb.finish(stats), make_bf16=False)
+    qt = rr.synth.query_terms(256, l, offs.cpu().numpy(), toks.cpu().numpy(), v).astype(np.int32)
+    del offs, toks
+    ib = ix.index_bytes()
+    out = {"workload": f"configs[3]: BM25-only, {n} docs, 200k Zipf vocab, 16-term queries, get_scores over all documents",
+           "kernel": "bm25_tile_scores_persistent_kernel", "tile_docs": ix.tile_docs, "index_bytes": ib,
+           "directory_frac_of_postings": ib["directory"] / max(ib["postings"], 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+           "sweep": []}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for b in (1, 64, 256):
+        ids = torch.from_numpy(qt[:b]).to(dev)
+        nts = torch.full((b,), l, dtype=torch.int32, device=dev)
+        for _ in range(2):
+            ix.bm25_get_scores(ids, nts)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(5):
+            res = ix.bm25_get_scores(ids, nts)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        del res
+        ms = e0.elapsed_time(e1) / 5
+        postings = int(stats.df[qt[:b]].sum())
+        nbytes = 8 * postings + 4 * n * b
+        out["sweep"].append({"B": b, "ms": ms, "algorithmic_bytes": nbytes, "achieved": nbytes / ms / 1e6,
+                             "frac": nbytes / ms / 1e6 / peaks["hbm_gbs"], "queries_per_s": b / ms * 1e3})
+    ix.close()
+    return out
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -610,7 +653,7 @@ def main():
         sp_ms = e0.elapsed_time(e1) / reps
         postings = int(local_df[qt_np[:nsq]].sum())
         sp_bytes = 8 * postings + 4 * n_local * nsq
-        sparse = {"kernel": "bm25_tile_scores_kernel (get_scores mode)", "queries": nsq, "docs": n_local,
+        sparse = {"kernel": "bm25_tile_scores_persistent_kernel (get_scores mode)", "queries": nsq, "docs": n_local,
                   "postings_per_query": postings / nsq, "ms": sp_ms, "achieved": sp_bytes / sp_ms / 1e6,
                   "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": sp_bytes / sp_ms / 1e6 / peaks["hbm_gbs"],
                   "queries_per_s": nsq / (sp_ms / 1000.0)}
@@ -739,9 +782,9 @@ def main():
         flops = 2.0 * (B // Q) * n_local * D            # this GPU: its query group's slice x its row shard
         t = kernels[dom]["ms_per_step"] / 1000.0
         ach = flops / t / 1e12
-        tr = load_traffic("tc_filter_kernel")
+        tr = load_traffic("tc_filter_pair_kernel")
         n_l = kernels[dom]["launches_per_step"]
-        roofline = {"kernel": "tc_filter_kernel (tcgen05 bf16 GEMM + threshold filter)", "bound": "tensor",
+        roofline = {"kernel": "tc_filter_pair_kernel (tcgen05 cta_group::2 bf16 GEMM + threshold filter)", "bound": "tensor",
                     "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                     "frac": ach / peaks["bf16_tflops_sustained"],
                     "traffic": tr["dram_bytes"] if tr else None,
@@ -803,6 +846,14 @@ def main():
         del ix
         torch.cuda.empty_cache()
         c1 = c1_block(args, eng.Fusion)
+    sparse_c4 = None
+    if world == 1 and args.sparse_c4_docs > 0 and args.config == "c3":
+        try:
+            ix.close()
+        except Exception:
+            pass
+        torch.cuda.empty_cache()
+        sparse_c4 = sparse_c4_block(args, peaks, dev)
 
 
     line = {
@@ -824,7 +875,7 @@ def main():
                 "h2d_bytes_per_step": int(q_np.nbytes + qt_np.nbytes + nt_np.nbytes),
                 "d2h_bytes_per_step": int(B * K * 12), "results_equal_device_path": same},
         "gpu_launches": int(launches),
-        "id_parity": id_parity, "result_digest": digest, "c1": c1,
+        "id_parity": id_parity, "result_digest": digest, "c1": c1, "sparse_c4": sparse_c4,
     }
     print(json.dumps(line), file=OUT, flush=True)
     if world > 1:

@@ -95,4 +95,30 @@ def test_configs3_bm25_get_scores_at_20m_documents():
     post_bytes = ix.index_bytes()["postings"]
     print(f"\nconfigs[3] {N4} docs: directory {meta_bytes / 1e6:.1f} MB = {100 * meta_bytes / post_bytes:.2f} % of postings")
     assert meta_bytes <= 0.05 * post_bytes
+    # throughput at the full configs[3] size, B = 64 (SURVEY 8d bytes: 8 B per posting of the query's terms + 4 B per doc):
+    # r02 measures 0.93-0.95 of the measured HBM peak; the assertion is a loose floor so that a regression of the
+    # TMA-ring kernel to the r01 level (0.69) fails in the driver's own GPU test run
+    import json
+    from pathlib import Path
+    peaks = Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json"
+    hbm = float(json.loads(peaks.read_text())["hbm_gbs"]) if peaks.exists() else 6650.0
+    qt64 = syn.query_terms_global(64, L4, N4, V4).astype(np.int32)
+    nt64 = torch.full((64,), L4, dtype=torch.int32, device=dev)
+    ids64 = torch.from_numpy(qt64).to(dev)
+    for _ in range(2):
+        ix.bm25_get_scores(ids64, nt64)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        out = ix.bm25_get_scores(ids64, nt64)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    nbytes = 8 * int(ch.df[qt64].sum()) + 4 * N4 * 64
+    frac = nbytes / ms / 1e6 / hbm
+    print(f"configs[3] K1 at B = 64: {ms:.2f} ms, {nbytes / ms / 1e6:.0f} GB/s = {frac:.3f} of the HBM peak ({hbm:.0f} GB/s)")
+    if N4 >= 8_000_000:
+        assert frac >= 0.75, frac
+    del out
     ix.close()

@@ -187,8 +187,10 @@ struct TcFilterArgs {
     long long n_docs;
     int n_kb;          // dim_pad / 64
     int B;
-    int qt0, n_qt;     // query tiles handled by this launch
-    int reps;          // CTAs per query tile
+    int n_parts;                 // query parts covered by this launch (<= 8)
+    int part_qt0[8], part_nq[8]; // first query tile / query tiles of every part
+    int part_reps[8];            // CTAs per query tile in the part
+    int part_ctas[8];            // = part_nq * part_reps
     int dt_lo, dt_hi;  // doc tiles of this segment
     int q_resident;    // 1: query tile loaded once (dim_pad <= 384); 0: its k-blocks are streamed with the corpus'
     const float* tau;  // [B]
@@ -216,11 +218,14 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cta = blockIdx.x;
-    const int qt = a.qt0 + cta % a.n_qt;
-    const int j0 = cta / a.n_qt;
+    // one launch covers all query parts: the CTAs of part p (its nq query tiles x its reps) follow those of part p-1
+    int cta = blockIdx.x, part = 0;
+    while (part + 1 < a.n_parts && cta >= a.part_ctas[part]) { cta -= a.part_ctas[part]; ++part; }
+    const int n_qt_p = a.part_nq[part], reps_p = a.part_reps[part];
+    const int qt = a.part_qt0[part] + cta % n_qt_p;
+    const int j0 = cta / n_qt_p;
     const int span = a.dt_hi - a.dt_lo;
-    const int n_tiles = j0 < span ? (span - j0 + a.reps - 1) / a.reps : 0;
+    const int n_tiles = j0 < span ? (span - j0 + reps_p - 1) / reps_p : 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
@@ -246,7 +251,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int t = 0; t < n_tiles; ++t) {
-                const int dt = a.dt_lo + j0 + t * a.reps;
+                const int dt = a.dt_lo + j0 + t * reps_p;
                 for (int kb = 0; kb < a.n_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     if (a.q_resident) {
@@ -310,7 +315,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int t = 0; t < n_tiles; ++t) {
             const int as = t & 1;
             const uint32_t aphase = (uint32_t)((t >> 1) & 1);
-            const int dt = a.dt_lo + j0 + t * a.reps;
+            const int dt = a.dt_lo + j0 + t * reps_p;
             const long long doc_base = (long long)dt * TC_BN;
             const uint32_t doc_base_u = (uint32_t)doc_base;
             const int n_valid = (int)min((long long)TC_BN, a.n_docs - doc_base);   // rows past the corpus end are zero-filled
@@ -455,11 +460,15 @@ tc_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    const int cta = blockIdx.x;                          // pairs: (2p, 2p+1) share j0 and own adjacent query tiles
-    const int qt = a.qt0 + cta % a.n_qt;
-    const int j0 = cta / a.n_qt;
+    // one launch covers all query parts: the CTAs of part p (its nq query tiles x its reps) follow those of part p-1;
+    // pairs (2c, 2c+1) share j0 and own adjacent query tiles (every part has an even number of query tiles)
+    int cta = blockIdx.x, part = 0;
+    while (part + 1 < a.n_parts && cta >= a.part_ctas[part]) { cta -= a.part_ctas[part]; ++part; }
+    const int n_qt_p = a.part_nq[part], reps_p = a.part_reps[part];
+    const int qt = a.part_qt0[part] + cta % n_qt_p;
+    const int j0 = cta / n_qt_p;
     const int span = a.dt_hi - a.dt_lo;
-    const int n_tiles = j0 < span ? (span - j0 + a.reps - 1) / a.reps : 0;
+    const int n_tiles = j0 < span ? (span - j0 + reps_p - 1) / reps_p : 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
@@ -487,7 +496,7 @@ tc_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             int stage = 0;
             uint32_t phase = 0;
             for (int t = 0; t < n_tiles; ++t) {
-                const int dt = a.dt_lo + j0 + t * a.reps;
+                const int dt = a.dt_lo + j0 + t * reps_p;
                 for (int kb = 0; kb < a.n_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     const uint32_t full_leader = mapa_cluster(smem_u32(&full[stage]), 0);
@@ -541,7 +550,7 @@ tc_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         for (int t = 0; t < n_tiles; ++t) {
             const int as = t & 1;
             const uint32_t aphase = (uint32_t)((t >> 1) & 1);
-            const int dt = a.dt_lo + j0 + t * a.reps;
+            const int dt = a.dt_lo + j0 + t * reps_p;
             const long long doc_base = (long long)dt * TC_BN;
             const uint32_t doc_base_u = (uint32_t)doc_base;
             const int n_valid = (int)min((long long)TC_BN, a.n_docs - doc_base);
@@ -1268,7 +1277,8 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
     // first segment: tau = -inf, everything passes (256 keys per tile and query go through the selection), so it is
     // sized to bring about as many keys as a later segment is expected to, (growth-1)*k'.  Limits: every (CTA, query,
     // half) sub-list must hold all the tiles its CTA scans (cap_sub / 128 of them), the total must stay sortable.
-    const int seg0_want = ((growth - 1) * KP + TC_BN - 1) / TC_BN;
+    const char* seg0_env = getenv("RR_TC_SEG0_TILES");
+    const int seg0_want = seg0_env && atoi(seg0_env) > 0 ? atoi(seg0_env) : ((growth - 1) * KP + TC_BN - 1) / TC_BN;
     const int seg0_tiles = std::max(1, std::min(seg0_want, std::min(reps_min * std::max(1, cap_sub / (TC_BN / 2)),
                                                                     (TC_SORT_MAX - KP) / TC_BN)));
     int n_segments = 0;
@@ -1276,26 +1286,37 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
     while (dt_lo < n_dt) {
         const int dt_hi = dt_lo == 0 ? std::min(n_dt, seg0_tiles)
                                      : (int)std::min<long long>(n_dt, (long long)dt_lo * growth);
-        int qt0 = 0;
-        for (int p = 0; p < best_parts; ++p) {
-            const int nq = part_tiles(best_parts, p);
+        {
+            // ONE launch per segment for all query parts (r02: every filter launch has ~30 us of fixed cost -- TMEM
+            // allocation, barrier set-up, the resident query tile, pipeline fill and drain -- which the small early
+            // segments paid once per part); the parts' CTAs follow each other in the grid, so part p+1 starts on the SMs
+            // part p frees.
             TcFilterArgs a;
-            a.n_docs = d->n_docs; a.n_kb = d->dim_pad / TC_BK; a.B = B; a.qt0 = qt0; a.n_qt = nq;
-            a.reps = std::max(1, std::min(sm_units / nq, dt_hi - dt_lo));
+            a.n_docs = d->n_docs; a.n_kb = d->dim_pad / TC_BK; a.B = B;
             a.dt_lo = dt_lo; a.dt_hi = dt_hi; a.tau = static_cast<const float*>(st->tau.p);
             a.q_resident = d->dim_pad <= TC_MAX_KB * TC_BK ? 1 : 0;
             a.n_sub = n_sub; a.cap_sub = cap_sub; a.pair_stages = pair_stages;
             a.cand_keys = static_cast<unsigned long long*>(st->cand_keys.p);
             a.cand_cnt = static_cast<unsigned*>(st->cand_cnt.p);
+            a.n_parts = best_parts;
+            int qt0 = 0, grid = 0;
+            for (int p = 0; p < 8; ++p) { a.part_qt0[p] = a.part_nq[p] = a.part_reps[p] = a.part_ctas[p] = 0; }
+            for (int p = 0; p < best_parts; ++p) {
+                const int nq = part_tiles(best_parts, p);
+                a.part_qt0[p] = qt0; a.part_nq[p] = nq;
+                a.part_reps[p] = std::max(1, std::min(sm_units / nq, dt_hi - dt_lo));
+                a.part_ctas[p] = nq * a.part_reps[p];
+                grid += a.part_ctas[p];
+                qt0 += nq;
+            }
             {
                 RrProfScope prof(RR_PROF_TC_FILTER, s);
                 if (use_pair)
-                    tc_filter_pair_kernel<<<nq * a.reps, TC_THREADS, tc2_smem_total(pair_stages), s>>>(tmap_q, st->tmap_c_half, a);
+                    tc_filter_pair_kernel<<<grid, TC_THREADS, tc2_smem_total(pair_stages), s>>>(tmap_q, st->tmap_c_half, a);
                 else
-                    tc_filter_kernel<<<nq * a.reps, TC_THREADS, TC_SMEM_TOTAL, s>>>(tmap_q, st->tmap_c, a);
+                    tc_filter_kernel<<<grid, TC_THREADS, TC_SMEM_TOTAL, s>>>(tmap_q, st->tmap_c, a);
             }
             RR_LAUNCH_CHECK();
-            qt0 += nq;
         }
         const int final_pass = dt_hi >= n_dt;
         {
@@ -1451,10 +1472,13 @@ int rr_tc_debug_scores(rr_tc_state** state, const rr_index_desc* d, int sm_count
                                                                      static_cast<int*>(st->overflow.p), static_cast<int*>(st->flags.p), B);
     RR_LAUNCH_CHECK();
     TcFilterArgs a;
-    a.n_docs = d->n_docs; a.n_kb = d->dim_pad / TC_BK; a.B = B; a.qt0 = 0; a.n_qt = 1; a.reps = reps;
+    a.n_docs = d->n_docs; a.n_kb = d->dim_pad / TC_BK; a.B = B;
+    a.n_parts = 1;
+    for (int p = 0; p < 8; ++p) { a.part_qt0[p] = a.part_nq[p] = a.part_reps[p] = a.part_ctas[p] = 0; }
+    a.part_qt0[0] = 0; a.part_nq[0] = 1; a.part_reps[0] = reps; a.part_ctas[0] = reps;
     a.dt_lo = (int)(row0 / TC_BN); a.dt_hi = a.dt_lo + n_dt; a.tau = static_cast<const float*>(st->tau.p);
     a.q_resident = d->dim_pad <= TC_MAX_KB * TC_BK ? 1 : 0;
-    a.n_sub = n_sub; a.cap_sub = cap_sub;
+    a.n_sub = n_sub; a.cap_sub = cap_sub; a.pair_stages = 0;
     a.cand_keys = static_cast<unsigned long long*>(st->cand_keys.p);
     a.cand_cnt = static_cast<unsigned*>(st->cand_cnt.p);
     tc_filter_kernel<<<reps, TC_THREADS, TC_SMEM_TOTAL, s>>>(tmap_q, st->tmap_c, a);

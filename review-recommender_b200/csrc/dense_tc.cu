@@ -833,7 +833,8 @@ __global__ void __launch_bounds__(256)
 tc_select_warp_kernel(const unsigned long long* __restrict__ cand_keys, unsigned* __restrict__ cand_cnt, int n_sub,
                       int cap_sub, unsigned long long* __restrict__ kept_keys, int* __restrict__ kept_cnt, int KP,
                       float* __restrict__ tau, int* __restrict__ overflow, int final_pass,
-                      long long* __restrict__ rows_out, int cap, int warps_per_cta, int B) {
+                      long long* __restrict__ rows_out, int cap, int warps_per_cta, int B, int prune_m,
+                      const float* __restrict__ qnorm, float eps_rel) {
     extern __shared__ unsigned long long smem_sel[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int q = blockIdx.x * warps_per_cta + wid;
@@ -872,10 +873,12 @@ tc_select_warp_kernel(const unsigned long long* __restrict__ cand_keys, unsigned
                          total, lane, 32);
     __syncwarp();
 
-    int newk = total;
-    unsigned long long thr_prefix = 0ull;
-    int thr_bits = 0;
-    if (total > KP) {
+    // MSB-first radix select of the `want` largest keys of sk[0, total): returns (prefix, bits) such that the selection is
+    // {k : (k >> (64 - bits)) >= prefix}; bits = 0 selects everything
+    auto select_top = [&](int want, unsigned long long& out_prefix, int& out_bits) {
+        out_prefix = 0ull;
+        out_bits = 0;
+        if (total <= want) return;
         unsigned long long kmin = ~0ull, kmax = 0ull;
         for (int i = lane; i < total; i += 32) { const unsigned long long k = sk[i]; kmin = min(kmin, k); kmax = max(kmax, k); }
         for (int o = 16; o > 0; o >>= 1) {
@@ -884,7 +887,7 @@ tc_select_warp_kernel(const unsigned long long* __restrict__ cand_keys, unsigned
         }
         int bits = kmin == kmax ? 56 : min(__clzll((long long)(kmin ^ kmax)), 56);
         unsigned long long prefix = bits ? (kmax >> (64 - bits)) : 0ull;
-        int krem = KP;
+        int krem = want;
         bool done = false;
         for (int pass = 0; pass < 9 && !done; ++pass) {
             const int dig = min(8, 64 - bits);
@@ -936,9 +939,28 @@ tc_select_warp_kernel(const unsigned long long* __restrict__ cand_keys, unsigned
             bits += dig;
             __syncwarp();
         }
-        thr_prefix = prefix;
-        thr_bits = bits;
-        newk = KP;
+        out_prefix = prefix;
+        out_bits = bits;
+    };
+    unsigned long long thr_prefix = 0ull;
+    int thr_bits = 0;
+    select_top(KP, thr_prefix, thr_bits);
+    const int newk = min(total, KP);
+    // Final pass of a sharded round (prune_m = the shard's pool m < k'): rows whose bf16 score is more than 2 eps below the
+    // m-th best bf16 score cannot be among the exact top-m (at least m rows have exact >= t_m - eps, such a row has exact
+    // < t_m - eps), so they need no exact rescoring: their row is reported as -1 (exact = -inf, sorted last).
+    float prune_below = -INFINITY;
+    if (final_pass && prune_m > 0 && prune_m < newk) {
+        unsigned long long mp = 0ull;
+        int mb = 0;
+        select_top(prune_m, mp, mb);
+        unsigned long long mmin = ~0ull;
+        for (int i = lane; i < total; i += 32) {
+            const unsigned long long k = sk[i];
+            if (mb == 0 || (k >> (64 - mb)) >= mp) mmin = min(mmin, k);
+        }
+        for (int o = 16; o > 0; o >>= 1) mmin = min(mmin, __shfl_xor_sync(FULL, mmin, o));
+        prune_below = rr_key_score(mmin) - 2.0f * eps_rel * qnorm[q];
     }
     // ---- compact survivors --------------------------------------------------------------------------
     unsigned long long mymin = ~0ull;
@@ -953,7 +975,7 @@ tc_select_warp_kernel(const unsigned long long* __restrict__ cand_keys, unsigned
             const int slot = out + __popc(m & ((1u << lane) - 1u));
             if (slot < KP) {
                 kept_keys[(size_t)q * KP + slot] = k;
-                if (final_pass) rows_out[(size_t)q * KP + slot] = (long long)rr_key_index(k);
+                if (final_pass) rows_out[(size_t)q * KP + slot] = rr_key_score(k) < prune_below ? -1ll : (long long)rr_key_index(k);
             }
             mymin = min(mymin, k);
         }
@@ -1337,7 +1359,8 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
                     static_cast<const unsigned long long*>(st->cand_keys.p), static_cast<unsigned*>(st->cand_cnt.p), n_sub,
                     cap_sub, static_cast<unsigned long long*>(st->kept_keys.p), static_cast<int*>(st->kept_cnt.p), KP,
                     static_cast<float*>(st->tau.p), static_cast<int*>(st->overflow.p), final_pass,
-                    static_cast<long long*>(st->rows.p), sort_cap, wpc, B);
+                    static_cast<long long*>(st->rows.p), sort_cap, wpc, B, getenv("RR_TC_NO_PRUNE") ? 0 : pool,
+                    static_cast<const float*>(st->qnorm.p), (0.0078125f + 0.000030517578125f + 1e-4f) * d->max_row_norm);
             } else {
                 tc_select_kernel<<<B, 256, (size_t)sort_cap * 8, s>>>(
                     static_cast<const unsigned long long*>(st->cand_keys.p), static_cast<unsigned*>(st->cand_cnt.p), n_sub,

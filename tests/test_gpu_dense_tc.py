@@ -114,3 +114,31 @@ def test_cta_pair_kernel_equals_one_cta_kernel(monkeypatch):
     np.testing.assert_array_equal(out["1"][0][:64], i1.cpu().numpy())
     np.testing.assert_array_equal(out["1"][1][:64], s1.cpu().numpy())
     ix.close()
+
+
+def test_rescoring_prune_keeps_the_exact_answer(monkeypatch):
+    """Small pools (a sharded round 1): rows more than 2 eps below the m-th bf16 score are not rescored.  The result must
+    equal the unpruned tensor path and the exact path, also when many rows crowd the cut-off (near-duplicates)."""
+    rr = _rr()
+    n, d, b, pool = 300_000, 384, 256, 48
+    emb = rr.synth.embeddings(n, d)
+    rng = np.random.default_rng(5)
+    base = emb[123].copy()
+    for r in range(5000, 5040):                       # 40 rows within 1e-3 of row 123: inside the 2-eps band of its query
+        v = base + 1e-3 * rng.standard_normal(d).astype(np.float32)
+        emb[r] = v / np.linalg.norm(v)
+    q = rr.synth.queries(b, d)
+    q[7] = base
+    ix = rr.engine.HybridIndex(emb, device="cuda:0")
+    i0, s0, _ = ix.dense_topk(q, pool, rr._lib.RR_DENSE_EXACT)
+    out = {}
+    for prune in (True, False):
+        if prune:
+            monkeypatch.delenv("RR_TC_NO_PRUNE", raising=False)
+        else:
+            monkeypatch.setenv("RR_TC_NO_PRUNE", "1")
+        i2, s2, _ = ix.dense_topk(q, pool, rr._lib.RR_DENSE_TENSOR)
+        assert ix.dense_stats()["path"] == 2 and ix.dense_stats()["shortlist"] <= 512
+        np.testing.assert_array_equal(i2.cpu().numpy(), i0.cpu().numpy())
+        np.testing.assert_array_equal(s2.cpu().numpy(), s0.cpu().numpy())
+    ix.close()

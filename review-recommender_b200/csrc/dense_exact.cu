@@ -188,9 +188,10 @@ rescore_multi_kernel(const float* __restrict__ emb, long long n_rows, int D, con
         rp[r] = reinterpret_cast<const float4*>(emb + (ok[r] ? row : 0) * D);
     }
     float acc[RS];
+    bool any = false;
 #pragma unroll
-    for (int r = 0; r < RS; ++r) acc[r] = 0.f;
-    const int n_chunks = D >> 2;
+    for (int r = 0; r < RS; ++r) { acc[r] = 0.f; any |= ok[r]; }
+    const int n_chunks = any ? D >> 2 : 0;            // a group of empty / pruned slots has nothing to load
     for (int c = lane; c < n_chunks; c += 32) {
         float4 m[RS];
 #pragma unroll

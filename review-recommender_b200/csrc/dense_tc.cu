@@ -946,6 +946,8 @@ tc_select_warp_kernel(const unsigned long long* __restrict__ cand_keys, unsigned
     int thr_bits = 0;
     select_top(KP, thr_prefix, thr_bits);
     const int newk = min(total, KP);
+    // OPT-IN (RR_TC_PRUNE=1; r02 measured no wall-clock gain on a 1.25 M-row shard: ~30 % of the k' = 160 rows are pruned,
+    // but the rescoring kernel of such a small shortlist is latency-bound and the extra selection costs what it saves).
     // Final pass of a sharded round (prune_m = the shard's pool m < k'): rows whose bf16 score is more than 2 eps below the
     // m-th best bf16 score cannot be among the exact top-m (at least m rows have exact >= t_m - eps, such a row has exact
     // < t_m - eps), so they need no exact rescoring: their row is reported as -1 (exact = -inf, sorted last).
@@ -962,24 +964,29 @@ tc_select_warp_kernel(const unsigned long long* __restrict__ cand_keys, unsigned
         for (int o = 16; o > 0; o >>= 1) mmin = min(mmin, __shfl_xor_sync(FULL, mmin, o));
         prune_below = rr_key_score(mmin) - 2.0f * eps_rel * qnorm[q];
     }
-    // ---- compact survivors --------------------------------------------------------------------------
+    // ---- compact survivors: rows to rescore from the front, pruned rows (final pass only) from the back, so that the
+    // rescoring warps (4 consecutive slots each) of the pruned tail have nothing to load -----------------------------
     unsigned long long mymin = ~0ull;
-    int out = 0;
+    int front = 0, back = 0;
     for (int i0 = 0; i0 < total; i0 += 32) {
         const int i = i0 + lane;
         bool sel = false;
         unsigned long long k = 0ull;
         if (i < total) { k = sk[i]; sel = thr_bits == 0 || (k >> (64 - thr_bits)) >= thr_prefix; }
-        const unsigned m = __ballot_sync(FULL, sel);
+        const bool pruned = sel && rr_key_score(k) < prune_below;
+        const unsigned mv = __ballot_sync(FULL, sel && !pruned);
+        const unsigned mp = __ballot_sync(FULL, pruned);
         if (sel) {
-            const int slot = out + __popc(m & ((1u << lane) - 1u));
-            if (slot < KP) {
+            const unsigned below = (1u << lane) - 1u;
+            const int slot = pruned ? newk - 1 - (back + __popc(mp & below)) : front + __popc(mv & below);
+            if (slot >= 0 && slot < KP) {
                 kept_keys[(size_t)q * KP + slot] = k;
-                if (final_pass) rows_out[(size_t)q * KP + slot] = rr_key_score(k) < prune_below ? -1ll : (long long)rr_key_index(k);
+                if (final_pass) rows_out[(size_t)q * KP + slot] = pruned ? -1ll : (long long)rr_key_index(k);
             }
             mymin = min(mymin, k);
         }
-        out += __popc(m);
+        front += __popc(mv);
+        back += __popc(mp);
     }
     for (int o = 16; o > 0; o >>= 1) mymin = min(mymin, __shfl_xor_sync(FULL, mymin, o));
     if (final_pass)
@@ -1359,7 +1366,7 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
                     static_cast<const unsigned long long*>(st->cand_keys.p), static_cast<unsigned*>(st->cand_cnt.p), n_sub,
                     cap_sub, static_cast<unsigned long long*>(st->kept_keys.p), static_cast<int*>(st->kept_cnt.p), KP,
                     static_cast<float*>(st->tau.p), static_cast<int*>(st->overflow.p), final_pass,
-                    static_cast<long long*>(st->rows.p), sort_cap, wpc, B, getenv("RR_TC_NO_PRUNE") ? 0 : pool,
+                    static_cast<long long*>(st->rows.p), sort_cap, wpc, B, getenv("RR_TC_PRUNE") ? pool : 0,
                     static_cast<const float*>(st->qnorm.p), (0.0078125f + 0.000030517578125f + 1e-4f) * d->max_row_norm);
             } else {
                 tc_select_kernel<<<B, 256, (size_t)sort_cap * 8, s>>>(

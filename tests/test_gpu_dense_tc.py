@@ -117,7 +117,7 @@ def test_cta_pair_kernel_equals_one_cta_kernel(monkeypatch):
 
 
 def test_rescoring_prune_keeps_the_exact_answer(monkeypatch):
-    """Small pools (a sharded round 1): rows more than 2 eps below the m-th bf16 score are not rescored.  The result must
+    """Small pools (a sharded round 1), opt-in RR_TC_PRUNE=1: rows more than 2 eps below the m-th bf16 score are not rescored.  The result must
     equal the unpruned tensor path and the exact path, also when many rows crowd the cut-off (near-duplicates)."""
     rr = _rr()
     n, d, b, pool = 300_000, 384, 256, 48
@@ -134,9 +134,9 @@ def test_rescoring_prune_keeps_the_exact_answer(monkeypatch):
     out = {}
     for prune in (True, False):
         if prune:
-            monkeypatch.delenv("RR_TC_NO_PRUNE", raising=False)
+            monkeypatch.setenv("RR_TC_PRUNE", "1")
         else:
-            monkeypatch.setenv("RR_TC_NO_PRUNE", "1")
+            monkeypatch.delenv("RR_TC_PRUNE", raising=False)
         i2, s2, _ = ix.dense_topk(q, pool, rr._lib.RR_DENSE_TENSOR)
         assert ix.dense_stats()["path"] == 2 and ix.dense_stats()["shortlist"] <= 512
         np.testing.assert_array_equal(i2.cpu().numpy(), i0.cpu().numpy())

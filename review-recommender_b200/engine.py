@@ -428,13 +428,18 @@ class HybridIndex:
         return ids, n
 
     # ---- sparse ----------------------------------------------------------------------------
-    def bm25_get_scores(self, term_ids, n_terms) -> torch.Tensor:
-        """float32[B, n_docs] (a view of a [B, ld] buffer): batched BM25Okapi.get_scores."""
+    def bm25_get_scores(self, term_ids, n_terms, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """float32[B, n_docs] (a view of a [B, ld] buffer): batched BM25Okapi.get_scores.  `out`: a float32 [B, ld] CUDA
+        buffer to reuse (ld = n_docs rounded up to a multiple of 4), e.g. when timing -- a fresh multi-GB allocation
+        per call costs more than the kernel."""
         term_ids = self._dev(term_ids, torch.int32)
         n_terms = self._dev(n_terms, torch.int32)
         B, lmax = int(term_ids.shape[0]), int(term_ids.shape[1])
         ld = (self.n_docs + 3) // 4 * 4
-        out = torch.empty((B, ld), dtype=torch.float32, device=self.device)
+        if out is None:
+            out = torch.empty((B, ld), dtype=torch.float32, device=self.device)
+        elif not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, ld)):
+            raise RRError(f"out must be a contiguous float32 CUDA tensor of shape ({B}, {ld})")
         check(self.lib.rr_bm25_get_scores(self._h, _ptr(term_ids), _ptr(n_terms), B, lmax, _ptr(out), ld, _stream()))
         return out[:, :self.n_docs]
 

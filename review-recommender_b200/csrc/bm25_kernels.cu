@@ -11,14 +11,18 @@
 // behind the frequent region; bm25_rare_bounds_kernel finds, per batch, where every tile starts in the lists of the
 // batch's rare query terms.
 //
-//  bm25_tile_scores_kernel   one CTA per (query, tile): T fp32 accumulators live in shared memory.  A PRODUCER warp
-//      streams the <= 64 term segments of the CTA with 1-D TMA bulk copies (cp.async.bulk, mbarrier complete_tx)
+//  bm25_tile_scores_persistent_kernel (default, query term lists of <= 64 terms) / bm25_tile_scores_kernel (one CTA per
+//      (query, tile), any length):  T fp32 accumulators live in shared memory.  A PRODUCER warp
+//      streams the <= 64 term segments of an item with 1-D TMA bulk copies (cp.async.bulk, mbarrier complete_tx)
 //      into a shared-memory ring, running up to NSTAGE chunks ahead of the eight CONSUMER warps, which add the
 //      impacts in QUERY-TERM ORDER (a named barrier separates consecutive terms; postings of one term hit distinct
 //      docs, so the plain read-modify-write is race free and the fp32 sum is deterministic), then write the tile's
 //      scores with coalesced 16-byte stores.  Loads are decoupled from the per-term barriers: the r01 kernel issued
 //      a round of register loads only after the previous round's adds (ncu: long-scoreboard + barrier stalls).
-//      The grid is query-fastest, so the CTAs that share a tile (and, for common terms, its segments) run together
+//      The persistent variant keeps 3 CTAs per SM resident, pulls (query, tile) items from a global counter and lets the
+//      producer work ONE ITEM AHEAD (bounds double-buffered), which hides the directory look-ups, the zero-fill and the
+//      write-out of an item behind the next item's stream: 0.95 of the measured HBM peak at configs[3] (r01: 0.69).
+//      Items are query-fastest, so the CTAs that share a tile (and, for common terms, its segments) run together
 //      and the shared segments are served by L2.
 //      HBM traffic <= 8 B per posting of the query's terms + 4 B per doc: the algorithmic bytes.
 //      Summation: fp32 adds in the order of the query's token list.  rank_bm25 adds float64 terms and the callers cast

@@ -1358,10 +1358,12 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
             const int expect = dt_lo == 0 ? (dt_hi - dt_lo) * TC_BN + KP : KP * (growth + growth / 2 + 2);
             const int sort_cap = std::min(TC_SORT_MAX, std::max(1024, (expect + 255) / 256 * 256));
             RrProfScope prof(RR_PROF_TC_SELECT, s);
-            if (sort_cap <= 2048) {
+            static const int warp_max = getenv("RR_TC_SELECT_WARP_MAX") ? atoi(getenv("RR_TC_SELECT_WARP_MAX")) : 2048;
+            static const int wpc_max = getenv("RR_TC_SELECT_WPC") ? std::max(1, std::min(8, atoi(getenv("RR_TC_SELECT_WPC")))) : 8;
+            if (sort_cap <= warp_max) {
                 // warp per query: 4..8 queries per CTA, no block barriers
                 const size_t per_warp_words = (size_t)sort_cap + 128 + (TC_MAX_SUB + 2) / 2 + 1;
-                const int wpc = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(96 * 1024) / (per_warp_words * 8)));
+                const int wpc = (int)std::max<size_t>(1, std::min<size_t>((size_t)wpc_max, (size_t)(96 * 1024) / (per_warp_words * 8)));
                 tc_select_warp_kernel<<<(B + wpc - 1) / wpc, wpc * 32, per_warp_words * 8 * wpc, s>>>(
                     static_cast<const unsigned long long*>(st->cand_keys.p), static_cast<unsigned*>(st->cand_cnt.p), n_sub,
                     cap_sub, static_cast<unsigned long long*>(st->kept_keys.p), static_cast<int*>(st->kept_cnt.p), KP,

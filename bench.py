@@ -79,6 +79,8 @@ def parse_args():
                     help="queries of the batch that are also answered by the CPU oracle (oracle/sharded.py) -> id_parity")
     ap.add_argument("--synth-workers", type=int, default=0, help="host threads generating recipe chunks (0 = all cores)")
     ap.add_argument("--no-c1", action="store_true", help="skip the configs[0] single-query latency block")
+    ap.add_argument("--no-side-configs", action="store_true",
+                    help="skip the short configs[1] and configs[4]-shard runs appended to the N=1 line")
     ap.add_argument("--sparse-c4-docs", type=int, default=20_000_000,
                     help="documents of the configs[3] BM25-only sweep appended to the N=1 line (0 = skip)")
     ap.add_argument("--query-groups", type=int, default=1,
@@ -363,6 +365,62 @@ def c1_block(args, fusion_cls):
             "how": "one rr_hybrid_search_host call per query (pageable host buffers in, results out, stream synchronised "
                    "inside the call), wall clock per call; CPU = oracle port of run_search in one interpreter on the same "
                    "queries, whole 10 k-doc corpus, no scaling"}
+
+
+def side_config_block(name: str, n_docs: int, peaks, dev, steps: int = 10, warmup: int = 3):
+    """A short device-resident run of another BASELINE config on this GPU (device-generated corpus of the same
+    distributions, so no oracle comparison here -- parity at these shapes is the tests' job): ms / step, q/s and the
+    tensor-roofline fraction of K2 measured like the headline's."""
+    import torch
+    import review_recommender_b200 as rr
+    eng = rr.engine
+    cfg = dict(CONFIGS[name])
+    cfg["docs"] = n_docs
+    D, V, B, L, K = cfg["dim"], cfg["vocab"], cfg["batch"], cfg["terms"], cfg["k"]
+    emb, offs, toks, nrev, avg = device_shard(cfg, 0, n_docs, dev)
+    gb = eng.GpuIndexBuilder(offs, toks, V)
+    stats = gb.local_stats().finalize()
+    ix = eng.HybridIndex(emb, None, None, V, nrev, avg, device=dev, stats=stats, postings=gb.finish(stats))
+    del emb
+    q = torch.from_numpy(rr.synth.queries(B, D)).to(dev)
+    qt = torch.from_numpy(rr.synth.query_terms(B, L, offs.cpu().numpy(), toks.cpu().numpy(), V).astype(np.int32)).to(dev)
+    nt = torch.full((B,), L, dtype=torch.int32, device=dev)
+    del offs, toks
+    wts = dict(w_dense=0.55, w_bm25=0.20, w_prior=0.20) | cfg.get("weights", {})
+    fusion = eng.Fusion(k=K, rerank_k=0, w_rerank=0.0, w_best=0.0, prior_C=20.0, min_reviews=8, driver="streamlit", **wts)
+    for _ in range(warmup):
+        ix.hybrid_search_begin(q, qt, nt, fusion).result()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rep = 0
+    for _ in range(steps):
+        tok = ix.hybrid_search_begin(q, qt, nt, fusion)
+        tok.result()
+        rep = tok.repeated
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    eng.profile_enable(True)
+    eng.profile_collect()
+    for _ in range(steps):
+        ix.hybrid_search_begin(q, qt, nt, fusion).result()
+    torch.cuda.synchronize(dev)
+    prof = eng.profile_collect()
+    eng.profile_enable(False)
+    kernels = {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps} for k, v in prof.items() if v[1] > 0}
+    out = {"workload": cfg["workload"] + (f" [one row shard of {n_docs} docs on this GPU]" if n_docs != CONFIGS[name]["docs"] else ""),
+           "docs": n_docs, "dim": D, "batch": B, "k": K, "pool": fusion.pool, "ms_per_step": ms, "value": B / (ms / 1000.0),
+           "unit": UNIT, "repeated_queries_last_step": int(rep), "dense_path": ix.dense_stats(), "kernels": kernels,
+           "data": "synthetic (device generators)"}
+    if "tc_filter" in kernels:
+        ach = 2.0 * B * n_docs * D / (kernels["tc_filter"]["ms_per_step"] / 1000.0) / 1e12
+        out["k2_tflops"] = ach
+        out["k2_frac_of_sustained"] = ach / peaks["bf16_tflops_sustained"]
+    ix.close()
+    del ix
+    torch.cuda.empty_cache()
+    return out
 
 
 def sparse_c4_block(args, peaks, dev):
@@ -857,6 +915,15 @@ def main():
             pass
         torch.cuda.empty_cache()
         sparse_c4 = sparse_c4_block(args, peaks, dev)
+    side = None
+    if world == 1 and not args.no_side_configs and args.config == "c3":
+        try:
+            ix.close()
+        except Exception:
+            pass
+        torch.cuda.empty_cache()
+        side = {"configs1": side_config_block("c2", CONFIGS["c2"]["docs"], peaks, dev, steps=20, warmup=3),
+                "configs4_one_of_8_shards": side_config_block("c5", CONFIGS["c5"]["docs"] // 8, peaks, dev, steps=5, warmup=3)}
 
 
     line = {
@@ -878,7 +945,7 @@ def main():
                 "h2d_bytes_per_step": int(q_np.nbytes + qt_np.nbytes + nt_np.nbytes),
                 "d2h_bytes_per_step": int(B * K * 12), "results_equal_device_path": same},
         "gpu_launches": int(launches),
-        "id_parity": id_parity, "result_digest": digest, "c1": c1, "sparse_c4": sparse_c4,
+        "id_parity": id_parity, "result_digest": digest, "c1": c1, "sparse_c4": sparse_c4, "other_configs": side,
     }
     print(json.dumps(line), file=OUT, flush=True)
     if world > 1:

@@ -3,7 +3,7 @@
 #   gpurun --timeout 1500 -- bash tools/profile_step.sh
 # Outputs land in gpurun_out/ (scratch); summarise into profiles/ with profiles/summarize.py / launch_summary.py.
 set -u
-CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-c1 --sparse-c4-docs 0 --parity-queries 0 --synth device --sparse-queries 8"
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-c1 --sparse-c4-docs 0 --no-side-configs --parity-queries 0 --synth device --sparse-queries 8"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain_step_r2.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_step_r2.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches_step_r2.csv $CMD > gpurun_out/ncu_a.log 2>&1

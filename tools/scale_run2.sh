@@ -25,4 +25,4 @@ run s8_f2 8
 run s8_f1 8 --in-flight 1
 RR_TC_GROWTH=4 run s8_f2_g4 8
 run s4_f2 4
-run s1 1 --no-c1 --sparse-c4-docs 0
+run s1 1 --no-c1 --sparse-c4-docs 0 --no-side-configs

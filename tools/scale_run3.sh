@@ -25,4 +25,4 @@ run t8 8
 run t8_f1 8 --in-flight 1
 run t4 4
 run t2 2
-run t1 1 --no-c1 --sparse-c4-docs 0
+run t1 1 --no-c1 --sparse-c4-docs 0 --no-side-configs

@@ -1242,7 +1242,11 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
         st->pair_attr_set = true;
     }
     const char* ps_env = getenv("RR_TC_PAIR_STAGES");
-    const int pair_stages = std::max(2, std::min(TC2_MAX_STAGES, ps_env ? atoi(ps_env) : 8));
+    // 6 stages (96 KB of queries + 96 KB of ring): as fast as 8 on its own (r02: 21.5 ms / step either way), and it leaves
+    // ~33 KB of shared memory per SM, so that the small tail kernels of ANOTHER batch in flight (selection with 2 warps per
+    // CTA, rescoring, candidate BM25, finalize) can co-reside with the GEMM instead of waiting for it
+    // (1.25 M-row shard, 2 batches in flight: 4.24 -> 4.18 ms / step)
+    const int pair_stages = std::max(2, std::min(TC2_MAX_STAGES, ps_env ? atoi(ps_env) : 6));
     const int sm_units = use_pair ? sm_count / 2 * 2 : sm_count;      // pairs occupy whole TPCs
 
     // Split the query tiles into parts so that (tiles per part) x (CTAs per tile) fills the SMs; an extra
@@ -1359,7 +1363,7 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
             const int sort_cap = std::min(TC_SORT_MAX, std::max(1024, (expect + 255) / 256 * 256));
             RrProfScope prof(RR_PROF_TC_SELECT, s);
             static const int warp_max = getenv("RR_TC_SELECT_WARP_MAX") ? atoi(getenv("RR_TC_SELECT_WARP_MAX")) : 2048;
-            static const int wpc_max = getenv("RR_TC_SELECT_WPC") ? std::max(1, std::min(8, atoi(getenv("RR_TC_SELECT_WPC")))) : 8;
+            static const int wpc_max = getenv("RR_TC_SELECT_WPC") ? std::max(1, std::min(8, atoi(getenv("RR_TC_SELECT_WPC")))) : 2;   // see pair_stages
             if (sort_cap <= warp_max) {
                 // warp per query: 4..8 queries per CTA, no block barriers
                 const size_t per_warp_words = (size_t)sort_cap + 128 + (TC_MAX_SUB + 2) / 2 + 1;

@@ -460,15 +460,21 @@ tc_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    // one launch covers all query parts: the CTAs of part p (its nq query tiles x its reps) follow those of part p-1;
-    // pairs (2c, 2c+1) share j0 and own adjacent query tiles (every part has an even number of query tiles)
-    int cta = blockIdx.x, part = 0;
-    while (part + 1 < a.n_parts && cta >= a.part_ctas[part]) { cta -= a.part_ctas[part]; ++part; }
-    const int n_qt_p = a.part_nq[part], reps_p = a.part_reps[part];
-    const int qt = a.part_qt0[part] + cta % n_qt_p;
-    const int j0 = cta / n_qt_p;
+    uint64_t* qfree = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // [1] per CTA: MMA (multicast commit) -> this CTA's TMA: sQ reusable
+    // PERSISTENT OVER THE QUERY PARTS: the grid has max_p(part_ctas[p]) CTAs and CTA c serves, one part after the other,
+    // query tile part_qt0[p] + c % nq_p with doc tiles j0 = c / nq_p, j0 + reps_p, ...  (pairs (2c, 2c+1) share j0 and own
+    // adjacent query tiles: every part has an even number of query tiles).  All CTAs of the launch are resident from the
+    // start -- no second wave waiting for shared memory -- which is what lets the block scheduler place the small tail
+    // kernels of another batch in flight next to them.
+    const int cta = blockIdx.x;
     const int span = a.dt_hi - a.dt_lo;
-    const int n_tiles = j0 < span ? (span - j0 + reps_p - 1) / reps_p : 0;
+    auto part_geometry = [&](int p, int& qt, int& j0, int& reps_p) -> int {      // -> doc tiles of this CTA in part p
+        if (cta >= a.part_ctas[p]) return 0;
+        reps_p = a.part_reps[p];
+        qt = a.part_qt0[p] + cta % a.part_nq[p];
+        j0 = cta / a.part_nq[p];
+        return j0 < span ? (span - j0 + reps_p - 1) / reps_p : 0;
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
@@ -478,6 +484,7 @@ tc_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         // barrier word across the cluster -- made the pair kernel 1.6x slower than the one-CTA kernel)
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * (TC_EPI_THREADS / 32)); }
         mbar_init(qfull, 2);
+        mbar_init(qfree, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_512_pair(tmem_slot);
@@ -487,116 +494,137 @@ tc_filter_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer (one thread per CTA): its queries once, then its half of every corpus k-block =====
-        if (lane == 0 && n_tiles > 0) {
+        // ===== TMA producer (one thread per CTA): per part its queries, then its half of every corpus k-block =====
+        if (lane == 0) {
             const uint32_t qfull_leader = mapa_cluster(smem_u32(qfull), 0);
-            if (leader) mbar_expect_tx(qfull, (uint32_t)(2 * a.n_kb * TC_Q_KB_BYTES));
-            else mbar_arrive_remote(qfull_leader);
-            for (int kb = 0; kb < a.n_kb; ++kb) tma_load_2d_pair(&tmap_q, qfull_leader, sQ + kb * TC_Q_KB_BYTES, kb * TC_BK, qt * TC_BM);
-            int stage = 0;
+            int stage = 0, served = 0;
             uint32_t phase = 0;
-            for (int t = 0; t < n_tiles; ++t) {
-                const int dt = a.dt_lo + j0 + t * reps_p;
-                for (int kb = 0; kb < a.n_kb; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1u);
-                    const uint32_t full_leader = mapa_cluster(smem_u32(&full[stage]), 0);
-                    if (leader) mbar_expect_tx(&full[stage], (uint32_t)(2 * TC2_B_KB_BYTES));
-                    else mbar_arrive_remote(full_leader);
-                    tma_load_2d_pair(&tmap_c_half, full_leader, sB + stage * TC2_B_KB_BYTES, kb * TC_BK,
-                                     dt * TC_BN + (int)rank * (TC_BN / 2));
-                    if (++stage == TC2_STAGES) { stage = 0; phase ^= 1u; }
+            for (int p = 0; p < a.n_parts; ++p) {
+                int qt = 0, j0 = 0, reps_p = 1;
+                const int n_tiles = part_geometry(p, qt, j0, reps_p);
+                if (n_tiles == 0) continue;
+                if (served > 0) mbar_wait(qfree, (uint32_t)((served - 1) & 1));     // the previous part's MMAs are done with sQ
+                if (leader) mbar_expect_tx(qfull, (uint32_t)(2 * a.n_kb * TC_Q_KB_BYTES));
+                else mbar_arrive_remote(qfull_leader);
+                for (int kb = 0; kb < a.n_kb; ++kb)
+                    tma_load_2d_pair(&tmap_q, qfull_leader, sQ + kb * TC_Q_KB_BYTES, kb * TC_BK, qt * TC_BM);
+                ++served;
+                for (int t = 0; t < n_tiles; ++t) {
+                    const int dt = a.dt_lo + j0 + t * reps_p;
+                    for (int kb = 0; kb < a.n_kb; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1u);
+                        const uint32_t full_leader = mapa_cluster(smem_u32(&full[stage]), 0);
+                        if (leader) mbar_expect_tx(&full[stage], (uint32_t)(2 * TC2_B_KB_BYTES));
+                        else mbar_arrive_remote(full_leader);
+                        tma_load_2d_pair(&tmap_c_half, full_leader, sB + stage * TC2_B_KB_BYTES, kb * TC_BK,
+                                         dt * TC_BN + (int)rank * (TC_BN / 2));
+                        if (++stage == TC2_STAGES) { stage = 0; phase ^= 1u; }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: one thread of the LEADER CTA issues for the pair =====
-        if (leader && lane == 0 && n_tiles > 0) {
-            mbar_wait(qfull, 0u);
-            tc_fence_after();
-            int stage = 0;
+        if (leader && lane == 0) {
+            int stage = 0, served = 0, tt = 0;
             uint32_t phase = 0;
-            for (int t = 0; t < n_tiles; ++t) {
-                const int as = t & 1;
-                const uint32_t aphase = (uint32_t)((t >> 1) & 1);
-                mbar_wait(&tempty[as], aphase ^ 1u);       // both epilogues have drained this accumulator
+            for (int p = 0; p < a.n_parts; ++p) {
+                int qt = 0, j0 = 0, reps_p = 1;
+                const int n_tiles = part_geometry(p, qt, j0, reps_p);
+                if (n_tiles == 0) continue;
+                mbar_wait(qfull, (uint32_t)(served & 1));
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_BN);
-                for (int kb = 0; kb < a.n_kb; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                ++served;
+                for (int t = 0; t < n_tiles; ++t, ++tt) {
+                    const int as = tt & 1;
+                    const uint32_t aphase = (uint32_t)((tt >> 1) & 1);
+                    mbar_wait(&tempty[as], aphase ^ 1u);       // both epilogues have drained this accumulator
                     tc_fence_after();
-                    const uint64_t da = umma_desc_sw128(sQ + kb * TC_Q_KB_BYTES);
-                    const uint64_t db = umma_desc_sw128(sB + stage * TC2_B_KB_BYTES);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_BN);
+                    for (int kb = 0; kb < a.n_kb; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint64_t da = umma_desc_sw128(sQ + kb * TC_Q_KB_BYTES);
+                        const uint64_t db = umma_desc_sw128(sB + stage * TC2_B_KB_BYTES);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k)
-                        umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kInstrDescPair, (uint32_t)((kb | k) != 0));
-                    umma_commit_pair(&empty[stage]);
-                    if (++stage == TC2_STAGES) { stage = 0; phase ^= 1u; }
+                        for (int k = 0; k < TC_BK / 16; ++k)
+                            umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kInstrDescPair, (uint32_t)((kb | k) != 0));
+                        umma_commit_pair(&empty[stage]);
+                        if (++stage == TC2_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    umma_commit_pair(&tfull[as]);
                 }
-                umma_commit_pair(&tfull[as]);
+                umma_commit_pair(qfree);                      // every MMA that reads this part's queries has retired
             }
         }
     } else if (warp >= 4) {
         // ===== epilogue (both CTAs): identical to tc_filter_kernel, the drain signal goes to the leader =====
         const int ew = (warp - 4) & 3;
         const int half = (warp - 4) >> 2;
-        const int q = qt * TC_BM + ew * 32 + lane;
-        const bool active = q < a.B;
-        const float tau = active ? a.tau[q] : INFINITY;
-        const int sub = j0 * 2 + half;
-        unsigned long long* my_keys = a.cand_keys + ((size_t)(active ? q : 0) * a.n_sub + sub) * a.cap_sub;
-        unsigned cnt = 0;
         const unsigned cap = (unsigned)a.cap_sub;
         const uint32_t tempty_leader0 = mapa_cluster(smem_u32(&tempty[0]), 0);
-        for (int t = 0; t < n_tiles; ++t) {
-            const int as = t & 1;
-            const uint32_t aphase = (uint32_t)((t >> 1) & 1);
-            const int dt = a.dt_lo + j0 + t * reps_p;
-            const long long doc_base = (long long)dt * TC_BN;
-            const uint32_t doc_base_u = (uint32_t)doc_base;
-            const int n_valid = (int)min((long long)TC_BN, a.n_docs - doc_base);
-            mbar_wait(&tfull[as], aphase);
-            tc_fence_after();
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * TC_BN + half * (TC_BN / 2));
+        int tt = 0;
+        for (int p = 0; p < a.n_parts; ++p) {
+            int qt = 0, j0 = 0, reps_p = 1;
+            const int n_tiles = part_geometry(p, qt, j0, reps_p);
+            if (n_tiles == 0) continue;
+            const int q = qt * TC_BM + ew * 32 + lane;
+            const bool active = q < a.B;
+            const float tau = active ? a.tau[q] : INFINITY;
+            const int sub = j0 * 2 + half;
+            unsigned long long* my_keys = a.cand_keys + ((size_t)(active ? q : 0) * a.n_sub + sub) * a.cap_sub;
+            unsigned cnt = 0;
+            for (int t = 0; t < n_tiles; ++t, ++tt) {
+                const int as = tt & 1;
+                const uint32_t aphase = (uint32_t)((tt >> 1) & 1);
+                const int dt = a.dt_lo + j0 + t * reps_p;
+                const long long doc_base = (long long)dt * TC_BN;
+                const uint32_t doc_base_u = (uint32_t)doc_base;
+                const int n_valid = (int)min((long long)TC_BN, a.n_docs - doc_base);
+                mbar_wait(&tfull[as], aphase);
+                tc_fence_after();
+                const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * TC_BN + half * (TC_BN / 2));
 #pragma unroll 1
-            for (int chunk = 0; chunk < TC_BN / 64; chunk += 2) {
-                uint32_t v[2][32];
-                tmem_ld_x32(taddr0 + (uint32_t)(chunk * 32), v[0]);
-                tmem_ld_x32(taddr0 + (uint32_t)(chunk * 32 + 32), v[1]);
-                tmem_ld_wait();
+                for (int chunk = 0; chunk < TC_BN / 64; chunk += 2) {
+                    uint32_t v[2][32];
+                    tmem_ld_x32(taddr0 + (uint32_t)(chunk * 32), v[0]);
+                    tmem_ld_x32(taddr0 + (uint32_t)(chunk * 32 + 32), v[1]);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float m8[4];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float m = __uint_as_float(v[h][8 * g]);
-#pragma unroll
-                        for (int e = 1; e < 8; ++e) m = fmaxf(m, __uint_as_float(v[h][8 * g + e]));
-                        m8[g] = m;
-                    }
-                    const float m32 = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
-                    if (active && m32 >= tau) {
-                        const int c0 = half * (TC_BN / 2) + (chunk + h) * 32;
+                    for (int h = 0; h < 2; ++h) {
+                        float m8[4];
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
-                            if (m8[g] >= tau) {
+                            float m = __uint_as_float(v[h][8 * g]);
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    const uint32_t sb = v[h][8 * g + e];
-                                    const int col = c0 + 8 * g + e;
-                                    const bool pass = __uint_as_float(sb) >= tau && col < n_valid;
-                                    st_pred_v2(my_keys + cnt, sb, doc_base_u + (uint32_t)col, pass && cnt < cap);
-                                    cnt += pass ? 1u : 0u;
+                            for (int e = 1; e < 8; ++e) m = fmaxf(m, __uint_as_float(v[h][8 * g + e]));
+                            m8[g] = m;
+                        }
+                        const float m32 = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+                        if (active && m32 >= tau) {
+                            const int c0 = half * (TC_BN / 2) + (chunk + h) * 32;
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                if (m8[g] >= tau) {
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) {
+                                        const uint32_t sb = v[h][8 * g + e];
+                                        const int col = c0 + 8 * g + e;
+                                        const bool pass = __uint_as_float(sb) >= tau && col < n_valid;
+                                        st_pred_v2(my_keys + cnt, sb, doc_base_u + (uint32_t)col, pass && cnt < cap);
+                                        cnt += pass ? 1u : 0u;
+                                    }
                                 }
                             }
                         }
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(tempty_leader0 + (uint32_t)(as * 8));
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote(tempty_leader0 + (uint32_t)(as * 8));
+            if (active) a.cand_cnt[(size_t)q * a.n_sub + sub] = cnt;
         }
-        if (active) a.cand_cnt[(size_t)q * a.n_sub + sub] = cnt;
     }
     tc_fence_before();
     cluster_sync_all();                                   // both CTAs are done with TMEM and with each other's barriers
@@ -1344,9 +1372,11 @@ int rr_tc_dense_topk(rr_tc_state** state, const rr_index_desc* d, int sm_count, 
             }
             {
                 RrProfScope prof(RR_PROF_TC_FILTER, s);
-                if (use_pair)
-                    tc_filter_pair_kernel<<<grid, TC_THREADS, tc2_smem_total(pair_stages), s>>>(tmap_q, st->tmap_c_half, a);
-                else
+                if (use_pair) {
+                    int grid_pair = 0;             // persistent over the parts: CTA c serves part 0, then part 1, ...
+                    for (int p = 0; p < best_parts; ++p) grid_pair = std::max(grid_pair, a.part_ctas[p]);
+                    tc_filter_pair_kernel<<<grid_pair, TC_THREADS, tc2_smem_total(pair_stages), s>>>(tmap_q, st->tmap_c_half, a);
+                } else
                     tc_filter_kernel<<<grid, TC_THREADS, TC_SMEM_TOTAL, s>>>(tmap_q, st->tmap_c, a);
             }
             RR_LAUNCH_CHECK();

@@ -100,3 +100,31 @@ def test_dict_based_oracle_agrees_on_strings():
     want = bm.get_scores(["t4", "t18", "t4", "t61"])
     np.testing.assert_allclose(got, want, rtol=BM25_RTOL)
     ix.close()
+
+
+def test_fp32_accumulation_error_bound_is_pinned():
+    """rank_bm25 adds float64 terms and the callers cast once to float32; K1 / K1c add the correctly rounded fp32
+    of every term in fp32, in query-token order.  The deviation is bounded by ~(L + 1) * 2^-24 relative -- far inside
+    north_star's 1e-5 -- and K1c equals K1 bit for bit.  16-term queries (configs[3] shape) over a Zipf corpus."""
+    import torch
+    rr = _rr()
+    n, v, l = 60_000, 4000, 16
+    offs, toks = rr.synth.corpus_tokens(n, v)
+    csr = BM25OkapiCSR(offs, toks, v)
+    ix = _index(offs, toks, v, tile=12288)
+    qt = rr.synth.query_terms(8, l, offs, toks, v).astype(np.int32)
+    nt = np.full(8, l, dtype=np.int32)
+    got = ix.bm25_get_scores(qt, nt).cpu().numpy().astype(np.float64)
+    worst = 0.0
+    for i in range(8):
+        want = csr.get_scores(qt[i].tolist())
+        nz = want != 0
+        worst = max(worst, float(np.max(np.abs(got[i][nz] - want[nz]) / want[nz])))
+        assert np.array_equal(got[i] == 0, want == 0)
+    bound = (l + 1) * 2.0 ** -24
+    print(f"max relative deviation from the float64 sum: {worst:.3e} (bound {bound:.3e})")
+    assert worst <= bound
+    cand = torch.randint(0, n, (8, 150), device="cuda", dtype=torch.int64)
+    full = ix.bm25_get_scores(qt, nt)
+    assert torch.equal(ix.bm25_candidates(qt, nt, cand), torch.gather(full, 1, cand))
+    ix.close()

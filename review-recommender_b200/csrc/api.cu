@@ -322,7 +322,7 @@ static int dense_topk_locked(rr_index* ix, const float* d_q, int32_t B, int32_t 
         if (!rr_tc_supported(ix->cc_major, ix->cc_minor))
             return rr_fail(RR_EUNSUPPORTED, "tensor path needs an sm_100 device (found sm_%d%d)", ix->cc_major, ix->cc_minor);
         // the tensor path takes at most 8 x SM query tiles per call: very large batches go through in slices
-        const int32_t slice = 65536;
+        static const int32_t slice = getenv("RR_TC_MAX_BATCH") && atoi(getenv("RR_TC_MAX_BATCH")) >= 128 ? atoi(getenv("RR_TC_MAX_BATCH")) : 65536;
         for (int32_t b0 = 0; b0 < B; b0 += slice) {
             const int32_t nb = std::min(slice, B - b0);
             RR_TRY(rr_tc_dense_topk(&ix->tc, &ix->d, ix->sm_count, d_q + (int64_t)b0 * ix->d.dim, nb, pool,

@@ -136,3 +136,60 @@ def test_batches_in_flight_on_two_handles_equal_the_synchronous_search():
         assert torch.equal(r0, r1) and torch.equal(f0, f1)
     lanes[1][0].close()
     ix.close()
+
+
+def test_small_host_batches_replay_a_graph_with_fresh_inputs():
+    """rr_hybrid_search_host, B <= 8 on the exact path: the second call with a shape captures a CUDA graph and later calls
+    replay it.  Every call must see ITS inputs (the graph reads the handle's staging buffers) and return what the plain
+    path returns; interleaving shapes (B = 1, 3, 1) and fusion parameters keeps separate graphs."""
+    import os
+    rr = _rr()
+    n, d, v = 6000, 64, 900
+    c = rr.synth.make_corpus(n, d, v)
+    q = rr.synth.queries(40, d)
+    qt = rr.synth.query_terms(40, 4, c.doc_offsets, c.token_ids, v).astype(np.int32)
+    fa = rr.engine.Fusion(k=10, rerank_k=0, w_rerank=0.0, w_best=0.0)
+    fb = rr.engine.Fusion(k=7, rerank_k=0, w_dense=0.3, w_bm25=0.5, w_rerank=0.0, w_best=0.0, driver="cli")
+    plan = [(i, 1, fa) for i in range(6)] + [(6, 3, fa), (9, 1, fb), (10, 3, fa), (13, 1, fb), (14, 1, fa), (15, 3, fb), (18, 3, fb)]
+    results = {}
+    for graphs in (True, False):
+        if graphs:
+            os.environ.pop("RR_NO_GRAPHS", None)
+        else:
+            os.environ["RR_NO_GRAPHS"] = "1"
+        try:
+            ix = rr.engine.HybridIndex(c.emb, c.doc_offsets, c.token_ids, v, c.n_reviews, c.avg_stars)
+            out = []
+            for i0, b, f in plan:
+                rr.engine.launch_count(reset=True)
+                r, s = ix.hybrid_search_host(q[i0:i0 + b], qt[i0:i0 + b], np.full(b, 4, dtype=np.int32), f)
+                out.append((r.copy(), s.copy(), rr.engine.launch_count()))
+            results[graphs] = out
+            ix.close()
+        finally:
+            os.environ.pop("RR_NO_GRAPHS", None)
+    for (r1, s1, l1), (r0, s0, l0) in zip(results[True], results[False]):
+        np.testing.assert_array_equal(r1, r0)
+        np.testing.assert_array_equal(s1, s0)
+    assert results[True][5][2] == 1 and results[False][5][2] > 1, "the sixth identical-shape call must be one graph launch"
+
+
+def test_tensor_path_slices_very_large_batches(monkeypatch):
+    """AUTO / TENSOR mode must not reject a batch that exceeds what one tensor-path call takes: it goes through
+    in slices (RR_TC_MAX_BATCH shrinks the slice so that a 600-query batch needs three)."""
+    monkeypatch.setenv("RR_TC_MAX_BATCH", "256")
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import numpy as np, review_recommender_b200 as rr
+        emb = rr.synth.embeddings(70_000, 128); q = rr.synth.queries(600, 128)
+        ix = rr.engine.HybridIndex(emb)
+        i2, s2, c2 = ix.dense_topk(q, 50, rr._lib.RR_DENSE_TENSOR)
+        assert ix.dense_stats()["path"] == 2
+        i1, s1, c1 = ix.dense_topk(q, 50, rr._lib.RR_DENSE_EXACT)
+        assert (i1 == i2).all() and (s1 == s2).all() and (c1 == c2).all()
+        print("sliced ok")
+    """)
+    import os
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ), capture_output=True, text=True, timeout=300,
+                       cwd=str(__import__("pathlib").Path(__file__).resolve().parent.parent))
+    assert r.returncode == 0 and "sliced ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -561,7 +561,11 @@ int rr_launch_bm25_tile_scores(const rr_index_desc* d, const int32_t* d_terms, c
         RR_CUDA(cudaFuncSetAttribute(bm25_tile_scores_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         optin.done(smem, dev);
     }
-    if (B < 8) d_rtab = nullptr;          // small batches: the CTAs search their own rare-list bounds (one launch less)
+    // tiny batches may let the CTAs search their own rare-list bounds (one launch less), RR_BM25_PREPASS_MIN_B sets from which
+    // batch size the pre-pass runs.  Default 1 = always: with the persistent kernel the producer warp resolves the bounds one
+    // item ahead, and ~5 rare terms x 2 searches x 3 dependent round trips per item made it the bottleneck at B = 1
+    static const int prepass_min_b = env_int("RR_BM25_PREPASS_MIN_B", 1, 1, 1 << 20);
+    if (B < prepass_min_b) d_rtab = nullptr;
     if (d_rtab != nullptr) {
         const long long total = (long long)B * l_max * (d->n_tiles + 1);
         RrProfScope prof(RR_PROF_MISC, stream);

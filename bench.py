@@ -69,7 +69,8 @@ def parse_args():
     ap.add_argument("--in-flight", type=int, default=0,
                     help="batches in flight (2 = consecutive steps alternate between two handles / CUDA streams over the "
                          "same index, so one step's latency-bound tail -- selection, exchange, host wait -- runs under the next "
-                         "step's GEMM).  0 = auto: 1 on a single GPU (power-capped GEMM: measured +0.6 %), 2 on several")
+                         "step's GEMM).  0 = auto: 1 on a single GPU (power-capped GEMM: measured +0.6 %), 3 on several (r02, 8 GPUs: "
+                         "3.57 / 3.65 / 3.44 ms per step with 1 / 2 / 3 in flight on one box, 3.50 / 3.445 with 1 / 2 on another)")
     ap.add_argument("--synth", default="recipe", choices=["recipe", "device", "clustered"],
                     help="recipe = the SURVEY 8d NumPy recipe, generated per 1 M-row chunk on the host (default; the only "
                          "mode with id_parity); device = same distributions drawn with torch generators in HBM (fast set-up "
@@ -571,7 +572,7 @@ def main():
     if Q < 1 or world % Q:
         raise SystemExit("--query-groups must divide the number of GPUs")
     if args.in_flight <= 0:
-        args.in_flight = 2 if (world > 1 and Q == 1) else 1
+        args.in_flight = 3 if (world > 1 and Q == 1) else 1
     searcher = rr.dist.GridSearcher(None, Q, lanes=args.in_flight if Q == 1 else 1) if world > 1 else None   # creates the process sub-groups (collective)
     qg, shard, R = rr.dist.GridSearcher.layout(rank, world, Q)
     row0 = N * shard // R

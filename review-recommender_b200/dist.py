@@ -108,6 +108,27 @@ def local_pool(pool: int, world: int) -> int:
     return min(pool, max(16, m))
 
 
+class _NoStream:
+    """Stands in for a CUDA stream / event when the index lives on the CPU (protocol tests with gloo and a stub index)."""
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def synchronize(self):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+
+def _on_cuda(ix) -> bool:
+    dev = getattr(ix, "device", None)
+    return dev is not None and torch.device(dev).type == "cuda"
+
+
 class _Lane:
     """One batch in flight: its own handle over the shared index tensors (own scratch), its own stream, buffers."""
 
@@ -136,7 +157,8 @@ class PendingShardedSearch:
         nf = int(idx.numel())
         self.repeated = self.s.last_repeated = nf
         lane, G = self.lane, self.s.world
-        with torch.cuda.stream(lane.stream):
+        cuda = not isinstance(lane.stream, _NoStream)
+        with (torch.cuda.stream(lane.stream) if cuda else lane.stream):
             if nf > 0:
                 # a shard may hold more pool members than it sent, or could not certify its tensor-path result:
                 # repeat those queries with m = pool through the synchronous entry points (always exact)
@@ -153,10 +175,11 @@ class PendingShardedSearch:
                 self.rows[idx[:nf]] = r2[:nf]
                 self.final[idx[:nf]] = f2[:nf]
                 lane.stream.synchronize()
-        cur = torch.cuda.current_stream()
-        if cur != lane.stream:
-            self.rows.record_stream(cur)
-            self.final.record_stream(cur)
+        if cuda:
+            cur = torch.cuda.current_stream()
+            if cur != lane.stream:
+                self.rows.record_stream(cur)
+                self.final.record_stream(cur)
         return self.rows, self.final
 
 
@@ -194,7 +217,7 @@ class ShardedSearcher:
 
     def _lane_list(self):
         if self._lanes is None or self._lanes[0].ix is not self.ix:
-            if self.n_lanes == 1:
+            if self.n_lanes == 1 or not _on_cuda(self.ix):
                 lanes = [_Lane(self.ix, None)]                  # runs on the caller's current stream
             else:
                 # every lane has its own stream, so the caller's stream stays free for the next batch's ingest
@@ -260,6 +283,12 @@ class ShardedSearcher:
         lanes = self._lane_list()
         lane = lanes[self._next % len(lanes)]
         self._next += 1
+        if not _on_cuda(lane.ix):
+            # host-side protocol run (stub index): same rounds, nothing asynchronous
+            run = _Lane(lane.ix, _NoStream())
+            rows, final, flags = self._round(run, q, term_ids, n_terms, fusion, mode, m, deferred=True)
+            lane.flags_host = flags.clone()
+            return PendingShardedSearch(self, run, (q, term_ids, n_terms, fusion, mode), rows, final, lane.flags_host, _NoStream())
         cur = torch.cuda.current_stream()
         if lane.stream is None:
             lane_stream = cur

@@ -300,6 +300,10 @@ int rr_best_review_scores(const float* d_rev_emb, const int64_t* d_rev_range, in
 int rr_normalize_rows(const float* d_in, int64_t n_rows, int32_t dim, float* d_out_f32, uint16_t* d_out_bf16,
                       int32_t dim_pad, float* d_norms, int device, rr_stream);
 
+/* max over the rows of ||row||_2 into *d_out (device float): rr_index_desc.max_row_norm, the scale of the tensor path's
+ * bf16 error bound.  (~1 for the reference's unit-norm Vn, app/app_product_search.py:110.) */
+int rr_max_row_norm(const float* d_in, int64_t n_rows, int32_t dim, float* d_out, int device, rr_stream);
+
 /* The bf16 copy alone (rows already normalised by the caller): round-to-nearest-even, zero padding. */
 int rr_bf16_rows(const float* d_in, int64_t n_rows, int32_t dim, uint16_t* d_out_bf16, int32_t dim_pad,
                  int device, rr_stream);

@@ -90,6 +90,7 @@ SIGNATURES = {
     "rr_bm25_gpu_build_finish": (C.c_int, [_P, _P, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rr_bm25_gpu_build_free": (None, [_P]),
     "rr_normalize_rows": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, C.c_int32, _P, C.c_int, _P]),
+    "rr_max_row_norm": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int, _P]),
     "rr_bf16_rows": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int, _P]),
     "rr_gate_factors": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_double,
                                   _P, _P, C.c_int, _P]),

@@ -461,6 +461,14 @@ extern "C" int rr_normalize_rows(const float* d_in, int64_t n_rows, int32_t dim,
                                     static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int rr_max_row_norm(const float* d_in, int64_t n_rows, int32_t dim, float* d_out, int device, rr_stream stream) {
+    if (!d_in || !d_out || n_rows < 0 || dim <= 0) return rr_fail(RR_EINVAL, "rr_max_row_norm: bad argument");
+    RR_CUDA(cudaSetDevice(device));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    return rr_launch_max_row_norm(d_in, n_rows, dim, d_out, sms, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int rr_bf16_rows(const float* d_in, int64_t n_rows, int32_t dim, uint16_t* d_out_bf16, int32_t dim_pad,
                             int device, rr_stream stream) {
     if (!d_in || !d_out_bf16 || n_rows < 0 || dim <= 0 || dim_pad < dim || dim_pad % 64)

@@ -125,6 +125,31 @@ bf16_rows_kernel(const float* __restrict__ in, long long n_rows, int D, __nv_bfl
 
 }  // namespace
 
+// max over the rows of ||row||_2 (the bf16 error bound of the tensor path scales with it): one warp per row, float
+// accumulation, atomicMax on the (non-negative) float bits.  *d_out must be zeroed by the caller.
+__global__ void __launch_bounds__(256)
+max_row_norm_kernel(const float* __restrict__ x, long long n_rows, int D, unsigned* __restrict__ out_bits) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    float best = 0.f;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {
+        float ss = 0.f;
+        for (int d = lane; d < D; d += 32) { const float v = x[r * D + d]; ss = fmaf(v, v, ss); }
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        best = fmaxf(best, sqrtf(ss));
+    }
+    if (lane == 0 && best > 0.f) atomicMax(out_bits, __float_as_uint(best));
+}
+
+int rr_launch_max_row_norm(const float* d_in, int64_t n_rows, int D, float* d_out, int sm_count, cudaStream_t stream) {
+    RR_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float), stream));
+    if (n_rows <= 0) return RR_OK;
+    RrProfScope prof(RR_PROF_MISC, stream);
+    max_row_norm_kernel<<<sm_count * 8, 256, 0, stream>>>(d_in, (long long)n_rows, D, reinterpret_cast<unsigned*>(d_out));
+    RR_LAUNCH_CHECK();
+    return RR_OK;
+}
+
 int rr_launch_bf16_rows(const float* d_in, int64_t n_rows, int D, uint16_t* d_out, int dim_pad, int sm_count,
                         cudaStream_t stream) {
     if (n_rows <= 0) return RR_OK;

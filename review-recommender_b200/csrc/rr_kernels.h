@@ -35,6 +35,7 @@ int rr_launch_best_review(const float* d_rev_emb, const int64_t* d_rev_range, in
 int rr_launch_normalize_rows(const float* d_in, int64_t n_rows, int D, float* d_out_f32, uint16_t* d_out_bf16,
                              int dim_pad, float* d_norms, cudaStream_t stream);
 
+int rr_launch_max_row_norm(const float* d_in, int64_t n_rows, int D, float* d_out, int sm_count, cudaStream_t stream);
 int rr_launch_bf16_rows(const float* d_in, int64_t n_rows, int D, uint16_t* d_out, int dim_pad, int sm_count,
                         cudaStream_t stream);
 

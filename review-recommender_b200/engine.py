@@ -302,7 +302,11 @@ class HybridIndex:
         if share is not None:
             self.emb_bf16, self.dim_pad, self.max_row_norm = share.emb_bf16, share.dim_pad, share.max_row_norm
         else:
-            self.max_row_norm = float(torch.linalg.vector_norm(self.emb, dim=1).max().item()) if self.n_docs else 0.0
+            self.max_row_norm = 0.0
+            if self.n_docs:
+                mx = torch.empty(1, dtype=torch.float32, device=self.device)
+                check(self.lib.rr_max_row_norm(_ptr(self.emb), self.n_docs, self.dim, _ptr(mx), self.device.index or 0, _stream()))
+                self.max_row_norm = float(mx.item()) * (1.0 + 1e-6)      # float accumulation slack: the bound must not be low
         if make_bf16 and self.emb_bf16 is None:
             self.dim_pad = (self.dim + 63) // 64 * 64
             bf = torch.empty((self.n_docs, self.dim_pad), dtype=torch.bfloat16, device=self.device)

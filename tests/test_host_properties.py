@@ -54,3 +54,27 @@ def test_flatten_corpus_equals_the_dict_walk(corpus):
     np.testing.assert_array_equal(o1, o2)
     np.testing.assert_array_equal(i1, i2.astype(np.int32) if len(i2) else i1)
     assert list(v1.keys()) == v2
+
+
+def test_synthetic_recipe_is_pinned():
+    """The SURVEY 8d recipe (rr.synth) decides the benchmark corpus, the queries and hence bench.py's `result_digest`, which
+    must be identical for every GPU count and every round: a digest of recipe samples guards against drift."""
+    import hashlib
+    import numpy as np
+    import review_recommender_b200 as rr
+    s = rr.synth
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(s.embeddings(2000, 384)[::97]).tobytes())
+    offs, toks = s.corpus_tokens(3000, 50000)
+    h.update(offs.tobytes())
+    h.update(toks.tobytes())
+    nr, av = s.metadata(3000)
+    h.update(nr.tobytes())
+    h.update(av.tobytes())
+    h.update(s.queries(64, 384).tobytes())
+    h.update(s.query_terms(64, 4, offs, toks, 50000).tobytes())
+    assert h.hexdigest() == "51d2ae0ec74a291c033ed77129101e59c208a6776ff59bafac551eb831039612"
+    # rows of a shard are the same rows whichever rank generates them
+    a = s.embeddings(700, 16, row0=1_999_800)
+    b = s.embeddings(400, 16, row0=2_000_000)
+    np.testing.assert_array_equal(a[200:600], b)

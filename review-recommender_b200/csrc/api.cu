@@ -297,7 +297,7 @@ static int dense_exact_locked(rr_index* ix, const float* d_q, int32_t B, int32_t
     chunk = std::min(chunk, B);
     if (chunk > 8) chunk = chunk / 8 * 8;
     RR_TRY(ix->scores.ensure(sizeof(float) * (size_t)ld * chunk));
-    RR_TRY(ix->select.ensure(rr_exact_scratch_bytes(chunk, std::min<int64_t>(pool, n))));
+    RR_TRY(ix->select.ensure(rr_exact_scratch_bytes(chunk, (int)std::min<int64_t>(pool, n), n, ix->sm_count)));
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = std::min(chunk, B - b0);
         RR_TRY(rr_launch_dense_scores_f32(ix->d.d_emb_f32, n, ix->d.dim, d_q + (int64_t)b0 * ix->d.dim, nb,

@@ -26,7 +26,7 @@ namespace {
 
 constexpr int QB = 8;              // queries per CTA in the GEMV kernel
 constexpr int GEMV_THREADS = 256;  // 8 warps
-constexpr int GEMV_ROWS = 2;       // rows per warp iteration
+constexpr int GEMV_ROWS = 4;       // rows per warp iteration
 
 __device__ __forceinline__ float warp_xor_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 16);
@@ -35,6 +35,38 @@ __device__ __forceinline__ float warp_xor_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     return v;
+}
+
+// warp_xor_sum of NQ values per lane (NQ = 1, 2, 4, 8) with 9 shuffles instead of 40 for NQ = 8: at the offsets 16, 8, 4
+// a lane keeps one half of its values and trades the other half with its xor partner, so every value still receives
+// exactly the additions of the butterfly (own + partner's, offsets 16, 8, 4, 2, 1 in that order) and the sums are
+// bit-identical to warp_xor_sum.  On return v[0] is the sum of value `b` (the return value) on the lanes that own it;
+// -1 on the other lanes.
+template <int NQ>
+__device__ __forceinline__ int warp_xor_sum_multi(float (&v)[NQ], int lane) {
+    int b = 0, width = NQ;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        if (width > 1) {
+            const int h = width >> 1;
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < NQ / 2; ++i) {
+                if (i < h) {
+                    const float send = up ? v[i] : v[i + h];
+                    const float keep = up ? v[i + h] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            b = b * 2 + (up ? 1 : 0);
+            width = h;
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+        }
+    }
+    // NQ = 8: offsets 16, 8, 4 chose the value, every lane of a group of 4 holds the same sum; one of them reports it
+    constexpr int group = 32 / NQ;
+    return (lane & (group - 1)) == 0 ? b : -1;
 }
 
 __device__ __forceinline__ float4 ldg_row16(const float4* p) {
@@ -73,17 +105,20 @@ __device__ __forceinline__ float lane_partial_scalar(const float* __restrict__ r
     return acc;
 }
 
-// scores[b, row] for b in [0, nq), all rows.  Queries of the CTA's group live in smem.
-template <bool VEC4>
+// scores[b, row] for b in [0, nq), all rows.  Queries of the CTA's group live in smem.  NQ = queries per CTA (8 for
+// batches; 1 / 2 / 4 for the single-query calls of the Streamlit app, where 8 accumulators per row would spend 8x the
+// FMAs, shared-memory reads and shuffles and the registers that limit the loads in flight), ROWS = corpus rows a warp
+// has in flight.  The per-(row, query) arithmetic is canonical_dot for every instantiation.
+template <bool VEC4, int NQ, int ROWS>
 __global__ void __launch_bounds__(GEMV_THREADS)
 dense_scores_f32_kernel(const float* __restrict__ emb, long long n_rows, int D,
                         const float* __restrict__ queries, int n_queries,
                         float* __restrict__ scores, long long ld_scores) {
-    extern __shared__ __align__(16) float s_q[];   // [QB][Dp]
+    extern __shared__ __align__(16) float s_q[];   // [NQ][Dp]
     const int Dp = (D + 3) & ~3;
-    const int q0 = blockIdx.y * QB;
-    const int nq = min(QB, n_queries - q0);
-    for (int i = threadIdx.x; i < QB * Dp; i += GEMV_THREADS) {
+    const int q0 = blockIdx.y * NQ;
+    const int nq = min(NQ, n_queries - q0);
+    for (int i = threadIdx.x; i < NQ * Dp; i += GEMV_THREADS) {
         const int b = i / Dp, d = i - b * Dp;
         s_q[i] = (b < nq && d < D) ? queries[(long long)(q0 + b) * D + d] : 0.f;
     }
@@ -95,24 +130,25 @@ dense_scores_f32_kernel(const float* __restrict__ emb, long long n_rows, int D,
 
     if constexpr (VEC4) {
         const int n_chunks = D >> 2;
-        for (long long r0 = gw * GEMV_ROWS; r0 < n_rows; r0 += warps_total * GEMV_ROWS) {
-            float acc[GEMV_ROWS][QB];
+        for (long long r0 = gw * ROWS; r0 < n_rows; r0 += warps_total * ROWS) {
+            float acc[ROWS][NQ];
 #pragma unroll
-            for (int rr = 0; rr < GEMV_ROWS; ++rr)
+            for (int rr = 0; rr < ROWS; ++rr)
 #pragma unroll
-                for (int b = 0; b < QB; ++b) acc[rr][b] = 0.f;
+                for (int b = 0; b < NQ; ++b) acc[rr][b] = 0.f;
+#pragma unroll 3
             for (int c = lane; c < n_chunks; c += 32) {
-                float4 m[GEMV_ROWS];
+                float4 m[ROWS];
 #pragma unroll
-                for (int rr = 0; rr < GEMV_ROWS; ++rr) {
+                for (int rr = 0; rr < ROWS; ++rr) {
                     const long long r = min(r0 + rr, n_rows - 1);
                     m[rr] = ldg_row16(reinterpret_cast<const float4*>(emb + r * D) + c);
                 }
 #pragma unroll
-                for (int b = 0; b < QB; ++b) {
+                for (int b = 0; b < NQ; ++b) {
                     const float4 x = reinterpret_cast<const float4*>(s_q + b * Dp)[c];
 #pragma unroll
-                    for (int rr = 0; rr < GEMV_ROWS; ++rr) {
+                    for (int rr = 0; rr < ROWS; ++rr) {
                         float a = acc[rr][b];
                         a = fmaf(x.x, m[rr].x, a);
                         a = fmaf(x.y, m[rr].y, a);
@@ -123,13 +159,10 @@ dense_scores_f32_kernel(const float* __restrict__ emb, long long n_rows, int D,
                 }
             }
 #pragma unroll
-            for (int rr = 0; rr < GEMV_ROWS; ++rr) {
+            for (int rr = 0; rr < ROWS; ++rr) {
                 const long long r = r0 + rr;
-#pragma unroll
-                for (int b = 0; b < QB; ++b) {
-                    const float s = warp_xor_sum(acc[rr][b]);
-                    if (lane == b && b < nq && r < n_rows) scores[(long long)(q0 + b) * ld_scores + r] = s;
-                }
+                const int b = warp_xor_sum_multi<NQ>(acc[rr], lane);
+                if (b >= 0 && b < nq && r < n_rows) scores[(long long)(q0 + b) * ld_scores + r] = acc[rr][0];
             }
         }
     } else {
@@ -385,31 +418,34 @@ sort_keys_kernel(const unsigned long long* __restrict__ keys, int k_cap, const R
 }
 
 // ---------------------------------------------------------------------------------------------
-// Small score rows (n <= 16384, the single-query shape of the Streamlit app): ONE kernel per call instead of the
-// 15-launch radix pipeline above.  One CTA per row: all n composite keys go to shared memory, an MSB-first radix
-// select (8-bit digits, shared-memory histogram, early exit) finds the k-th key, the k survivors are compacted and
-// bitonic-sorted, indices / scores are written in (score desc, row asc) order.
+// Short score rows and small batches: top-k inside shared memory instead of the 15-launch radix pipeline above.
+//   n <= 16384 (the single-query shape of the Streamlit app): ONE kernel, one CTA per row (topk_small_kernel);
+//   longer rows, at most TC_MAX_ROWS queries, k <= 1024: a tree of the same step (topk_chunk_kernel) -- every CTA takes a
+//   chunk of <= 16384 scores and keeps its k largest composite keys, the next level does the same over the surviving
+//   keys, the last level (one CTA per row) sorts: 2 launches up to ~1.7 M rows at k = 150, 3 beyond.
+// The step: all keys of the chunk go to shared memory, an MSB-first radix select (8-bit digits, shared-memory histogram,
+// early exit) finds the k-th key, the k survivors are compacted; the final level bitonic-sorts them and writes indices /
+// scores in (score desc, row asc) order.  The top-k of the union of per-chunk top-k lists is the top-k of the row, and the
+// composite keys are unique, so the result is the radix pipeline's bit for bit.
 // ---------------------------------------------------------------------------------------------
 constexpr int TS_MAX_N = 16384;
 constexpr int TS_THREADS = 512;
+constexpr int TC_MAX_ROWS = 8;
+constexpr int TC_MAX_K = 1024;
 
-__global__ void __launch_bounds__(TS_THREADS)
-topk_small_kernel(const float* __restrict__ scores, long long ld, int n, int k, long long* __restrict__ out_idx,
-                  float* __restrict__ out_score, int32_t* __restrict__ out_count, int out_ld, int k_pad) {
-    extern __shared__ unsigned long long ts_keys[];            // [n] keys, then [k_pad] survivors
-    unsigned long long* sel = ts_keys + n;
+// The kk largest of the n keys in shared memory -> sel[0, kk) (unordered), sel[kk, k_pad) = 0.  Keys are unique except for
+// 0 ("empty"), and kk <= the number of non-zero keys.  Called by all TS_THREADS threads; the keys may have been written
+// just before the call (the first barrier orders them); sel is complete for every thread on return.
+__device__ __forceinline__ void cta_select_keys(const unsigned long long* keys, int n, int kk, unsigned long long* sel,
+                                                int k_pad) {
     __shared__ unsigned s_hist[256];
     __shared__ unsigned long long s_prefix;
     __shared__ int s_bits, s_krem, s_done, s_out;
-    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    const float* src = scores + (long long)row * ld;
-    for (int i = tid; i < n; i += TS_THREADS) {
-        unsigned long long key = rr_make_key(src[i], (uint32_t)i);
-        ts_keys[i] = key ? key : 1ull;
-    }
-    const int kk = min(k, n);
+    const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) { s_bits = 0; s_prefix = 0ull; s_krem = kk; s_done = kk >= n ? 1 : 0; s_out = 0; }
+    for (int i = tid; i < k_pad; i += TS_THREADS) sel[i] = 0ull;
     __syncthreads();
+    if (kk <= 0) return;
     for (int pass = 0; pass < 8; ++pass) {
         if (s_done) break;
         const int bits = s_bits;
@@ -418,7 +454,7 @@ topk_small_kernel(const float* __restrict__ scores, long long ld, int n, int k, 
         __syncthreads();
         const int shift = 64 - bits - 8;
         for (int i = tid; i < n; i += TS_THREADS) {
-            const unsigned long long key = ts_keys[i];
+            const unsigned long long key = keys[i];
             if (bits == 0 || (key >> (64 - bits)) == prefix) atomicAdd(&s_hist[(unsigned)((key >> shift) & 0xFFu)], 1u);
         }
         __syncthreads();
@@ -446,13 +482,11 @@ topk_small_kernel(const float* __restrict__ scores, long long ld, int n, int k, 
     // survivors: every key whose top `bits` bits are >= the pivot prefix (exactly kk of them)
     const int bits = s_bits;
     const unsigned long long prefix = s_prefix;
-    for (int i = tid; i < k_pad; i += TS_THREADS) sel[i] = 0ull;
-    __syncthreads();
     for (int i0 = 0; i0 < n; i0 += TS_THREADS) {
         const int i = i0 + tid;
         bool take = false;
         unsigned long long key = 0ull;
-        if (i < n) { key = ts_keys[i]; take = bits == 0 || (key >> (64 - bits)) >= prefix; }
+        if (i < n) { key = keys[i]; take = bits == 0 || (key >> (64 - bits)) >= prefix; }
         const unsigned m = __ballot_sync(0xffffffffu, take);
         int base = 0;
         if (lane == 0 && m) base = atomicAdd(&s_out, __popc(m));
@@ -463,6 +497,14 @@ topk_small_kernel(const float* __restrict__ scores, long long ld, int n, int k, 
         }
     }
     __syncthreads();
+}
+
+// sel[0, k_pad) sorted descending (k_pad a power of two), the first kk written as (index, score); the rest of the k output
+// slots are -1 / -inf
+__device__ __forceinline__ void cta_sort_and_write(unsigned long long* sel, int k_pad, int k, int kk, int row,
+                                                   long long* __restrict__ out_idx, float* __restrict__ out_score,
+                                                   int32_t* __restrict__ out_count, int out_ld) {
+    const int tid = threadIdx.x;
     for (int size = 2; size <= k_pad; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int i = tid; i < k_pad / 2; i += TS_THREADS) {
@@ -487,38 +529,138 @@ topk_small_kernel(const float* __restrict__ scores, long long ld, int n, int k, 
     if (tid == 0 && out_count) out_count[row] = kk;
 }
 
+__global__ void __launch_bounds__(TS_THREADS)
+topk_small_kernel(const float* __restrict__ scores, long long ld, int n, int k, long long* __restrict__ out_idx,
+                  float* __restrict__ out_score, int32_t* __restrict__ out_count, int out_ld, int k_pad) {
+    extern __shared__ unsigned long long ts_keys[];            // [n] keys, then [k_pad] survivors
+    unsigned long long* sel = ts_keys + n;
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const float* src = scores + (long long)row * ld;
+    for (int i = tid; i < n; i += TS_THREADS) {
+        unsigned long long key = rr_make_key(src[i], (uint32_t)i);
+        ts_keys[i] = key ? key : 1ull;
+    }
+    const int kk = min(k, n);
+    cta_select_keys(ts_keys, n, kk, sel, k_pad);
+    cta_sort_and_write(sel, k_pad, k, kk, row, out_idx, out_score, out_count, out_ld);
+}
+
+// One level of the tree.  grid = (chunks of the row, rows).  FROM_KEYS: the source is the previous level's key array
+// (0 = empty slot), else the score row itself.  FINAL (one chunk per row): sort and write the result; otherwise the chunk's
+// survivors go to out_keys[row][chunk][k] (unordered, zero-padded).
+template <bool FROM_KEYS, bool FINAL>
+__global__ void __launch_bounds__(TS_THREADS)
+topk_chunk_kernel(const float* __restrict__ scores, const unsigned long long* __restrict__ in_keys, long long ld, long long n,
+                  int chunk, int k, unsigned long long* __restrict__ out_keys, long long out_ld,
+                  long long* __restrict__ out_idx, float* __restrict__ out_score, int32_t* __restrict__ out_count,
+                  int out_ld2, int k_pad) {
+    extern __shared__ unsigned long long ts_keys[];            // [chunk] keys, then [k_pad] survivors
+    unsigned long long* sel = ts_keys + chunk;
+    __shared__ int s_valid;
+    const int row = blockIdx.y, tid = threadIdx.x;
+    const long long lo = (long long)blockIdx.x * chunk;
+    const int n_loc = (int)min((long long)chunk, n - lo);
+    int valid = n_loc;
+    if (FROM_KEYS) {
+        if (tid == 0) s_valid = 0;
+        __syncthreads();
+        const unsigned long long* src = in_keys + (long long)row * ld + lo;
+        int nz = 0;
+        for (int i = tid; i < n_loc; i += TS_THREADS) {
+            const unsigned long long key = src[i];
+            ts_keys[i] = key;
+            nz += key != 0ull;
+        }
+        for (int o = 16; o > 0; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+        if ((tid & 31) == 0 && nz) atomicAdd(&s_valid, nz);
+        __syncthreads();
+        valid = s_valid;
+    } else {
+        const float* src = scores + (long long)row * ld + lo;
+        for (int i = tid; i < n_loc; i += TS_THREADS) {
+            const unsigned long long key = rr_make_key(src[i], (uint32_t)(lo + i));
+            ts_keys[i] = key ? key : 1ull;
+        }
+    }
+    const int kk = min(k, valid);
+    cta_select_keys(ts_keys, n_loc, kk, sel, k_pad);
+    if (FINAL) {
+        cta_sort_and_write(sel, k_pad, k, kk, row, out_idx, out_score, out_count, out_ld2);
+    } else {
+        unsigned long long* dst = out_keys + (long long)row * out_ld + (long long)blockIdx.x * k;
+        for (int i = tid; i < k; i += TS_THREADS) dst[i] = sel[i];
+    }
+}
+
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 }  // namespace
 
-size_t rr_exact_scratch_bytes(int rows, int k) {
-    return sizeof(RsRow) * (size_t)rows + sizeof(unsigned) * (size_t)rows * RS_BINS +
-           sizeof(unsigned long long) * (size_t)rows * (size_t)k + 256;
+// Levels of the shared-memory top-k tree for rows of n scores (see topk_chunk_kernel): chunk[l] source elements per CTA,
+// groups[l] CTAs per row; the last level has one group.  False when the tree does not apply.
+struct ChunkPlan { int levels; int chunk[12]; int groups[12]; };
+
+static bool plan_chunked_topk(int64_t n, int rows, int k, int sm_count, ChunkPlan* p) {
+    if (n <= TS_MAX_N || rows > TC_MAX_ROWS || k > TC_MAX_K || k < 1 || k >= n || n > (int64_t)1 << 31) return false;
+    if (getenv("RR_NO_CHUNKED_TOPK")) return false;
+    // level 0: enough chunks to fill the SMs, few enough that their survivors fit ONE final CTA when the row allows it
+    const int64_t fit = std::max<int64_t>(1, TS_MAX_N / k);                 // chunks whose k survivors fit one CTA
+    int64_t c = std::max((n + std::max(sm_count, 1) - 1) / std::max(sm_count, 1), (n + fit - 1) / fit);
+    c = std::min<int64_t>(TS_MAX_N, std::max<int64_t>(2048, (c + 1023) / 1024 * 1024));
+    int l = 0;
+    int64_t cur = n;
+    p->chunk[l] = (int)c; p->groups[l] = (int)((cur + c - 1) / c); cur = (int64_t)p->groups[l] * k; ++l;
+    while (cur > TS_MAX_N) {
+        if (l >= 10) return false;
+        p->chunk[l] = TS_MAX_N; p->groups[l] = (int)((cur + TS_MAX_N - 1) / TS_MAX_N); cur = (int64_t)p->groups[l] * k; ++l;
+    }
+    p->chunk[l] = (int)cur; p->groups[l] = 1; ++l;
+    p->levels = l;
+    return true;
+}
+
+size_t rr_exact_scratch_bytes(int rows, int k, int64_t n, int sm_count) {
+    size_t bytes = sizeof(RsRow) * (size_t)rows + sizeof(unsigned) * (size_t)rows * RS_BINS +
+                   sizeof(unsigned long long) * (size_t)rows * (size_t)k + 256;
+    ChunkPlan p;
+    const int tree_rows = std::min(rows, TC_MAX_ROWS);         // the last slice of a larger batch may take the tree
+    if (plan_chunked_topk(n, tree_rows, k, sm_count, &p)) {
+        // two key arrays used alternately: level 0's survivors and level 1's
+        const size_t a = (size_t)p.groups[0] * k, b = p.levels > 2 ? (size_t)p.groups[1] * k : 0;
+        bytes = std::max(bytes, sizeof(unsigned long long) * (size_t)tree_rows * (a + b) + 256);
+    }
+    return bytes;
+}
+
+template <bool VEC4, int NQ, int ROWS>
+static int launch_gemv(const float* d_emb, int64_t n_rows, int D, const float* d_q, int n_queries, float* d_scores,
+                       int64_t ld_scores, int sm_count, cudaStream_t stream) {
+    const int Dp = (D + 3) & ~3;
+    const size_t smem = sizeof(float) * (size_t)NQ * Dp;
+    const int warps_per_cta = GEMV_THREADS / 32;
+    const long long want = (n_rows + (long long)warps_per_cta * ROWS - 1) / ((long long)warps_per_cta * ROWS);
+    const int groups = (n_queries + NQ - 1) / NQ;
+    const long long cap = (long long)sm_count * 8;
+    dim3 grid((unsigned)max(1ll, min(want, cap)), (unsigned)groups);
+    if (smem > 48 * 1024)
+        RR_CUDA(cudaFuncSetAttribute(dense_scores_f32_kernel<VEC4, NQ, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RrProfScope prof(RR_PROF_DENSE_GEMV, stream);
+    dense_scores_f32_kernel<VEC4, NQ, ROWS><<<grid, GEMV_THREADS, smem, stream>>>(d_emb, n_rows, D, d_q, n_queries, d_scores, ld_scores);
+    RR_LAUNCH_CHECK();
+    return RR_OK;
 }
 
 int rr_launch_dense_scores_f32(const float* d_emb, int64_t n_rows, int D, const float* d_q, int n_queries,
                                float* d_scores, int64_t ld_scores, int sm_count, cudaStream_t stream) {
     if (n_queries <= 0 || n_rows <= 0) return RR_OK;
-    const int Dp = (D + 3) & ~3;
-    const size_t smem = sizeof(float) * (size_t)QB * Dp;
     const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_emb) & 15) == 0);
-    const int warps_per_cta = GEMV_THREADS / 32;
-    long long want = (n_rows + (long long)warps_per_cta * GEMV_ROWS - 1) / ((long long)warps_per_cta * GEMV_ROWS);
-    const int groups = (n_queries + QB - 1) / QB;
-    long long cap = (long long)sm_count * 8;
-    unsigned gx = (unsigned)max(1ll, min(want, cap));
-    dim3 grid(gx, (unsigned)groups);
-    if (smem > 48 * 1024) {
-        RR_CUDA(cudaFuncSetAttribute(dense_scores_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RR_CUDA(cudaFuncSetAttribute(dense_scores_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    RrProfScope prof(RR_PROF_DENSE_GEMV, stream);
-    if (vec4)
-        dense_scores_f32_kernel<true><<<grid, GEMV_THREADS, smem, stream>>>(d_emb, n_rows, D, d_q, n_queries, d_scores, ld_scores);
-    else
-        dense_scores_f32_kernel<false><<<grid, GEMV_THREADS, smem, stream>>>(d_emb, n_rows, D, d_q, n_queries, d_scores, ld_scores);
-    RR_LAUNCH_CHECK();
-    return RR_OK;
+    if (!vec4) return launch_gemv<false, QB, 1>(d_emb, n_rows, D, d_q, n_queries, d_scores, ld_scores, sm_count, stream);
+    // RR_GEMV_WIDE=1: the 8-query kernel for every batch size (A/B switch of the narrow instantiations)
+    if (n_queries > 4 || getenv("RR_GEMV_WIDE"))
+        return launch_gemv<true, QB, GEMV_ROWS>(d_emb, n_rows, D, d_q, n_queries, d_scores, ld_scores, sm_count, stream);
+    if (n_queries > 2) return launch_gemv<true, 4, 4>(d_emb, n_rows, D, d_q, n_queries, d_scores, ld_scores, sm_count, stream);
+    if (n_queries > 1) return launch_gemv<true, 2, 4>(d_emb, n_rows, D, d_q, n_queries, d_scores, ld_scores, sm_count, stream);
+    return launch_gemv<true, 1, 4>(d_emb, n_rows, D, d_q, n_queries, d_scores, ld_scores, sm_count, stream);
 }
 
 int rr_launch_rescore(const float* d_emb, int64_t n_rows, int D, const float* d_q, const int64_t* d_rows,
@@ -584,6 +726,46 @@ int rr_launch_topk_rows(const float* d_scores, int64_t ld, int64_t n, int rows, 
         topk_small_kernel<<<rows, TS_THREADS, smem, stream>>>(d_scores, ld, (int)n, k, reinterpret_cast<long long*>(d_idx), d_score,
                                                             d_count, out_ld, k_pad);
         RR_LAUNCH_CHECK();
+        return RR_OK;
+    }
+    ChunkPlan plan;
+    if (plan_chunked_topk(n, rows, k, sm_count, &plan)) {
+        const int k_pad = max(2, next_pow2(k));
+        static RrSmemOptIn optin;
+        int dev = 0;
+        const size_t smem_max = sizeof(unsigned long long) * ((size_t)TS_MAX_N + TC_MAX_K);
+        if (optin.needed(smem_max, &dev)) {
+            RR_CUDA(cudaFuncSetAttribute(topk_chunk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+            RR_CUDA(cudaFuncSetAttribute(topk_chunk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+            RR_CUDA(cudaFuncSetAttribute(topk_chunk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+            optin.done(smem_max, dev);
+        }
+        unsigned long long* buf[2];
+        buf[0] = static_cast<unsigned long long*>(d_scratch);
+        buf[1] = buf[0] + (size_t)rows * plan.groups[0] * k;
+        RrProfScope prof(RR_PROF_SELECT_ROWS, stream);
+        long long cur_n = n;
+        const unsigned long long* src = nullptr;
+        for (int l = 0; l < plan.levels; ++l) {
+            const int chunk = plan.chunk[l], groups = plan.groups[l];
+            const size_t smem = sizeof(unsigned long long) * ((size_t)chunk + k_pad);
+            const dim3 grid((unsigned)groups, (unsigned)rows);
+            unsigned long long* dst = buf[l & 1];
+            const long long keys_ld = (long long)groups * k;
+            if (l == 0)
+                topk_chunk_kernel<false, false><<<grid, TS_THREADS, smem, stream>>>(
+                    d_scores, nullptr, ld, cur_n, chunk, k, dst, keys_ld, nullptr, nullptr, nullptr, 0, k_pad);
+            else if (l + 1 < plan.levels)
+                topk_chunk_kernel<true, false><<<grid, TS_THREADS, smem, stream>>>(
+                    nullptr, src, cur_n, cur_n, chunk, k, dst, keys_ld, nullptr, nullptr, nullptr, 0, k_pad);
+            else
+                topk_chunk_kernel<true, true><<<grid, TS_THREADS, smem, stream>>>(
+                    nullptr, src, cur_n, cur_n, chunk, k, nullptr, 0, reinterpret_cast<long long*>(d_idx), d_score, d_count,
+                    out_ld, k_pad);
+            RR_LAUNCH_CHECK();
+            src = dst;
+            cur_n = keys_ld;
+        }
         return RR_OK;
     }
     char* p = static_cast<char*>(d_scratch);

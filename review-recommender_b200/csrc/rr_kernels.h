@@ -18,7 +18,7 @@ int rr_launch_bm25_candidates(const rr_index_desc* d, int V, const int32_t* d_te
                               const int32_t* d_uncertified = nullptr);
 
 // dense_exact.cu
-size_t rr_exact_scratch_bytes(int rows, int k);
+size_t rr_exact_scratch_bytes(int rows, int k, int64_t n, int sm_count);
 int rr_launch_dense_scores_f32(const float* d_emb, int64_t n_rows, int D, const float* d_q, int n_queries,
                                float* d_scores, int64_t ld_scores, int sm_count, cudaStream_t stream);
 int rr_launch_rescore(const float* d_emb, int64_t n_rows, int D, const float* d_q, const int64_t* d_rows,

@@ -65,3 +65,37 @@ def test_ties_and_duplicates_are_ordered_by_row():
     np.testing.assert_array_equal(idx9.cpu().numpy()[8], idx)
     np.testing.assert_array_equal(sims9.cpu().numpy()[8], sims.cpu().numpy()[0])
     ix.close()
+
+
+@pytest.mark.parametrize("n,d,b,k", [(16_385, 16, 1, 150), (200_000, 16, 1, 150), (200_000, 16, 8, 1024), (150_000, 8, 3, 1),
+                                      (2_500_000, 8, 2, 150),         # three levels: 153 chunks -> 2 -> 1
+                                      (1_200_000, 8, 1, 1000)])       # 74 chunks x 1000 survivors -> 5 -> 1
+def test_topk_tree_equals_the_radix_pipeline(n, d, b, k, monkeypatch):
+    """Small batches over long rows select through the shared-memory top-k tree (topk_chunk_kernel); RR_NO_CHUNKED_TOPK=1
+    sends the same scores through the radix-select pipeline.  Same rows, same similarities, same order -- also with rows
+    that tie across chunk borders."""
+    rr = _rr()
+    emb = rr.synth.embeddings(n, d)
+    q = rr.synth.queries(b, d)
+    for r in (3, 16_384, n // 2, n - 1):                 # copies of the best row of query 0, spread over the chunks
+        emb[r] = q[0] / np.linalg.norm(q[0])
+    ix = rr.engine.HybridIndex(emb, device="cuda:0", make_bf16=False)
+    out = {}
+    for tree in (True, False):
+        if tree:
+            monkeypatch.delenv("RR_NO_CHUNKED_TOPK", raising=False)
+        else:
+            monkeypatch.setenv("RR_NO_CHUNKED_TOPK", "1")
+        rr.engine.launch_count(reset=True)
+        idx, sims, cnt = ix.dense_topk(q, k, rr._lib.RR_DENSE_EXACT)
+        out[tree] = (idx.cpu().numpy(), sims.cpu().numpy(), cnt.cpu().numpy(), rr.engine.launch_count())
+    np.testing.assert_array_equal(out[True][0], out[False][0])
+    np.testing.assert_array_equal(out[True][1], out[False][1])
+    np.testing.assert_array_equal(out[True][2], out[False][2])
+    assert out[True][3] + 8 <= out[False][3], "the tree must replace the 15-launch pipeline by 2-4 launches"
+    twins = sorted({3, 16_384, n // 2, n - 1})
+    assert list(out[True][0][0][:min(k, len(twins))]) == twins[:min(k, len(twins))]
+    ref_idx, ref_sims = cosine_topk_canonical(q[b - 1], emb, k)
+    np.testing.assert_allclose(out[True][1][b - 1], ref_sims, rtol=0, atol=DENSE_ATOL)
+    assert_ids_match_modulo_ties(out[True][0][b - 1], out[True][1][b - 1], ref_idx, ref_sims, 2 * DENSE_ATOL)
+    ix.close()

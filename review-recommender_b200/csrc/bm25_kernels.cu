@@ -530,6 +530,84 @@ bm25_candidates_kernel(const uint2* __restrict__ postings, const uint64_t* __res
     if (dense_out) *at(dense_out, oid) = dense_in[gid];
 }
 
+
+// The same gather for SMALL batches (a single query of the Streamlit app: 150 candidates), forward index only: one WARP per
+// candidate.  The lanes read the document's whole {term, impact} list at once (one memory round trip instead of the ~6
+// dependent probes per term of a binary search), every query term is matched by a ballot, and the impacts found are added
+// in query-term order -- the additions of bm25_candidates_kernel, bit for bit (a term that is absent adds +0.0f to a sum
+// that is never -0).
+__global__ void __launch_bounds__(256)
+bm25_candidates_warp_kernel(const unsigned long long* __restrict__ fwd_off, const uint2* __restrict__ fwd_data, int V,
+                            long long n_docs, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_len,
+                            int l_max, const long long* __restrict__ cand, int pool, int B,
+                            const double* __restrict__ n_reviews, const double* __restrict__ avg_stars, long long row_offset,
+                            float* __restrict__ bm25_out, double* __restrict__ n_out, double* __restrict__ avg_out,
+                            long long* __restrict__ grow_out, int pack_bg, long long pack_stride,
+                            const float* __restrict__ dense_in, float* __restrict__ dense_out,
+                            const int* __restrict__ uncertified) {
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gid >= (long long)B * pool) return;                  // warp-uniform
+    const int q = (int)(gid / pool);
+    long long oid = gid;
+    long long shift = 0;
+    if (pack_bg > 0) {
+        const int g = q / pack_bg;
+        oid = (long long)(q - g * pack_bg) * pool + (gid - (long long)q * pool);
+        shift = (long long)g * pack_stride;
+    }
+    auto at = [shift](auto* base, long long i) {
+        using T = std::remove_pointer_t<decltype(base)>;
+        return reinterpret_cast<T*>(reinterpret_cast<char*>(base) + shift) + i;
+    };
+    const long long doc = cand[gid];
+    const bool valid = doc >= 0 && doc < n_docs;
+    // metadata loads go out before the list is walked
+    double nrev = 0.0, avg = __longlong_as_double(0x7FF8000000000000ll);
+    if (lane == 0 && valid) {
+        if (n_reviews) nrev = n_reviews[doc];
+        if (avg_stars) avg = avg_stars[doc];
+    }
+    float sum = 0.f;
+    if (valid && V > 0 && q_terms != nullptr) {
+        const unsigned long long f0 = fwd_off[doc], f1 = fwd_off[doc + 1];
+        const uint2* list = fwd_data + f0;
+        const int n = (int)(f1 - f0);
+        int L = q_len[q];
+        if (L > l_max) L = l_max;
+        for (int l0 = 0; l0 < L; l0 += 32) {                 // query terms in blocks of 32: lane j owns term l0 + j
+            const int nl = min(32, L - l0);
+            int my_term = -1;
+            if (lane < nl) {
+                my_term = q_terms[(long long)q * l_max + l0 + lane];
+                if (my_term >= V) my_term = -1;
+            }
+            float my_impact = 0.f;
+            for (int c0 = 0; c0 < n; c0 += 32) {
+                uint2 e = make_uint2(0xFFFFFFFFu, 0u);
+                if (c0 + lane < n) e = __ldg(&list[c0 + lane]);
+                for (int l = 0; l < nl; ++l) {
+                    const int t = __shfl_sync(0xffffffffu, my_term, l);
+                    if (t < 0) continue;
+                    const unsigned hit = __ballot_sync(0xffffffffu, e.x == (uint32_t)t);
+                    if (hit) {
+                        const float imp = __uint_as_float(__shfl_sync(0xffffffffu, e.y, __ffs(hit) - 1));
+                        if (lane == l) my_impact = imp;
+                    }
+                }
+            }
+            for (int l = 0; l < nl; ++l) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, my_impact, l));
+        }
+    }
+    if (lane != 0) return;
+    if (bm25_out) *at(bm25_out, oid) = sum;
+    if (n_out) *at(n_out, oid) = (valid && n_reviews) ? nrev : 0.0;
+    if (avg_out) *at(avg_out, oid) = avg;
+    const bool poisoned = uncertified != nullptr && uncertified[q] != 0;
+    if (grow_out) *at(grow_out, oid) = poisoned ? -2 : (valid ? row_offset + doc : -1);
+    if (dense_out) *at(dense_out, oid) = dense_in[gid];
+}
+
 }  // namespace
 
 size_t rr_bm25_rtab_bytes(int B, int l_max, int n_tiles) {
@@ -624,6 +702,19 @@ int rr_launch_bm25_candidates(const rr_index_desc* d, int V, const int32_t* d_te
     if (total <= 0) return RR_OK;
     const int threads = 256;
     RrProfScope prof(RR_PROF_BM25_CAND, stream);
+    // small batches (the latency path): one warp per candidate over the forward index; RR_BM25_CAND_WARP=0 disables
+    const char* warp_env = getenv("RR_BM25_CAND_WARP");
+    const bool warp_ok = !(warp_env && atoi(warp_env) == 0);
+    if (warp_ok && total <= 8192 && d->d_fwd_off != nullptr && d->d_fwd_data != nullptr) {
+        const unsigned blocks_w = (unsigned)((total * 32 + threads - 1) / threads);
+        bm25_candidates_warp_kernel<<<blocks_w, threads, 0, stream>>>(
+            reinterpret_cast<const unsigned long long*>(d->d_fwd_off), reinterpret_cast<const uint2*>(d->d_fwd_data), V,
+            (long long)d->n_docs, d_terms, d_nterms, l_max, reinterpret_cast<const long long*>(d_cand), pool, B,
+            d->d_n_reviews, d->d_avg_stars, (long long)d->row_offset, d_bm25, d_n_out, d_avg_out,
+            reinterpret_cast<long long*>(d_grow_out), pack_bg, (long long)pack_stride, d_dense_in, d_dense_out, d_uncertified);
+        RR_LAUNCH_CHECK();
+        return RR_OK;
+    }
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
     bm25_candidates_kernel<<<blocks, threads, 0, stream>>>(
         reinterpret_cast<const uint2*>(d->d_postings), d->d_tile_base, d->d_dir, d->d_term_slot,

@@ -421,21 +421,26 @@ sort_keys_kernel(const unsigned long long* __restrict__ keys, int k_cap, const R
 // Short score rows and small batches: top-k inside shared memory instead of the 15-launch radix pipeline above.
 //   n <= 16384 (the single-query shape of the Streamlit app): ONE kernel, one CTA per row (topk_small_kernel);
 //   longer rows, at most TC_MAX_ROWS queries, k <= 1024: a tree of the same step (topk_chunk_kernel) -- every CTA takes a
-//   chunk of <= 16384 scores and keeps its k largest composite keys, the next level does the same over the surviving
-//   keys, the last level (one CTA per row) sorts: 2 launches up to ~1.7 M rows at k = 150, 3 beyond.
+//   chunk of <= 4096 scores and keeps its k largest composite keys, the next level does the same over the surviving
+//   keys, the last level (one CTA per row, <= 8192 keys) sorts: 2 launches up to ~220 k rows at k = 150, 3 up to ~12 M.
 // The step: all keys of the chunk go to shared memory, an MSB-first radix select (8-bit digits, shared-memory histogram,
 // early exit) finds the k-th key, the k survivors are compacted; the final level bitonic-sorts them and writes indices /
 // scores in (score desc, row asc) order.  The top-k of the union of per-chunk top-k lists is the top-k of the row, and the
 // composite keys are unique, so the result is the radix pipeline's bit for bit.
 // ---------------------------------------------------------------------------------------------
 constexpr int TS_MAX_N = 16384;
-constexpr int TS_THREADS = 512;
+constexpr int TS_THREADS = 1024;         // 32 warps: the select is a chain of short dependent phases, more warps hide their latency
 constexpr int TC_MAX_ROWS = 8;
 constexpr int TC_MAX_K = 1024;
 
 // The kk largest of the n keys in shared memory -> sel[0, kk) (unordered), sel[kk, k_pad) = 0.  Keys are unique except for
 // 0 ("empty"), and kk <= the number of non-zero keys.  Called by all TS_THREADS threads; the keys may have been written
 // just before the call (the first barrier orders them); sel is complete for every thread on return.
+// EXACT = false (the caller sorts sel and takes the first kk): the digit passes stop as soon as the keys at or above the
+// pivot bucket fit sel -- kk <= survivors <= k_pad, typically after 2 of the 4 score-digit passes.
+// The first pass sees the sign and the high exponent bits, which nearly all keys share: its histogram is built with one
+// shared-memory atomic per distinct digit of a warp (match.any) instead of 32 serialised ones on one address.
+template <bool EXACT>
 __device__ __forceinline__ void cta_select_keys(const unsigned long long* keys, int n, int kk, unsigned long long* sel,
                                                 int k_pad) {
     __shared__ unsigned s_hist[256];
@@ -453,9 +458,21 @@ __device__ __forceinline__ void cta_select_keys(const unsigned long long* keys, 
         if (tid < 256) s_hist[tid] = 0u;
         __syncthreads();
         const int shift = 64 - bits - 8;
-        for (int i = tid; i < n; i += TS_THREADS) {
-            const unsigned long long key = keys[i];
-            if (bits == 0 || (key >> (64 - bits)) == prefix) atomicAdd(&s_hist[(unsigned)((key >> shift) & 0xFFu)], 1u);
+        if (bits == 0) {
+            for (int i0 = 0; i0 < n; i0 += TS_THREADS) {
+                const int i = i0 + tid;
+                const unsigned live = __ballot_sync(0xffffffffu, i < n);
+                if (i < n) {
+                    const unsigned digit = (unsigned)(keys[i] >> 56);
+                    const unsigned peers = __match_any_sync(live, digit);
+                    if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], (unsigned)__popc(peers));
+                }
+            }
+        } else {
+            for (int i = tid; i < n; i += TS_THREADS) {
+                const unsigned long long key = keys[i];
+                if ((key >> (64 - bits)) == prefix) atomicAdd(&s_hist[(unsigned)((key >> shift) & 0xFFu)], 1u);
+            }
         }
         __syncthreads();
         if (tid < 32) {
@@ -474,12 +491,13 @@ __device__ __forceinline__ void cta_select_keys(const unsigned long long* keys, 
                 s_krem = (int)(krem - above);
                 s_prefix = (prefix << 8) | (unsigned long long)(255 - (lane * 8 + j));
                 s_bits = bits + 8;
-                if (loc[j] == krem - above || bits + 8 >= 64) s_done = 1;
+                const unsigned rem = krem - above;              // still wanted from the pivot bucket, which holds loc[j]
+                if (loc[j] == rem || bits + 8 >= 64 || (!EXACT && (unsigned)kk - rem + loc[j] <= (unsigned)k_pad)) s_done = 1;
             }
         }
         __syncthreads();
     }
-    // survivors: every key whose top `bits` bits are >= the pivot prefix (exactly kk of them)
+    // survivors: every key whose top `bits` bits are >= the pivot prefix (exactly kk of them; EXACT = false: kk .. k_pad)
     const int bits = s_bits;
     const unsigned long long prefix = s_prefix;
     for (int i0 = 0; i0 < n; i0 += TS_THREADS) {
@@ -505,16 +523,34 @@ __device__ __forceinline__ void cta_sort_and_write(unsigned long long* sel, int 
                                                    long long* __restrict__ out_idx, float* __restrict__ out_score,
                                                    int32_t* __restrict__ out_count, int out_ld) {
     const int tid = threadIdx.x;
-    for (int size = 2; size <= k_pad; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = tid; i < k_pad / 2; i += TS_THREADS) {
-                const int lo = 2 * i - (i & (stride - 1));
-                const int hi = lo + stride;
-                const bool desc = ((lo & size) == 0);
-                const unsigned long long a = sel[lo], b = sel[hi];
-                if ((a < b) == desc) { sel[lo] = b; sel[hi] = a; }
+    if (k_pad <= 256) {
+        // rank sort: a thread counts the keys above its own (the empty slots, all 0, by position) -- two barriers instead
+        // of the 36 steps of the bitonic network
+        unsigned long long mine = 0ull;
+        int rank = 0;
+        if (tid < k_pad) {
+            mine = sel[tid];
+#pragma unroll 8
+            for (int j = 0; j < k_pad; ++j) {
+                const unsigned long long o = sel[j];
+                rank += (o > mine || (o == mine && j < tid)) ? 1 : 0;
             }
-            __syncthreads();
+        }
+        __syncthreads();
+        if (tid < k_pad) sel[rank] = mine;
+        __syncthreads();
+    } else {
+        for (int size = 2; size <= k_pad; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = tid; i < k_pad / 2; i += TS_THREADS) {
+                    const int lo = 2 * i - (i & (stride - 1));
+                    const int hi = lo + stride;
+                    const bool desc = ((lo & size) == 0);
+                    const unsigned long long a = sel[lo], b = sel[hi];
+                    if ((a < b) == desc) { sel[lo] = b; sel[hi] = a; }
+                }
+                __syncthreads();
+            }
         }
     }
     for (int i = tid; i < k; i += TS_THREADS) {
@@ -541,7 +577,7 @@ topk_small_kernel(const float* __restrict__ scores, long long ld, int n, int k, 
         ts_keys[i] = key ? key : 1ull;
     }
     const int kk = min(k, n);
-    cta_select_keys(ts_keys, n, kk, sel, k_pad);
+    cta_select_keys<false>(ts_keys, n, kk, sel, k_pad);
     cta_sort_and_write(sel, k_pad, k, kk, row, out_idx, out_score, out_count, out_ld);
 }
 
@@ -583,7 +619,7 @@ topk_chunk_kernel(const float* __restrict__ scores, const unsigned long long* __
         }
     }
     const int kk = min(k, valid);
-    cta_select_keys(ts_keys, n_loc, kk, sel, k_pad);
+    cta_select_keys<!FINAL>(ts_keys, n_loc, kk, sel, k_pad);
     if (FINAL) {
         cta_sort_and_write(sel, k_pad, k, kk, row, out_idx, out_score, out_count, out_ld2);
     } else {
@@ -600,19 +636,34 @@ int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 // groups[l] CTAs per row; the last level has one group.  False when the tree does not apply.
 struct ChunkPlan { int levels; int chunk[12]; int groups[12]; };
 
+static int topk_env(const char* name, int dflt, int lo, int hi) {
+    const char* e = getenv(name);
+    if (!e) return dflt;
+    const int v = atoi(e);
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
 static bool plan_chunked_topk(int64_t n, int rows, int k, int sm_count, ChunkPlan* p) {
-    if (n <= TS_MAX_N || rows > TC_MAX_ROWS || k > TC_MAX_K || k < 1 || k >= n || n > (int64_t)1 << 31) return false;
+    // rows up to tree_min_n go through the one-kernel top-k; a level-0 CTA takes at most chunk_max scores, a middle level
+    // mid_chunk keys, the last level (one CTA per row) at most final_max keys.  Defaults from the r02 sweep at B = 1
+    // (profiles/r02_exact_path_gemv_topk.txt): 4096 / 8192 / 8192 -> 27 us at 100 k rows, 38 us at 1 M (16384 each: 31 / 46)
+    const int tree_min_n = topk_env("RR_TOPK_TREE_MIN_N", TS_MAX_N, 1024, TS_MAX_N);
+    if (n <= tree_min_n || rows > TC_MAX_ROWS || k > TC_MAX_K || k < 1 || k >= n || n > (int64_t)1 << 31) return false;
     if (getenv("RR_NO_CHUNKED_TOPK")) return false;
+    const int two_k = (2 * k + 1023) / 1024 * 1024;
+    const int chunk_max = std::max(two_k, topk_env("RR_TOPK_CHUNK_MAX", 4096, 1024, TS_MAX_N));
+    const int mid_chunk = std::max(two_k, topk_env("RR_TOPK_MID_CHUNK", 8192, 1024, TS_MAX_N));
+    const int final_max = std::max(two_k, topk_env("RR_TOPK_FINAL_MAX", 8192, 1024, TS_MAX_N));
     // level 0: enough chunks to fill the SMs, few enough that their survivors fit ONE final CTA when the row allows it
-    const int64_t fit = std::max<int64_t>(1, TS_MAX_N / k);                 // chunks whose k survivors fit one CTA
+    const int64_t fit = std::max<int64_t>(1, final_max / k);                // chunks whose k survivors fit the last level
     int64_t c = std::max((n + std::max(sm_count, 1) - 1) / std::max(sm_count, 1), (n + fit - 1) / fit);
-    c = std::min<int64_t>(TS_MAX_N, std::max<int64_t>(2048, (c + 1023) / 1024 * 1024));
+    c = std::min<int64_t>(chunk_max, std::max<int64_t>(1024, (c + 1023) / 1024 * 1024));
     int l = 0;
     int64_t cur = n;
     p->chunk[l] = (int)c; p->groups[l] = (int)((cur + c - 1) / c); cur = (int64_t)p->groups[l] * k; ++l;
-    while (cur > TS_MAX_N) {
+    while (cur > final_max) {                       // every middle level at least halves the keys (mid_chunk >= 2 k)
         if (l >= 10) return false;
-        p->chunk[l] = TS_MAX_N; p->groups[l] = (int)((cur + TS_MAX_N - 1) / TS_MAX_N); cur = (int64_t)p->groups[l] * k; ++l;
+        p->chunk[l] = mid_chunk; p->groups[l] = (int)((cur + mid_chunk - 1) / mid_chunk); cur = (int64_t)p->groups[l] * k; ++l;
     }
     p->chunk[l] = (int)cur; p->groups[l] = 1; ++l;
     p->levels = l;
@@ -711,7 +762,9 @@ int rr_launch_topk_rows(const float* d_scores, int64_t ld, int64_t n, int rows, 
     if (rows <= 0) return RR_OK;
     if (k > 8192) return rr_fail(RR_EINVAL, "top-k larger than 8192 is not supported");
     const int kk = (int)(k < n ? (int64_t)k : n);
-    if (n <= TS_MAX_N && n > 0 && !getenv("RR_NO_SMALL_TOPK")) {
+    ChunkPlan plan;
+    const bool tree = plan_chunked_topk(n, rows, k, sm_count, &plan);
+    if (!tree && n <= TS_MAX_N && n > 0 && !getenv("RR_NO_SMALL_TOPK")) {
         // single kernel per call for short rows (configs[0]: 10 k products)
         const int k_pad = max(2, next_pow2(max(kk, 1)));
         const size_t smem = sizeof(unsigned long long) * ((size_t)n + k_pad);
@@ -728,8 +781,7 @@ int rr_launch_topk_rows(const float* d_scores, int64_t ld, int64_t n, int rows, 
         RR_LAUNCH_CHECK();
         return RR_OK;
     }
-    ChunkPlan plan;
-    if (plan_chunked_topk(n, rows, k, sm_count, &plan)) {
+    if (tree) {
         const int k_pad = max(2, next_pow2(k));
         static RrSmemOptIn optin;
         int dev = 0;

@@ -73,16 +73,91 @@ __device__ void bitonic_desc(unsigned long long* key, unsigned* val, int n_pad) 
     }
 }
 
+// n_pad <= blockDim.x (the default pools of 100 / 150 candidates): rank sort -- every thread counts the keys above its
+// own (equal keys, i.e. the empty slots, by position) and moves its element there: two barriers instead of the 36 steps
+// of the bitonic network, same order for distinct keys
+__device__ void rank_sort_desc(unsigned long long* key, unsigned* val, int n_pad) {
+    const int i = threadIdx.x;
+    unsigned long long mine = 0ull;
+    unsigned v = 0u;
+    int rank = 0;
+    if (i < n_pad) {
+        mine = key[i]; v = val[i];
+#pragma unroll 8
+        for (int j = 0; j < n_pad; ++j) {
+            const unsigned long long o = key[j];
+            rank += (o > mine || (o == mine && j < i)) ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    if (i < n_pad) { key[rank] = mine; val[rank] = v; }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void sort_desc(unsigned long long* key, unsigned* val, int n_pad) {
+    if (n_pad <= (int)blockDim.x) rank_sort_desc(key, val, n_pad);
+    else bitonic_desc(key, val, n_pad);
+}
+
+// Block-wide reduction, result on every thread.  op must be associative and commutative (min / max / or / integer add):
+// the warps' partial results are combined by a second butterfly over aligned groups of 8 lanes (FUSE_THREADS / 32 = 8
+// warps), not by a serial walk.  scratch: >= 8 elements of T in shared memory.
+static_assert(FUSE_THREADS == 256, "block_reduce assumes 8 warps");
 template <class T, class Op>
 __device__ T block_reduce(T v, Op op, T* scratch) {
-    // scratch: >= 32 elements of T in shared memory
     for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
     __syncthreads();
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
     __syncthreads();
-    T r = scratch[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = op(r, scratch[w]);
+    T r = scratch[threadIdx.x & 7];
+    for (int o = 4; o > 0; o >>= 1) r = op(r, __shfl_xor_sync(0xffffffffu, r, o));
     return r;
+}
+
+// min, max and "holds a NaN" of NV float columns over the first P pool entries: one pass, one pair of barriers.
+// scratch_f >= 16 NV floats, scratch_i >= 8 ints.  bad: bit v set when column v holds a NaN.
+template <int NV>
+__device__ void block_minmax(const float* const (&col)[NV], int P, float (&lo)[NV], float (&hi)[NV], int& bad,
+                             float* scratch_f, int* scratch_i) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { lo[v] = INFINITY; hi[v] = -INFINITY; }
+    bad = 0;
+    for (int i = threadIdx.x; i < P; i += FUSE_THREADS) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const float x = col[v][i];
+            if (x != x) bad |= 1 << v;
+            lo[v] = fminf(lo[v], x); hi[v] = fmaxf(hi[v], x);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            lo[v] = fminf(lo[v], __shfl_xor_sync(0xffffffffu, lo[v], o));
+            hi[v] = fmaxf(hi[v], __shfl_xor_sync(0xffffffffu, hi[v], o));
+        }
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        const int w = threadIdx.x >> 5;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { scratch_f[(2 * v) * 8 + w] = lo[v]; scratch_f[(2 * v + 1) * 8 + w] = hi[v]; }
+        scratch_i[w] = bad;
+    }
+    __syncthreads();
+    const int g = threadIdx.x & 7;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { lo[v] = scratch_f[(2 * v) * 8 + g]; hi[v] = scratch_f[(2 * v + 1) * 8 + g]; }
+    bad = scratch_i[g];
+    for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            lo[v] = fminf(lo[v], __shfl_xor_sync(0xffffffffu, lo[v], o));
+            hi[v] = fmaxf(hi[v], __shfl_xor_sync(0xffffffffu, hi[v], o));
+        }
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
 }
 
 // NumPy pairwise-sum leaf enumeration (numpy/core/src/umath/loops_utils.h.src semantics):
@@ -123,7 +198,7 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
     float* s_best = s_final + a.p.pool;
     float* s_gate = s_best + a.p.pool;
     __shared__ double red_d[32];
-    __shared__ float red_f[32];
+    __shared__ float red_f[64];
     __shared__ int red_i[32];
     __shared__ int s_leaf_lo[FUSE_MAX_LEAVES], s_leaf_n[FUSE_MAX_LEAVES];
     __shared__ double s_leaf_r[FUSE_MAX_LEAVES * 8];
@@ -154,7 +229,7 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
     }
     __syncthreads();
     const int n_valid = block_reduce<int>(n_valid_local, [](int x, int y) { return x + y; }, red_i);
-    bitonic_desc(key, val, n_pad_in);
+    sort_desc(key, val, n_pad_in);
     const int P = min(a.p.pool, n_valid);
 
     // ---- 1b. sharded input with local top-m < pool: is the merged pool provably the global pool? -------
@@ -193,50 +268,30 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
         const long long e = a.extras_by_slot ? at(s, 4) : (long long)b * a.p.pool + i;
         s_best[i] = a.best ? a.best[e] : 0.f;
         s_gate[i] = a.gate ? a.gate[e] : 1.0f;
+        // the sorted keys are consumed (1b read key[P - 1] before the barrier above): key[] keeps the global row of every
+        // pool position from here on (val is reused by the second sort)
+        key[i] = (unsigned long long)a.grow[at(s, 8)];
     }
-    __syncthreads();
-    // keep the slot of every pool position (val is reused by the second sort)
-    // -> stash global rows in key[] after the sort is consumed
-    for (int i = tid; i < P; i += FUSE_THREADS) key[i] = (unsigned long long)a.grow[at((int)val[i], 8)];
     __syncthreads();
 
     // ---- 3. min-max of dense and bm25 (float32 semantics) ----------------------------------------
-    float dmm_lo, dmm_div, bmm_lo, bmm_div;
-    bool d_zero, b_zero;
-    {
-        float lo = INFINITY, hi = -INFINITY; int bad = 0;
-        for (int i = tid; i < P; i += FUSE_THREADS) { const float x = s_dense[i]; if (x != x) bad = 1; lo = fminf(lo, x); hi = fmaxf(hi, x); }
-        lo = block_reduce<float>(lo, [](float x, float y) { return fminf(x, y); }, red_f);
-        hi = block_reduce<float>(hi, [](float x, float y) { return fmaxf(x, y); }, red_f);
-        bad = block_reduce<int>(bad, [](int x, int y) { return x | y; }, red_i);
-        const double dl = (double)lo, dh = (double)hi;
-        d_zero = bad || isinf(lo) || isinf(hi) || (dh - dl < 1e-12) || P == 0;
-        dmm_lo = lo; dmm_div = (float)(dh - dl + 1e-12);
-    }
-    {
-        float lo = INFINITY, hi = -INFINITY; int bad = 0;
-        for (int i = tid; i < P; i += FUSE_THREADS) { const float x = s_bm25[i]; if (x != x) bad = 1; lo = fminf(lo, x); hi = fmaxf(hi, x); }
-        lo = block_reduce<float>(lo, [](float x, float y) { return fminf(x, y); }, red_f);
-        hi = block_reduce<float>(hi, [](float x, float y) { return fmaxf(x, y); }, red_f);
-        bad = block_reduce<int>(bad, [](int x, int y) { return x | y; }, red_i);
-        const double dl = (double)lo, dh = (double)hi;
-        b_zero = bad || isinf(lo) || isinf(hi) || (dh - dl < 1e-12) || P == 0;
-        bmm_lo = lo; bmm_div = (float)(dh - dl + 1e-12);
-    }
-
     // raw best-review similarities (pool order) get the same float32 min-max (:294, app/test.py:288)
-    float emm_lo = 0.f, emm_div = 1.f;
-    bool e_zero = false;
+    float dmm_lo, dmm_div, bmm_lo, bmm_div, emm_lo = 0.f, emm_div = 1.f;
+    bool d_zero, b_zero, e_zero = false;
     const bool best_raw = a.best != nullptr && a.p.best_is_raw;
-    if (best_raw) {
-        float lo = INFINITY, hi = -INFINITY; int bad = 0;
-        for (int i = tid; i < P; i += FUSE_THREADS) { const float x = s_best[i]; if (x != x) bad = 1; lo = fminf(lo, x); hi = fmaxf(hi, x); }
-        lo = block_reduce<float>(lo, [](float x, float y) { return fminf(x, y); }, red_f);
-        hi = block_reduce<float>(hi, [](float x, float y) { return fmaxf(x, y); }, red_f);
-        bad = block_reduce<int>(bad, [](int x, int y) { return x | y; }, red_i);
-        const double dl = (double)lo, dh = (double)hi;
-        e_zero = bad || isinf(lo) || isinf(hi) || (dh - dl < 1e-12) || P == 0;
-        emm_lo = lo; emm_div = (float)(dh - dl + 1e-12);
+    {
+        const float* const cols[3] = {s_dense, s_bm25, s_best};
+        float lo[3], hi[3];
+        int bad;
+        block_minmax<3>(cols, P, lo, hi, bad, red_f, red_i);
+        auto finish = [&](int v, float& mm_lo, float& mm_div) -> bool {
+            const double dl = (double)lo[v], dh = (double)hi[v];
+            mm_lo = lo[v]; mm_div = (float)(dh - dl + 1e-12);
+            return ((bad >> v) & 1) || isinf(lo[v]) || isinf(hi[v]) || (dh - dl < 1e-12) || P == 0;
+        };
+        d_zero = finish(0, dmm_lo, dmm_div);
+        b_zero = finish(1, bmm_lo, bmm_div);
+        if (best_raw) e_zero = finish(2, emm_lo, emm_div);
     }
 
     // ---- 4. g = nanmean(avg) over the pool, NumPy pairwise order -----------------------------------
@@ -290,14 +345,32 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
         if (pr != pr) pbad = 1;
         pl = fmin(pl, pr); ph = fmax(ph, pr);
         const double l1 = log1p(n);
+        s_avg[i] = l1;                   // avg is not read again: the blend (6) takes log1p(n) from here
         if (l1 != l1) lbad = 1;
         lmax = fmax(lmax, l1);
     }
-    pl = block_reduce<double>(pl, [](double x, double y) { return fmin(x, y); }, red_d);
-    ph = block_reduce<double>(ph, [](double x, double y) { return fmax(x, y); }, red_d);
-    lmax = block_reduce<double>(lmax, [](double x, double y) { return fmax(x, y); }, red_d);
-    pbad = block_reduce<int>(pbad, [](int x, int y) { return x | y; }, red_i);
-    lbad = block_reduce<int>(lbad, [](int x, int y) { return x | y; }, red_i);
+    {
+        // one combined reduction: min(pl), max(ph), max(lmax), or(pbad | lbad << 1)
+        int flags = pbad | (lbad << 1);
+        for (int o = 16; o > 0; o >>= 1) {
+            pl = fmin(pl, __shfl_xor_sync(0xffffffffu, pl, o));
+            ph = fmax(ph, __shfl_xor_sync(0xffffffffu, ph, o));
+            lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+            flags |= __shfl_xor_sync(0xffffffffu, flags, o);
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) { const int w = tid >> 5; red_d[w] = pl; red_d[8 + w] = ph; red_d[16 + w] = lmax; red_i[w] = flags; }
+        __syncthreads();
+        const int g8 = tid & 7;
+        pl = red_d[g8]; ph = red_d[8 + g8]; lmax = red_d[16 + g8]; flags = red_i[g8];
+        for (int o = 4; o > 0; o >>= 1) {
+            pl = fmin(pl, __shfl_xor_sync(0xffffffffu, pl, o));
+            ph = fmax(ph, __shfl_xor_sync(0xffffffffu, ph, o));
+            lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+            flags |= __shfl_xor_sync(0xffffffffu, flags, o);
+        }
+        pbad = flags & 1; lbad = (flags >> 1) & 1;
+    }
     if (lbad) lmax = nan64();
     const bool p_zero = pbad || isinf(pl) || isinf(ph) || (ph - pl < 1e-12) || P == 0;
     const double p_div = ph - pl + 1e-12;
@@ -314,7 +387,7 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
         const float bm = b_zero ? 0.f : __fdiv_rn(__fsub_rn(s_bm25[i], bmm_lo), bmm_div);
         const float pm = p_zero ? 0.f : (float)__ddiv_rn(__dadd_rn(s_prior[i], -pl), p_div);
         const double n = s_n[i];
-        const double l1 = log1p(n);
+        const double l1 = s_avg[i];      // log1p(n), computed in (5)
         const double vol = __ddiv_rn(l1, vol_div);
         const double prior = __dadd_rn((double)__fmul_rn(pm, 0.7f), __dmul_rn(0.3, vol));
 
@@ -377,7 +450,7 @@ fuse_topk_kernel(const FuseArgs a, int n_pad_in, int n_pad_pool) {
         val[i] = (unsigned)i;
     }
     __syncthreads();
-    bitonic_desc(key, val, n_pad_pool);
+    sort_desc(key, val, n_pad_pool);
     for (int i = tid; i < a.p.k; i += FUSE_THREADS) {
         const long long o = (long long)b * a.p.k + i;
         if (i < P) {

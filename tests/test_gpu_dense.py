@@ -68,8 +68,8 @@ def test_ties_and_duplicates_are_ordered_by_row():
 
 
 @pytest.mark.parametrize("n,d,b,k", [(16_385, 16, 1, 150), (200_000, 16, 1, 150), (200_000, 16, 8, 1024), (150_000, 8, 3, 1),
-                                      (2_500_000, 8, 2, 150),         # three levels: 153 chunks -> 2 -> 1
-                                      (1_200_000, 8, 1, 1000)])       # 74 chunks x 1000 survivors -> 5 -> 1
+                                      (2_500_000, 8, 2, 150),         # three levels: 611 chunks -> 12 -> 1
+                                      (1_200_000, 8, 1, 1000)])       # four levels: 293 chunks x 1000 survivors -> 36 -> 5 -> 1
 def test_topk_tree_equals_the_radix_pipeline(n, d, b, k, monkeypatch):
     """Small batches over long rows select through the shared-memory top-k tree (topk_chunk_kernel); RR_NO_CHUNKED_TOPK=1
     sends the same scores through the radix-select pipeline.  Same rows, same similarities, same order -- also with rows

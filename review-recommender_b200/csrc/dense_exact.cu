@@ -420,7 +420,7 @@ sort_keys_kernel(const unsigned long long* __restrict__ keys, int k_cap, const R
 // ---------------------------------------------------------------------------------------------
 // Short score rows and small batches: top-k inside shared memory instead of the 15-launch radix pipeline above.
 //   n <= 16384 (the single-query shape of the Streamlit app): ONE kernel, one CTA per row (topk_small_kernel);
-//   longer rows, at most TC_MAX_ROWS queries, k <= 1024: a tree of the same step (topk_chunk_kernel) -- every CTA takes a
+//   longer rows, at most TC_MAX_ROWS (32) queries, k <= 1024: a tree of the same step (topk_chunk_kernel) -- every CTA takes a
 //   chunk of <= 4096 scores and keeps its k largest composite keys, the next level does the same over the surviving
 //   keys, the last level (one CTA per row, <= 8192 keys) sorts: 2 launches up to ~220 k rows at k = 150, 3 up to ~12 M.
 // The step: all keys of the chunk go to shared memory, an MSB-first radix select (8-bit digits, shared-memory histogram,
@@ -430,7 +430,7 @@ sort_keys_kernel(const unsigned long long* __restrict__ keys, int k_cap, const R
 // ---------------------------------------------------------------------------------------------
 constexpr int TS_MAX_N = 16384;
 constexpr int TS_THREADS = 1024;         // 32 warps: the select is a chain of short dependent phases, more warps hide their latency
-constexpr int TC_MAX_ROWS = 8;
+constexpr int TC_MAX_ROWS = 32;             // default of RR_TOPK_TREE_MAX_ROWS
 constexpr int TC_MAX_K = 1024;
 
 // The kk largest of the n keys in shared memory -> sel[0, kk) (unordered), sel[kk, k_pad) = 0.  Keys are unique except for
@@ -643,12 +643,14 @@ static int topk_env(const char* name, int dflt, int lo, int hi) {
     return v < lo ? lo : (v > hi ? hi : v);
 }
 
+static int topk_tree_max_rows() { return topk_env("RR_TOPK_TREE_MAX_ROWS", TC_MAX_ROWS, 1, 64); }
+
 static bool plan_chunked_topk(int64_t n, int rows, int k, int sm_count, ChunkPlan* p) {
     // rows up to tree_min_n go through the one-kernel top-k; a level-0 CTA takes at most chunk_max scores, a middle level
     // mid_chunk keys, the last level (one CTA per row) at most final_max keys.  Defaults from the r02 sweep at B = 1
     // (profiles/r02_exact_path_gemv_topk.txt): 4096 / 8192 / 8192 -> 27 us at 100 k rows, 38 us at 1 M (16384 each: 31 / 46)
     const int tree_min_n = topk_env("RR_TOPK_TREE_MIN_N", TS_MAX_N, 1024, TS_MAX_N);
-    if (n <= tree_min_n || rows > TC_MAX_ROWS || k > TC_MAX_K || k < 1 || k >= n || n > (int64_t)1 << 31) return false;
+    if (n <= tree_min_n || rows > topk_tree_max_rows() || k > TC_MAX_K || k < 1 || k >= n || n > (int64_t)1 << 31) return false;
     if (getenv("RR_NO_CHUNKED_TOPK")) return false;
     const int two_k = (2 * k + 1023) / 1024 * 1024;
     const int chunk_max = std::max(two_k, topk_env("RR_TOPK_CHUNK_MAX", 4096, 1024, TS_MAX_N));
@@ -674,7 +676,7 @@ size_t rr_exact_scratch_bytes(int rows, int k, int64_t n, int sm_count) {
     size_t bytes = sizeof(RsRow) * (size_t)rows + sizeof(unsigned) * (size_t)rows * RS_BINS +
                    sizeof(unsigned long long) * (size_t)rows * (size_t)k + 256;
     ChunkPlan p;
-    const int tree_rows = std::min(rows, TC_MAX_ROWS);         // the last slice of a larger batch may take the tree
+    const int tree_rows = std::min(rows, topk_tree_max_rows());   // the last slice of a larger batch may take the tree
     if (plan_chunked_topk(n, tree_rows, k, sm_count, &p)) {
         // two key arrays used alternately: level 0's survivors and level 1's
         const size_t a = (size_t)p.groups[0] * k, b = p.levels > 2 ? (size_t)p.groups[1] * k : 0;

@@ -67,7 +67,7 @@ def test_ties_and_duplicates_are_ordered_by_row():
     ix.close()
 
 
-@pytest.mark.parametrize("n,d,b,k", [(16_385, 16, 1, 150), (200_000, 16, 1, 150), (200_000, 16, 8, 1024), (150_000, 8, 3, 1),
+@pytest.mark.parametrize("n,d,b,k", [(16_385, 16, 1, 150), (200_000, 16, 1, 150), (200_000, 16, 8, 1024), (150_000, 8, 3, 1), (200_000, 16, 20, 150),
                                       (2_500_000, 8, 2, 150),         # three levels: 611 chunks -> 12 -> 1
                                       (1_200_000, 8, 1, 1000)])       # four levels: 293 chunks x 1000 survivors -> 36 -> 5 -> 1
 def test_topk_tree_equals_the_radix_pipeline(n, d, b, k, monkeypatch):

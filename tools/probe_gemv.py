@@ -15,11 +15,12 @@ emb = torch.randn((n, d), device="cuda")
 emb /= emb.norm(dim=1, keepdim=True)
 ix = rr.engine.HybridIndex(emb, device="cuda:0", make_bf16=False)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for b in (1, 2, 4, 8, 16):
+for b in (1, 8, 16, 32, 64):
     q = torch.from_numpy(rr.synth.queries(b, d)).cuda()
     ref = None
-    for label, env in (("default", {}), ("wide gemv", {"RR_GEMV_WIDE": "1"}), ("radix top-k", {"RR_NO_CHUNKED_TOPK": "1"})):
-        for k in ("RR_GEMV_WIDE", "RR_NO_CHUNKED_TOPK"):
+    for label, env in (("default", {}), ("wide gemv", {"RR_GEMV_WIDE": "1"}), ("radix top-k", {"RR_NO_CHUNKED_TOPK": "1"}),
+                       ("tree <= 64 rows", {"RR_TOPK_TREE_MAX_ROWS": "64"})):
+        for k in ("RR_GEMV_WIDE", "RR_NO_CHUNKED_TOPK", "RR_TOPK_TREE_MAX_ROWS"):
             os.environ.pop(k, None)
         os.environ.update(env)
         for _ in range(3):

@@ -78,3 +78,22 @@ def test_synthetic_recipe_is_pinned():
     a = s.embeddings(700, 16, row0=1_999_800)
     b = s.embeddings(400, 16, row0=2_000_000)
     np.testing.assert_array_equal(a[200:600], b)
+
+
+def test_ptr_takes_the_fast_route_and_falls_back():
+    """engine._ptr (on the single-query latency path) returns the address ndarray.ctypes.data would, also for arrays
+    the buffer-protocol route refuses (read-only, empty, non-contiguous), and None for None."""
+    import numpy as np
+    import torch
+    from review_recommender_b200.engine import _ptr
+    a = np.arange(24, dtype=np.float32).reshape(4, 6)
+    ro = a.copy()
+    ro.flags.writeable = False
+    for arr in (a, a[1:], a[:, ::2], ro, np.empty((0, 6), np.float32), np.empty(0, np.int64)):
+        assert _ptr(arr) == arr.ctypes.data
+    t = torch.arange(5)
+    assert _ptr(t) == t.data_ptr()
+    assert _ptr(None) is None
+    import pytest
+    with pytest.raises(TypeError):
+        _ptr([1, 2, 3])

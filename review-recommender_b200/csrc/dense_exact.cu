@@ -11,11 +11,13 @@
 // BLAS sgemv only by fp32 summation order (<= ~1e-7 abs on unit vectors; tolerance 1e-6).
 //
 //  dense_scores_f32_kernel   HBM-bound multi-query GEMV: each warp streams corpus rows with
-//      16-byte loads (2 rows in flight), up to 8 queries per CTA sit in shared memory.
-//      Algorithmic bytes: 4*D per row per group of 8 queries.
-//  radix-select (rs_*)       exact top-k of every score row on 64-bit composite keys
-//      (score desc, row asc): 11/11/10-bit digit histograms, early exit once the pivot bucket
-//      is exactly consumed, then collect + bitonic sort of the k survivors.
+//      16-byte loads (4 rows in flight), the 1 / 2 / 4 / 8 queries of a CTA sit in shared memory
+//      (one instantiation per batch width).  Algorithmic bytes: 4*D per row per group of 8 queries.
+//  row top-k on 64-bit composite keys (score desc, row asc):
+//      topk_small_kernel / topk_chunk_kernel  rows of <= 16384 scores in ONE kernel, longer rows of small
+//      batches in a 2-3 level tree: keys in shared memory, MSB-first 8-bit radix select, rank sort;
+//      radix-select (rs_*)  everything else: 11/11/10-bit digit histograms over global memory, early
+//      exit once the pivot bucket is exactly consumed, then collect + bitonic sort of the k survivors.
 //  rescore_kernel (K3)       exact similarities of a shortlist (one warp per (query, row)).
 #include <cstdlib>
 
